@@ -1,0 +1,307 @@
+#!/usr/bin/env python3
+"""bench.py — particle-steps/s of the FastSLAM 1.0 hot path (BASELINE.json config 3: 65 536 particles x 256 landmarks).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one JSON line on rank 0)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port) on the host cores
+
+A "step" = one fastslam_update (fs1.rs:237-266) over all particles with that step's observation list (~12 of 256
+landmarks in range).  Timing: CUDA events on the engine's own stream around every step, L2 flushed (256 MiB memset)
+before each step so no step runs out of a warm cache; `value` = particles x K / sum of step times.  Inputs (particle
+state, maps) are resident in HBM; the per-step control + observation list (~300 B) rides in the launch parameters.
+`e2e` repeats the K steps through the public API with host buffers and a host read-back of the result every step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PARTICLES = 1 << 16          # per GPU (weak scaling: global = N_PARTICLES * n_gpus)
+SIDE = 16                      # 16 x 16 = 256 landmarks
+BYTES_POSE_WEIGHT = 64         # pose R24+W24, weight R8+W8
+BYTES_PER_OBS = 96             # landmark R48+W48 per (particle, observed landmark)
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled in the background during the measurement."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                                       "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            busy = [s for s in sm if s >= 0.5 * max(sm)] or sm
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_scenario(total_steps):
+    from rust_robotics_b200 import scenarios
+    return scenarios.c3_scenario(steps=total_steps)
+
+
+def obs_arrays(rr, sc):
+    return [rr.FastSlam1._obs(z) for z in sc.obs]
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (oracle port, glibc libm like the Rust reference), all host threads
+# ------------------------------------------------------------------------------------------------
+def cpu_run(sc, n, steps, warmup, threads, t0_step=0):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle
+    L = _oracle.load(libm=True)
+    o = _oracle.OracleFS(L, n, sc.m, seed=42, nth=n / 1.5)
+    L.orc_fs_set_threads(o.h, threads)
+    o.seed_map(sc.start, sc.landmarks)
+    arrs = [o.obs_array(z) for z in sc.obs]
+    import numpy as np
+    u = np.asarray(sc.control, dtype=np.float64)
+    up = u.ctypes.data_as(_oracle.c_dp)
+    for t in range(warmup):
+        L.orc_fs_step(o.h, up, arrs[t0_step + t], len(sc.obs[t0_step + t]))
+    t0 = time.perf_counter()
+    res = 0
+    for t in range(warmup, warmup + steps):
+        res += L.orc_fs_step(o.h, up, arrs[t0_step + t], len(sc.obs[t0_step + t]))
+    dt = time.perf_counter() - t0
+    return dt, res
+
+
+def cpu_baseline(sc, budget_s, max_steps, threads):
+    """bounded sample of the same workload: same map, same observation stream, fewer particles / steps"""
+    n = 4096
+    dt, _ = cpu_run(sc, n, 4, 1, threads)
+    per_step = dt / 4
+    steps = int(max(8, min(max_steps, budget_s / max(per_step, 1e-6))))
+    dt, res = cpu_run(sc, n, steps, 2, threads)
+    return {"value": n * steps / dt, "unit": "particle-steps/s", "cores": threads, "kind": "port",
+            "sample": f"oracle port (C, glibc libm, OpenMP x{threads}) of fs1.rs on {n} of {N_PARTICLES} particles x {sc.m} landmarks, "
+                      f"{steps} steps of the same observation stream, {res} resamples, {dt:.1f} s"}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sc = make_scenario(args.warmup + args.steps + 8)
+    # size the per-step sample so the whole run stays within ~2 minutes
+    n = 1024
+    dt, _ = cpu_run(sc, n, 4, 1, threads)
+    per_ps = dt / (4 * n)
+    budget = 90.0
+    n_fit = budget / (per_ps * (args.steps + args.warmup))
+    n = 256
+    while n * 2 <= min(n_fit, N_PARTICLES):
+        n *= 2
+    dt, res = cpu_run(sc, n, args.steps, args.warmup, threads)
+    value = n * args.steps / dt
+    line = {"impl": "reference", "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(sc, args.gpus),
+            "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": threads, "kind": "port",
+                             "sample": f"oracle port of fs1.rs (C, glibc libm, OpenMP x{threads}); each step = {n} of "
+                                       f"{N_PARTICLES} particles x {sc.m} landmarks, {res} resamples in {args.steps} steps"},
+            "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(sc, n_gpus):
+    return {"workload": "FastSLAM 1.0 (fs1.rs fastslam_update), BASELINE config 3", "particles_per_gpu": N_PARTICLES,
+            "particles": N_PARTICLES * n_gpus, "landmarks": sc.m, "mean_obs_per_step": round(sc.mean_k(), 2),
+            "nth": "particles/1.5", "start": "initialised map (cov 10 I), poses at truth", "seed": 42,
+            "parallelism": f"particle shards x{n_gpus}", "l2": "flushed (256 MiB memset) before every timed step"}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import rust_robotics_b200 as rr
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("gloo", init_method="env://")     # control plane only; the data path uses NCCL inside libpfgpu
+    K, W = args.steps, args.warmup
+    total = W + 3 * K + 4
+    sc = make_scenario(total)
+    arrs = obs_arrays(rr, sc)
+    n_global = N_PARTICLES * world
+    cfg = rr.FsConfig(nth=n_global / 1.5)
+    if world > 1:
+        import numpy as np
+        import torch
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            import ctypes as C
+            buf = C.create_string_buffer(128)
+            rc = rr.load_library().pfgpu_nccl_unique_id(buf)
+            if rc != 0:
+                raise SystemExit(f"pfgpu_nccl_unique_id failed: {rc}")
+            uid = torch.tensor(list(buf.raw), dtype=torch.uint8)
+        dist.broadcast(uid, 0)
+        g = rr.FastSlam1(n_global, sc.m, cfg, seed=42, device=local_rank, shard=(bytes(uid.tolist()), rank, world))
+    else:
+        g = rr.FastSlam1(N_PARTICLES, sc.m, cfg, seed=42, device=local_rank)
+    g.seed_map(sc.start, sc.landmarks)
+
+    def barrier():
+        g.sync()
+        if dist is not None:
+            dist.barrier()
+
+    def maxr(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    step = 0
+    for _ in range(W):                                   # warm-up (untimed)
+        g.fastslam_update(sc.control, sc.obs[step], want_flag=False, obs_array=arrs[step]); step += 1
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+
+    # ---- timed region 1: K steps, L2 flushed before each, one event pair per step ----
+    st0 = g.stats()
+    g.time_main_kernel(True)
+    barrier()
+    first = step
+    for t in range(K):
+        g.flush_l2()
+        g.mark(2 * t)
+        g.fastslam_update(sc.control, sc.obs[step], want_flag=False, obs_array=arrs[step]); step += 1
+        g.mark(2 * t + 1)
+    barrier()
+    step_ms = [g.elapsed_ms(2 * t, 2 * t + 1) for t in range(K)]
+    st1 = g.stats()
+    g.time_main_kernel(False)
+    t_flushed = maxr(sum(step_ms) * 1e-3)
+    launches = st1.kernel_launches - st0.kernel_launches
+    resamples = st1.resamples - st0.resamples
+    kernel_ms = st1.main_kernel_ms_sum / max(st1.main_kernel_count, 1)
+    alg_bytes = sum(N_PARTICLES * (BYTES_POSE_WEIGHT + BYTES_PER_OBS * len(sc.obs[first + t])) for t in range(K)) / K
+
+    # ---- timed region 2: the same K steps' successors back to back, no flush (steady state, informational) ----
+    barrier()
+    g.mark(8000)
+    for t in range(K):
+        g.fastslam_update(sc.control, sc.obs[step], want_flag=False, obs_array=arrs[step]); step += 1
+    g.mark(8001)
+    barrier()
+    t_noflush = maxr(g.elapsed_ms(8000, 8001) * 1e-3)
+
+    # ---- end to end: public API, host buffers in, result read back to the host every step ----
+    barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for t in range(K):
+        z = sc.obs[step]
+        did = g.fastslam_update(sc.control, z, want_flag=True); step += 1          # builds the C array from host data, syncs
+        idx, pose = g.get_best_particle()                                          # D2H of the step's result
+        h2d += 16 + 24 * len(z)
+        d2h += 4 + 8 * 4 + 16 * 296
+    barrier()
+    t_e2e = maxr(time.perf_counter() - t0)
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        threads = os.cpu_count() or 1
+        cpu = cpu_baseline(sc, 12.0, 400, threads) if world == 1 else None
+        line = {"metric": "particle-steps/sec", "value": n_global * K / t_flushed, "unit": "particle-steps/s",
+                "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_flushed / K * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": dict(workload_config(sc, world), resamples_in_timed_steps=int(resamples)),
+                "value_steady_state_no_flush": n_global * K / t_noflush,
+                "e2e": {"value": n_global * K / t_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d / K,
+                        "d2h_bytes_per_step": d2h / K},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "kernel": "fs_step_kernel (predict + per-observation EKF)", "achieved": achieved,
+                             "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": kernel_ms},
+                "clocks": clocks, "serial_fallbacks": int(st1.serial_fallbacks)}
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

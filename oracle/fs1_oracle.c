@@ -72,6 +72,19 @@ void orc_fs_get_state(const orc_fs* f, double* pw, double* lm) {
     if (lm) memcpy(lm, f->lm, f->n * f->m * sizeof(lm_t));
 }
 
+void orc_fs_seed_map(orc_fs* f, const double pose[3], const double* lxy, double sigma, double cov0) {
+    for (size_t i = 0; i < f->n; ++i) {
+        f->x[i] = pose[0]; f->y[i] = pose[1]; f->yaw[i] = pose[2]; f->w[i] = 1.0 / (double)f->n;
+        for (size_t l = 0; l < f->m; ++l) {
+            double z0, z1;
+            pfc_normal_pair(pfc_rng_block(f->seed, PFC_STREAM_INIT_A, 0, (uint64_t)(i * f->m + l)), &z0, &z1);
+            lm_t* q = &f->lm[i * f->m + l];
+            q->x = lxy[2 * l] + sigma * z0; q->y = lxy[2 * l + 1] + sigma * z1;
+            q->c00 = cov0; q->c01 = 0.0; q->c10 = 0.0; q->c11 = cov0;
+        }
+    }
+}
+
 /* normalize_angle fs1.rs:80-89 */
 static inline double normalize_angle(double a) {
     while (a > PFC_PI) a -= 2.0 * PFC_PI;

@@ -88,6 +88,8 @@ void orc_fs_free(orc_fs*);
 /* pose_w: n x 4 (weight, x, y, yaw) AoS; lm: n x m x 6 (x, y, c00, c01, c10, c11) AoS, particle-major */
 void orc_fs_set_state(orc_fs*, const double* pose_w, const double* lm);
 void orc_fs_get_state(const orc_fs*, double* pose_w, double* lm);
+/* twin of pfgpu_fs_seed_map (include/pfgpu.h): initialised map so the EKF branch is live from step 0 */
+void orc_fs_seed_map(orc_fs*, const double pose3[3], const double* landmarks_xy, double sigma, double cov0);
 int  orc_fs_step(orc_fs*, const double u[2], const orc_fs_obs* z, size_t k);  /* fastslam_update fs1.rs:237-266; returns 1 if resampled */
 int  orc_fs_step_with_noise(orc_fs*, const double u[2], const orc_fs_obs* z, size_t k,
                             const double* z0, const double* z1, double r_uniform01);

@@ -1,0 +1,332 @@
+// fs_kernels.cuh — FastSLAM 1.0 device kernels.  Reference: fs1.rs = crates/rust_robotics_slam/src/fastslam1.rs.
+//
+// HBM layout (per shard of n particles, m landmarks), structure of arrays:
+//   px[2][n], py[2][n], pyaw[2][n]     pose columns (ping-pong; device int `cur` selects the live set)
+//   w[n]                               persistent particle weight (fs1.rs:46)
+//   w_raw[n]                           weight after this step's likelihood products, before normalisation
+//   lm[2][m][6][n]                     landmark EKF state: field-major columns x, y, c00, c01, c10, c11 of
+//                                      landmark l are 6 contiguous n-vectors, so one observed landmark is 6
+//                                      fully coalesced column segments for a warp of consecutive particles
+//   cum[n], rcomb[n], idx[n]           exact cumulative weights, exact comb positions, ancestry
+#pragma once
+#include "common.cuh"
+#include "xsum.cuh"
+
+#define FS_NT 128
+#define FS_MAX_OBS 1024
+
+struct FsObsDev { double d, angle; int lm_id; int pad; };
+
+struct FsDev {
+    size_t n = 0, n_global = 0, offset = 0, m = 0;
+    double* px[2] = {nullptr, nullptr};
+    double* py[2] = {nullptr, nullptr};
+    double* pyaw[2] = {nullptr, nullptr};
+    double* lm[2] = {nullptr, nullptr};
+    int* cur = nullptr;
+    double* w = nullptr;
+    double* w_raw = nullptr;
+    double* cum = nullptr;
+    double* rcomb = nullptr;
+    uint32_t* idx = nullptr;
+    double* scal = nullptr;      // [0] S  [1] Q  [2] S2 (resample re-normalisation)  [3] neff  [4] cum total  [5] comb total
+    int* gate = nullptr;
+    FsObsDev* obs = nullptr;     // device copy of this step's observation list
+    double* best_w = nullptr; unsigned long long* best_i = nullptr;   // per-block argmax partials
+    unsigned int* counters = nullptr;   // device: [0] resamples done so far (= Philox call index of the next comb draw)
+};
+
+// Observation lists of up to FS_PARAM_OBS entries travel inside the kernel's launch parameters (no H2D copy).
+#define FS_PARAM_OBS 48
+struct FsObsParam { FsObsDev o[FS_PARAM_OBS]; };
+
+// ping-pong buffer selection by ternary (a runtime index into the by-value parameter struct would force a stack copy)
+__device__ __forceinline__ double* fs_px(const FsDev& d, int c) { return c ? d.px[1] : d.px[0]; }
+__device__ __forceinline__ double* fs_py(const FsDev& d, int c) { return c ? d.py[1] : d.py[0]; }
+__device__ __forceinline__ double* fs_pyaw(const FsDev& d, int c) { return c ? d.pyaw[1] : d.pyaw[0]; }
+__device__ __forceinline__ double* fs_lm(const FsDev& d, int c) { return c ? d.lm[1] : d.lm[0]; }
+__device__ __forceinline__ size_t lm_index(size_t n, size_t l, int f, size_t i) { return (l * 6 + (size_t)f) * n + i; }
+
+// normalize_angle fs1.rs:80-89.  The reference loops without bound (and would spin forever on +-inf); the
+// device caps the loop at 2^22 turns, i.e. |angle| up to ~2.6e7 rad behaves exactly like the reference.
+__device__ __forceinline__ double fs_normalize_angle(double a) {
+    int guard = 0;
+    while (a > PFC_PI && guard < (1 << 22)) { a -= 2.0 * PFC_PI; ++guard; }
+    while (a < -PFC_PI && guard < (1 << 23)) { a += 2.0 * PFC_PI; ++guard; }
+    return a;
+}
+
+struct FsLm { double x, y, c00, c01, c10, c11; };
+
+// update_landmark fs1.rs:140-183 for one (particle, observation) pair; returns the likelihood factor
+// (1.0 when the weight is left untouched).  L is updated in registers; *wrote_cov tells the caller whether
+// the covariance changed (branch A leaves it alone, fs1.rs:144-149).
+__device__ __forceinline__ double fs_update_landmark(FsLm& L, double px, double py, double pyaw, double z0, double z1,
+                                                     double r00, double r11, bool* wrote_cov) {
+    if (L.c00 > 100.0) {                                       // first observation of this landmark
+        double s, c;
+        pfc_sincos(pyaw + z1, &s, &c);
+        L.x = px + z0 * c;
+        L.y = py + z0 * s;
+        *wrote_cov = false;
+        return 1.0;
+    }
+    *wrote_cov = true;
+    // observation_model fs1.rs:92-99
+    double dx = L.x - px, dy = L.y - py;
+    double d2 = dx * dx + dy * dy;
+    double d = sqrt(d2);
+    double zp1 = fs_normalize_angle(pfc_atan2(dy, dx) - pyaw);
+    double y0 = z0 - d, y1 = fs_normalize_angle(z1 - zp1);     // innovation fs1.rs:155
+    // compute_jacobian fs1.rs:102-110
+    double h00 = dx / d, h01 = dy / d, h10 = -dy / d2, h11 = dx / d2;
+    double p00 = L.c00, p01 = L.c01, p10 = L.c10, p11 = L.c11;
+    // S = H P H^T + R  fs1.rs:161
+    double a00 = h00 * p00 + h01 * p10, a01 = h00 * p01 + h01 * p11;
+    double a10 = h10 * p00 + h11 * p10, a11 = h10 * p01 + h11 * p11;
+    double s00 = (a00 * h00 + a01 * h01) + r00;
+    double s01 = (a00 * h10 + a01 * h11) + 0.0;
+    double s10 = (a10 * h00 + a11 * h01) + 0.0;
+    double s11 = (a10 * h10 + a11 * h11) + r11;
+    // try_inverse().unwrap_or(identity) fs1.rs:164
+    double det = s00 * s11 - s10 * s01;
+    double i00, i01, i10, i11;
+    if (det == 0.0) { i00 = 1.0; i01 = 0.0; i10 = 0.0; i11 = 1.0; }
+    else { i00 = s11 / det; i01 = -s01 / det; i10 = -s10 / det; i11 = s00 / det; }
+    // K = P H^T S^-1 fs1.rs:165
+    double b00 = p00 * h00 + p01 * h01, b01 = p00 * h10 + p01 * h11;
+    double b10 = p10 * h00 + p11 * h01, b11 = p10 * h10 + p11 * h11;
+    double k00 = b00 * i00 + b01 * i10, k01 = b00 * i01 + b01 * i11;
+    double k10 = b10 * i00 + b11 * i10, k11 = b10 * i01 + b11 * i11;
+    L.x = L.x + (k00 * y0 + k01 * y1);                         // fs1.rs:168-170
+    L.y = L.y + (k10 * y0 + k11 * y1);
+    // P = (I - K H) P fs1.rs:173-174 (not symmetrised)
+    double m00 = 1.0 - (k00 * h00 + k01 * h10), m01 = 0.0 - (k00 * h01 + k01 * h11);
+    double m10 = 0.0 - (k10 * h00 + k11 * h10), m11 = 1.0 - (k10 * h01 + k11 * h11);
+    L.c00 = m00 * p00 + m01 * p10; L.c01 = m00 * p01 + m01 * p11;
+    L.c10 = m10 * p00 + m11 * p10; L.c11 = m10 * p01 + m11 * p11;
+    // likelihood fs1.rs:177-182
+    double det_s = s00 * s11 - s10 * s01;
+    if (det_s > 0.0) {
+        double t0 = y0 * i00 + y1 * i10, t1 = y0 * i01 + y1 * i11;
+        double mahal = t0 * y0 + t1 * y1;
+        return pfc_exp(-0.5 * mahal) / (2.0 * PFC_PI * sqrt(det_s));
+    }
+    return 1.0;
+}
+
+// fastslam_update fs1.rs:245-256: predict_particle (fs1.rs:123-137) then, per observation in list order,
+// update_landmark.  One thread = one particle; the observation list is staged in shared memory; each
+// observed landmark is 6 coalesced column loads and 2 or 6 column stores.
+template <bool PARAM_OBS>
+__global__ void __launch_bounds__(FS_NT) fs_step_kernel(FsDev d, const __grid_constant__ FsObsParam po, double u0, double u1,
+                                                        double dt, double sq0, double sq1, double r00, double r11,
+                                                        uint64_t seed, uint32_t call, int k_obs) {
+    extern __shared__ FsObsDev s_obs_fs[];
+    for (int j = threadIdx.x; j < k_obs; j += FS_NT) s_obs_fs[j] = PARAM_OBS ? po.o[j] : d.obs[j];
+    __syncthreads();
+    const size_t i = (size_t)blockIdx.x * FS_NT + threadIdx.x;
+    if (i >= d.n) return;
+    const int cur = *d.cur;
+    double* __restrict__ lm = fs_lm(d, cur);
+    double px = fs_px(d, cur)[i], py = fs_py(d, cur)[i], pyaw = fs_pyaw(d, cur)[i];
+    double z0, z1;
+    pfc_normal_pair(pfc_rng_block(seed, PFC_STREAM_FS_PREDICT, call, d.offset + i), &z0, &z1);
+    {   // predict_particle + motion_model fs1.rs:70-77,128-136
+        double un0 = u0 + z0 * sq0;
+        double un1 = u1 + z1 * sq1;
+        double s, c;
+        pfc_sincos(pyaw, &s, &c);
+        double nx = px + un0 * dt * c;
+        double ny = py + un0 * dt * s;
+        double nyaw = fs_normalize_angle(pyaw + un1 * dt);
+        px = nx; py = ny; pyaw = nyaw;
+    }
+    double w = d.w[i];
+    const size_t n = d.n;
+    for (int j = 0; j < k_obs; ++j) {
+        const size_t l = (size_t)s_obs_fs[j].lm_id;
+        const double zd = s_obs_fs[j].d, za = s_obs_fs[j].angle;
+        FsLm L;
+        L.x = lm[lm_index(n, l, 0, i)]; L.y = lm[lm_index(n, l, 1, i)];
+        L.c00 = lm[lm_index(n, l, 2, i)]; L.c01 = lm[lm_index(n, l, 3, i)];
+        L.c10 = lm[lm_index(n, l, 4, i)]; L.c11 = lm[lm_index(n, l, 5, i)];
+        bool wrote_cov;
+        double lik = fs_update_landmark(L, px, py, pyaw, zd, za, r00, r11, &wrote_cov);
+        lm[lm_index(n, l, 0, i)] = L.x; lm[lm_index(n, l, 1, i)] = L.y;
+        if (wrote_cov) {
+            lm[lm_index(n, l, 2, i)] = L.c00; lm[lm_index(n, l, 3, i)] = L.c01;
+            lm[lm_index(n, l, 4, i)] = L.c10; lm[lm_index(n, l, 5, i)] = L.c11;
+            w = w * lik;                                       // fs1.rs:181 (only when det_s > 0: lik == 1.0 otherwise)
+        }
+    }
+    fs_px(d, cur)[i] = px; fs_py(d, cur)[i] = py; fs_pyaw(d, cur)[i] = pyaw;
+    d.w_raw[i] = w;
+}
+
+// normalize_weights fs1.rs:196-203 (no uniform fallback)
+__global__ void __launch_bounds__(256) fs_normalize_kernel(FsDev d) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= d.n) return;
+    const double S = d.scal[0];
+    double x = d.w_raw[i];
+    d.w[i] = S > 0.0 ? x / S : x;
+}
+struct FsValWSq { const double* w; __device__ __forceinline__ double operator()(size_t i) const { double x = w[i]; return x * x; } };
+
+// compute_neff + gate fs1.rs:262-265
+__global__ void fs_gate_kernel(FsDev d, double nth) {
+    double Q = d.scal[1];
+    double neff = Q > 0.0 ? 1.0 / Q : 0.0;
+    d.scal[3] = neff;
+    *d.gate = neff < nth ? 1 : 0;
+}
+
+// resample() re-normalises first (fs1.rs:207): values w_i / S2 (or w_i when S2 == 0) are recomputed on the fly
+struct FsValWNorm2 {
+    const double* w; const double* scal; const int* gate;
+    __device__ __forceinline__ double operator()(size_t i) const { double S2 = scal[2]; double x = w[i]; return S2 > 0.0 ? x / S2 : x; }
+};
+// the comb r, r + 1/n, ... accumulated sequentially (fs1.rs:219-230)
+struct FsValComb { const double* scal; double inv; __device__ __forceinline__ double operator()(size_t i) const { return i == 0 ? scal[6] : inv; } };
+// let r = Uniform::new(0, 1/n).sample(rng)  (fs1.rs:219-220; rand 0.9: u01 * scale + low), drawn once per resample
+__global__ void fs_comb_kernel(FsDev d, uint64_t seed) {
+    if (!*d.gate) return;
+    double inv = 1.0 / (double)d.n_global;
+    double u01 = pfc_u01_52(pfc_blk_u64(pfc_rng_block(seed, PFC_STREAM_FS_RESAMPLE, d.counters[0], 0), 0));
+    d.scal[6] = u01 * (inv - 0.0) + 0.0;
+}
+
+// while r > cum_sum[j+1] && j < n-1 { j += 1 }  (fs1.rs:224-226): r and j are both non-decreasing, so slot t's
+// j is the first j with cum_incl[j] >= r_t, clamped to n-1.
+__global__ void __launch_bounds__(256) fs_search_kernel(FsDev d) {
+    if (!*d.gate) return;
+    const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= d.n) return;
+    const double r = d.rcomb[t];
+    const double* __restrict__ c = d.cum;
+    size_t lo = 0, hi = d.n;
+    while (lo < hi) {
+        size_t mid = lo + ((hi - lo) >> 1);
+        if (c[mid] < r) lo = mid + 1; else hi = mid;
+    }
+    d.idx[t] = (uint32_t)(lo < d.n ? lo : d.n - 1);
+}
+
+// particles[j].clone(): the pose columns and weight (fs1.rs:227-229)
+__global__ void __launch_bounds__(256) fs_gather_pose_kernel(FsDev d) {
+    if (!*d.gate) return;
+    const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= d.n) return;
+    const int cur = *d.cur;
+    const size_t j = d.idx[t];
+    fs_px(d, cur ^ 1)[t] = fs_px(d, cur)[j];
+    fs_py(d, cur ^ 1)[t] = fs_py(d, cur)[j];
+    fs_pyaw(d, cur ^ 1)[t] = fs_pyaw(d, cur)[j];
+    d.w[t] = 1.0 / (double)d.n_global;
+}
+// ... and the whole map: every one of the 6*m landmark columns is gathered through the same (monotone)
+// ancestry.  grid.x = particle chunks, grid.y = column groups of FS_GATHER_ROWS.
+#define FS_GATHER_ROWS 16
+__global__ void __launch_bounds__(256) fs_gather_lm_kernel(FsDev d) {
+    if (!*d.gate) return;
+    const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= d.n) return;
+    const int cur = *d.cur;
+    const double* __restrict__ src = fs_lm(d, cur);
+    double* __restrict__ dst = fs_lm(d, cur ^ 1);
+    const size_t j = d.idx[t];
+    const size_t rows = 6 * d.m;
+    const size_t r0 = (size_t)blockIdx.y * FS_GATHER_ROWS;
+#pragma unroll
+    for (int rr = 0; rr < FS_GATHER_ROWS; ++rr) {
+        size_t row = r0 + rr;
+        if (row < rows) dst[row * d.n + t] = src[row * d.n + j];
+    }
+}
+__global__ void fs_flip_kernel(FsDev d) { if (*d.gate) { *d.cur ^= 1; d.counters[0] += 1; } }
+
+// get_best_particle fs1.rs:269-274: max_by keeps the LAST maximum
+__global__ void __launch_bounds__(256) fs_best_kernel(FsDev d, int nblocks) {
+    __shared__ double sw[256];
+    __shared__ unsigned long long si[256];
+    double bw = -1.0; unsigned long long bi = 0; bool have = false;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < d.n; i += (size_t)nblocks * 256) {
+        double x = d.w[i];
+        if (!have || x >= bw) { bw = x; bi = i; have = true; }
+    }
+    sw[threadIdx.x] = have ? bw : -1.0; si[threadIdx.x] = have ? bi : 0ull;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            double ow = sw[threadIdx.x + o]; unsigned long long oi = si[threadIdx.x + o];
+            if (ow > sw[threadIdx.x] || (ow == sw[threadIdx.x] && oi > si[threadIdx.x])) { sw[threadIdx.x] = ow; si[threadIdx.x] = oi; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { d.best_w[blockIdx.x] = sw[0]; d.best_i[blockIdx.x] = si[0]; }
+}
+
+// AoS <-> SoA converters for upload/download (pose_w: n x 4, lm: n x m x 6 particle-major like Vec<Particle>)
+__global__ void __launch_bounds__(256) fs_unpack_pose_kernel(FsDev d, const double* pose_w) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= d.n) return;
+    const int cur = *d.cur;
+    d.w[i] = pose_w[4 * i]; fs_px(d, cur)[i] = pose_w[4 * i + 1]; fs_py(d, cur)[i] = pose_w[4 * i + 2]; fs_pyaw(d, cur)[i] = pose_w[4 * i + 3];
+}
+__global__ void __launch_bounds__(256) fs_pack_pose_kernel(FsDev d, double* pose_w) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= d.n) return;
+    const int cur = *d.cur;
+    pose_w[4 * i] = d.w[i]; pose_w[4 * i + 1] = fs_px(d, cur)[i]; pose_w[4 * i + 2] = fs_py(d, cur)[i]; pose_w[4 * i + 3] = fs_pyaw(d, cur)[i];
+}
+// chunk of particles [i0, i0+cnt): aos = cnt x m x 6
+__global__ void __launch_bounds__(256) fs_unpack_lm_kernel(FsDev d, const double* aos, size_t i0, size_t cnt) {
+    const size_t e = (size_t)blockIdx.x * 256 + threadIdx.x;      // element index in the AoS chunk
+    const size_t tot = cnt * d.m * 6;
+    if (e >= tot) return;
+    size_t ip = e / (d.m * 6), rem = e % (d.m * 6);
+    size_t l = rem / 6; int f = (int)(rem % 6);
+    fs_lm(d, *d.cur)[lm_index(d.n, l, f, i0 + ip)] = aos[e];
+}
+__global__ void __launch_bounds__(256) fs_pack_lm_kernel(FsDev d, double* aos, size_t i0, size_t cnt) {
+    const size_t e = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const size_t tot = cnt * d.m * 6;
+    if (e >= tot) return;
+    size_t ip = e / (d.m * 6), rem = e % (d.m * 6);
+    size_t l = rem / 6; int f = (int)(rem % 6);
+    aos[e] = fs_lm(d, *d.cur)[lm_index(d.n, l, f, i0 + ip)];
+}
+// create_particles fs1.rs:302-306: Particle::new (fs1.rs:54-62) with Landmark::new (fs1.rs:34-40)
+__global__ void __launch_bounds__(256) fs_init_kernel(FsDev d, double init_weight) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= d.n) return;
+    d.w[i] = init_weight; d.w_raw[i] = init_weight;
+    d.px[0][i] = 0.0; d.py[0][i] = 0.0; d.pyaw[0][i] = 0.0;
+    for (size_t l = 0; l < d.m; ++l) {
+        d.lm[0][lm_index(d.n, l, 0, i)] = 0.0; d.lm[0][lm_index(d.n, l, 1, i)] = 0.0;
+        d.lm[0][lm_index(d.n, l, 2, i)] = 1000.0; d.lm[0][lm_index(d.n, l, 3, i)] = 0.0;
+        d.lm[0][lm_index(d.n, l, 4, i)] = 0.0; d.lm[0][lm_index(d.n, l, 5, i)] = 1000.0;
+    }
+}
+
+// pfgpu_fs_seed_map: initialised map for benchmarks/tests (see include/pfgpu.h)
+__global__ void __launch_bounds__(256) fs_seed_pose_kernel(FsDev d, double x, double y, double yaw) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= d.n) return;
+    const int cur = *d.cur;
+    fs_px(d, cur)[i] = x; fs_py(d, cur)[i] = y; fs_pyaw(d, cur)[i] = yaw;
+    d.w[i] = 1.0 / (double)d.n_global; d.w_raw[i] = d.w[i];
+}
+__global__ void __launch_bounds__(256) fs_seed_lm_kernel(FsDev d, const double* lm_xy, double sigma, double cov0, uint64_t seed) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const size_t l = blockIdx.y;
+    if (i >= d.n) return;
+    double* lm = fs_lm(d, *d.cur);
+    double z0, z1;
+    pfc_normal_pair(pfc_rng_block(seed, PFC_STREAM_INIT_A, 0, (d.offset + i) * d.m + l), &z0, &z1);
+    lm[lm_index(d.n, l, 0, i)] = lm_xy[2 * l] + sigma * z0;
+    lm[lm_index(d.n, l, 1, i)] = lm_xy[2 * l + 1] + sigma * z1;
+    lm[lm_index(d.n, l, 2, i)] = cov0; lm[lm_index(d.n, l, 3, i)] = 0.0;
+    lm[lm_index(d.n, l, 4, i)] = 0.0; lm[lm_index(d.n, l, 5, i)] = cov0;
+}

@@ -1,0 +1,827 @@
+// pfgpu.cu — the C ABI of include/pfgpu.h: handles, step orchestration, upload/download.
+// Single translation unit: nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false (see __graft_entry__.build()).
+#include "common.cuh"
+#include "xsum.cuh"
+#include "pf_kernels.cuh"
+#include "fs_kernels.cuh"
+#include <new>
+#include <vector>
+#include <cmath>
+
+thread_local char g_pfgpu_err[512] = {0};
+
+extern "C" const char* pfgpu_last_error(void) { return g_pfgpu_err; }
+extern "C" const char* pfgpu_strerror(int s) {
+    switch (s) {
+        case PFGPU_OK: return "ok";
+        case PFGPU_ERR_INVALID: return "invalid parameter";
+        case PFGPU_ERR_UNSUPPORTED: return "valid in the reference but not supported by this build";
+        case PFGPU_ERR_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
+        case PFGPU_ERR_CUDA: return "CUDA runtime error (see pfgpu_last_error)";
+        case PFGPU_ERR_NCCL: return "NCCL error (see pfgpu_last_error)";
+        default: return "unknown status";
+    }
+}
+extern "C" int pfgpu_device_count(int* count) {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { *count = 0; snprintf(g_pfgpu_err, sizeof(g_pfgpu_err), "cudaGetDeviceCount: %s", cudaGetErrorString(e)); return PFGPU_ERR_NO_DEVICE; }
+    *count = c;
+    return c > 0 ? PFGPU_OK : PFGPU_ERR_NO_DEVICE;
+}
+
+static bool finite_d(double v) { return std::isfinite(v); }
+
+static int ctx_open(Ctx& ctx, int device) {
+    int count = 0;
+    int rc = pfgpu_device_count(&count);
+    if (rc) return rc;
+    if (device < 0 || device >= count) { snprintf(g_pfgpu_err, sizeof(g_pfgpu_err), "device %d out of range (%d devices)", device, count); return PFGPU_ERR_NO_DEVICE; }
+    PF_CUDA(cudaSetDevice(device));
+    ctx.device = device;
+    PF_CUDA(cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking));
+    int sms = 0;
+    PF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    ctx.num_sms = sms > 0 ? sms : PFGPU_NUM_SMS;
+    return 0;
+}
+
+#define PF_MARK_SLOTS 16384
+struct Marks {
+    std::vector<cudaEvent_t> ev = std::vector<cudaEvent_t>(PF_MARK_SLOTS, nullptr);
+    void* l2buf = nullptr;
+    size_t l2bytes = (size_t)256 << 20;      // > 126 MB L2
+};
+static int marks_mark(Ctx& ctx, Marks& m, int slot) {
+    if (slot < 0 || slot >= PF_MARK_SLOTS) return PFGPU_ERR_INVALID;
+    if (!m.ev[slot]) PF_CUDA(cudaEventCreate(&m.ev[slot]));
+    PF_CUDA(cudaEventRecord(m.ev[slot], ctx.stream));
+    return 0;
+}
+static int marks_elapsed(Marks& m, int a, int b, double* ms) {
+    if (a < 0 || a >= PF_MARK_SLOTS || b < 0 || b >= PF_MARK_SLOTS || !m.ev[a] || !m.ev[b] || !ms) return PFGPU_ERR_INVALID;
+    PF_CUDA(cudaEventSynchronize(m.ev[b]));
+    float f = 0.f;
+    PF_CUDA(cudaEventElapsedTime(&f, m.ev[a], m.ev[b]));
+    *ms = (double)f;
+    return 0;
+}
+static int marks_flush(Ctx& ctx, Marks& m) {
+    if (!m.l2buf) PF_CUDA(cudaMalloc(&m.l2buf, m.l2bytes));
+    PF_CUDA(cudaMemsetAsync(m.l2buf, 0, m.l2bytes, ctx.stream));
+    return 0;
+}
+static void marks_free(Marks& m) {
+    for (auto e : m.ev) if (e) cudaEventDestroy(e);
+    if (m.l2buf) cudaFree(m.l2buf);
+}
+
+struct KernelTimer {
+    bool on = false;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    double ms_sum = 0.0; uint64_t count = 0;
+};
+
+// ====================================================================================================
+// ParticleFilterLocalizer / MonteCarloLocalizer
+// ====================================================================================================
+struct pfgpu_pf {
+    Ctx ctx;
+    pfgpu_pf_config cfg;
+    uint64_t seed = 0;
+    PfDev d;
+    XsWork xs;
+    size_t obs_cap = 0;
+    double* mom15 = nullptr;
+    int mom_blocks = 0;
+    uint32_t n_predict = 0, n_resample = 0;
+    uint64_t steps = 0, resamples_unknown = 0;
+    int world = 1, rank = 0;
+    KernelTimer timer;
+    Marks marks;
+    double* h_pin = nullptr;   // pinned scratch (>= 64 doubles)
+};
+
+extern "C" void pfgpu_pf_default_config(pfgpu_pf_config* c, int mode) {
+    memset(c, 0, sizeof(*c));
+    c->n_particles = 100; c->resample_threshold = 0.5; c->range_noise = 0.2; c->velocity_noise = 2.0;
+    c->yaw_rate_noise = 40.0 * PFC_PI / 180.0; c->dt = 0.1; c->mode = mode;
+    c->max_particles = mode == 1 ? 5000 : 100; c->kld_epsilon = 0.05; c->kld_z = 2.326;
+}
+extern "C" int pfgpu_pf_config_validate(const pfgpu_pf_config* c) {
+    if (!c) return PFGPU_ERR_INVALID;
+    if (c->n_particles == 0) return PFGPU_ERR_INVALID;                                                   // pf.rs:82, mcl.rs:88
+    if (c->mode == 0) {
+        if (!finite_d(c->resample_threshold) || c->resample_threshold < 0.0 || c->resample_threshold > 1.0) return PFGPU_ERR_INVALID;  // pf.rs:87-94
+    } else if (c->mode == 1) {
+        if (c->max_particles < c->n_particles) return PFGPU_ERR_INVALID;                                 // mcl.rs:93-97
+        if (!finite_d(c->kld_epsilon) || c->kld_epsilon <= 0.0) return PFGPU_ERR_INVALID;                // mcl.rs:98-102
+        if (!finite_d(c->kld_z) || c->kld_z <= 0.0) return PFGPU_ERR_INVALID;                            // mcl.rs:103-107
+    } else return PFGPU_ERR_INVALID;
+    if (!finite_d(c->range_noise) || c->range_noise <= 0.0) return PFGPU_ERR_INVALID;                    // pf.rs:95-99
+    if (!finite_d(c->velocity_noise) || c->velocity_noise < 0.0) return PFGPU_ERR_INVALID;               // pf.rs:100-104
+    if (!finite_d(c->yaw_rate_noise) || c->yaw_rate_noise < 0.0) return PFGPU_ERR_INVALID;               // pf.rs:105-109
+    if (!finite_d(c->dt) || c->dt <= 0.0) return PFGPU_ERR_INVALID;                                      // pf.rs:110-114
+    return PFGPU_OK;
+}
+
+__global__ void pf_init_zero_kernel(PfDev d) {
+    const size_t i = (size_t)blockIdx.x * PF_NT + threadIdx.x;
+    if (i >= d.n) return;
+    Pose4 z; z.x = 0.0; z.y = 0.0; z.yaw = 0.0; z.v = 0.0;
+    pose_store(d.pose[0], i, z);
+    d.w[i] = 1.0 / (double)d.n_global;                 // Particle::new pf.rs:35-43
+    d.w_raw[i] = d.w[i];
+}
+// try_with_initial_state pf.rs:181-187 (random::<f64>()*2-1 ...) / mcl.rs:190-196 (random_range(-1.0..1.0) ...)
+__global__ void pf_init_state_kernel(PfDev d, double s0, double s1, double s2, double s3, uint64_t seed, int mode) {
+    const size_t i = (size_t)blockIdx.x * PF_NT + threadIdx.x;
+    if (i >= d.n) return;
+    pfc_u32x4 a = pfc_rng_block(seed, PFC_STREAM_INIT_A, 0, d.offset + i);
+    pfc_u32x4 b = pfc_rng_block(seed, PFC_STREAM_INIT_B, 0, d.offset + i);
+    Pose4 p;
+    if (mode == 0) {
+        p.x = s0 + pfc_u01_53(pfc_blk_u64(a, 0)) * 2.0 - 1.0;
+        p.y = s1 + pfc_u01_53(pfc_blk_u64(a, 1)) * 2.0 - 1.0;
+        p.yaw = s2 + pfc_u01_53(pfc_blk_u64(b, 0)) * 0.5 - 0.25;
+        p.v = s3 + pfc_u01_53(pfc_blk_u64(b, 1)) * 1.0 - 0.5;
+    } else {
+        p.x = s0 + (pfc_u01_52(pfc_blk_u64(a, 0)) * 2.0 + -1.0);
+        p.y = s1 + (pfc_u01_52(pfc_blk_u64(a, 1)) * 2.0 + -1.0);
+        p.yaw = s2 + (pfc_u01_52(pfc_blk_u64(b, 0)) * 0.5 + -0.25);
+        p.v = s3 + (pfc_u01_52(pfc_blk_u64(b, 1)) * 1.0 + -0.5);
+    }
+    pose_store(pf_pose(d, *d.cur), i, p);
+    d.w[i] = 1.0 / (double)d.n_global;
+    d.w_raw[i] = d.w[i];
+}
+__global__ void pf_unpack_kernel(PfDev d, const double* aos5) {
+    const size_t i = (size_t)blockIdx.x * PF_NT + threadIdx.x;
+    if (i >= d.n) return;
+    Pose4 p; p.x = aos5[5 * i]; p.y = aos5[5 * i + 1]; p.yaw = aos5[5 * i + 2]; p.v = aos5[5 * i + 3];
+    pose_store(pf_pose(d, *d.cur), i, p);
+    d.w[i] = aos5[5 * i + 4];
+    d.w_raw[i] = d.w[i];
+}
+__global__ void pf_pack_kernel(PfDev d, double* aos5) {
+    const size_t i = (size_t)blockIdx.x * PF_NT + threadIdx.x;
+    if (i >= d.n) return;
+    Pose4 p;
+    pose_load(pf_pose(d, *d.cur), i, p);
+    aos5[5 * i] = p.x; aos5[5 * i + 1] = p.y; aos5[5 * i + 2] = p.yaw; aos5[5 * i + 3] = p.v; aos5[5 * i + 4] = d.w[i];
+}
+
+static int pf_refresh_cache(pfgpu_pf* h) {      // refresh_cache pf.rs:499-503
+    PF_LAUNCH(h->ctx, pf_moments_kernel, h->mom_blocks, PF_NT, 0, h->d, h->mom_blocks);
+    PF_LAUNCH(h->ctx, pf_moments_reduce_kernel, 1, PF_NT, 0, h->d.partial, h->mom_blocks, h->mom15);
+    PF_LAUNCH(h->ctx, pf_moments_final_kernel, 1, 32, 0, h->d, h->mom15);
+    return 0;
+}
+
+static int pf_alloc(pfgpu_pf* h) {
+    PfDev& d = h->d;
+    const size_t n = d.n;
+    PF_CUDA(cudaMalloc(&d.pose[0], n * sizeof(Pose4)));
+    PF_CUDA(cudaMalloc(&d.pose[1], n * sizeof(Pose4)));
+    PF_CUDA(cudaMalloc(&d.cur, sizeof(int)));
+    PF_CUDA(cudaMemset(d.cur, 0, sizeof(int)));
+    PF_CUDA(cudaMalloc(&d.w_raw, n * sizeof(double)));
+    PF_CUDA(cudaMalloc(&d.w, n * sizeof(double)));
+    PF_CUDA(cudaMalloc(&d.cum, n * sizeof(double)));
+    PF_CUDA(cudaMalloc(&d.idx, n * sizeof(uint32_t)));
+    PF_CUDA(cudaMalloc(&d.scal, 32 * sizeof(double)));
+    PF_CUDA(cudaMemset(d.scal, 0, 32 * sizeof(double)));
+    PF_CUDA(cudaMalloc(&d.gate, sizeof(int)));
+    PF_CUDA(cudaMemset(d.gate, 0, sizeof(int)));
+    PF_CUDA(cudaMalloc(&d.counters, 4 * sizeof(unsigned int)));
+    PF_CUDA(cudaMemset(d.counters, 0, 4 * sizeof(unsigned int)));
+    h->mom_blocks = (int)std::min<size_t>((size_t)h->ctx.num_sms * 4, cdiv_u(n, PF_NT));
+    if (h->mom_blocks < 1) h->mom_blocks = 1;
+    PF_CUDA(cudaMalloc(&d.partial, (size_t)h->mom_blocks * PF_MOM * sizeof(double)));
+    PF_CUDA(cudaMalloc(&h->mom15, PF_MOM * sizeof(double)));
+    h->obs_cap = 1024;
+    PF_CUDA(cudaMalloc(&d.obs, h->obs_cap * 3 * sizeof(double)));
+    PF_CUDA(cudaMallocHost(&h->h_pin, 64 * sizeof(double)));
+    return xs_work_alloc(h->xs, n);
+}
+
+extern "C" int pfgpu_pf_create(const pfgpu_pf_config* cfg, uint64_t seed, int device, pfgpu_pf** out) {
+    if (!out) return PFGPU_ERR_INVALID;
+    *out = nullptr;
+    int rc = pfgpu_pf_config_validate(cfg);
+    if (rc) return rc;
+    if (cfg->mode == 1 && cfg->max_particles != cfg->n_particles) return PFGPU_ERR_UNSUPPORTED;   // KLD-adaptive N: SURVEY.md §8(f) row 3
+    if (cfg->n_particles > 0xFFFFFFFFull) return PFGPU_ERR_UNSUPPORTED;
+    pfgpu_pf* h = new (std::nothrow) pfgpu_pf();
+    if (!h) return PFGPU_ERR_CUDA;
+    rc = ctx_open(h->ctx, device);
+    if (rc) { delete h; return rc; }
+    h->cfg = *cfg; h->seed = seed;
+    h->d.n = h->d.n_global = cfg->n_particles; h->d.offset = 0;
+    rc = pf_alloc(h);
+    if (rc) { pfgpu_pf_destroy(h); return rc; }
+    PF_LAUNCH(h->ctx, pf_init_zero_kernel, cdiv_u(h->d.n, PF_NT), PF_NT, 0, h->d);
+    rc = pf_refresh_cache(h);
+    if (rc) { pfgpu_pf_destroy(h); return rc; }
+    PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+    *out = h;
+    return PFGPU_OK;
+}
+extern "C" int pfgpu_pf_create_sharded(const pfgpu_pf_config*, uint64_t, int, const void*, int, int, pfgpu_pf** out) {
+    if (out) *out = nullptr;
+    return PFGPU_ERR_UNSUPPORTED;
+}
+extern "C" void pfgpu_pf_destroy(pfgpu_pf* h) {
+    if (!h) return;
+    cudaSetDevice(h->ctx.device);
+    if (h->ctx.stream) cudaStreamSynchronize(h->ctx.stream);
+    PfDev& d = h->d;
+    cudaFree(d.pose[0]); cudaFree(d.pose[1]); cudaFree(d.cur); cudaFree(d.w_raw); cudaFree(d.w); cudaFree(d.cum);
+    cudaFree(d.idx); cudaFree(d.scal); cudaFree(d.gate); cudaFree(d.partial); cudaFree(d.obs); cudaFree(h->mom15); cudaFree(d.counters);
+    if (h->h_pin) cudaFreeHost(h->h_pin);
+    marks_free(h->marks);
+    xs_work_free(h->xs);
+    for (auto& p : h->timer.pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    if (h->ctx.stream) cudaStreamDestroy(h->ctx.stream);
+    delete h;
+}
+extern "C" int pfgpu_pf_sync(pfgpu_pf* h) {
+    if (!h) return PFGPU_ERR_INVALID;
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+    return 0;
+}
+extern "C" int pfgpu_pf_init_state(pfgpu_pf* h, const double s[4]) {
+    if (!h || !s) return PFGPU_ERR_INVALID;
+    for (int k = 0; k < 4; ++k) if (!finite_d(s[k])) return PFGPU_ERR_INVALID;     // validate_state pf.rs:505-513
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    PF_LAUNCH(h->ctx, pf_init_state_kernel, cdiv_u(h->d.n, PF_NT), PF_NT, 0, h->d, s[0], s[1], s[2], s[3], h->seed, h->cfg.mode);
+    return pf_refresh_cache(h);
+}
+extern "C" int pfgpu_pf_upload(pfgpu_pf* h, const double* aos5, size_t n) {
+    if (!h || !aos5 || n != h->d.n) return PFGPU_ERR_INVALID;
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    double* tmp = nullptr;
+    PF_CUDA(cudaMalloc(&tmp, n * 5 * sizeof(double)));
+    PF_CUDA(cudaMemcpyAsync(tmp, aos5, n * 5 * sizeof(double), cudaMemcpyHostToDevice, h->ctx.stream));
+    PF_LAUNCH(h->ctx, pf_unpack_kernel, cdiv_u(n, PF_NT), PF_NT, 0, h->d, tmp);
+    int rc = pf_refresh_cache(h);
+    PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+    cudaFree(tmp);
+    return rc;
+}
+extern "C" int pfgpu_pf_download(pfgpu_pf* h, double* aos5, size_t n) {
+    if (!h || !aos5 || n != h->d.n) return PFGPU_ERR_INVALID;
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    double* tmp = nullptr;
+    PF_CUDA(cudaMalloc(&tmp, n * 5 * sizeof(double)));
+    PF_LAUNCH(h->ctx, pf_pack_kernel, cdiv_u(n, PF_NT), PF_NT, 0, h->d, tmp);
+    PF_CUDA(cudaMemcpyAsync(aos5, tmp, n * 5 * sizeof(double), cudaMemcpyDeviceToHost, h->ctx.stream));
+    PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+    cudaFree(tmp);
+    return 0;
+}
+extern "C" int pfgpu_pf_count(pfgpu_pf* h, size_t* nl, size_t* ng) {
+    if (!h) return PFGPU_ERR_INVALID;
+    if (nl) *nl = h->d.n;
+    if (ng) *ng = h->d.n_global;
+    return 0;
+}
+
+static int pf_stage_obs(pfgpu_pf* h, const double* obs3, size_t k) {
+    for (size_t j = 0; j < k; ++j)                                   // validate_observations pf.rs:538-549
+        if (!finite_d(obs3[3 * j]) || !finite_d(obs3[3 * j + 1]) || !finite_d(obs3[3 * j + 2]) || obs3[3 * j] < 0.0)
+            return PFGPU_ERR_INVALID;
+    if (k <= PF_PARAM_OBS) return 0;                                 // short lists ride in the launch parameters
+    if (k > h->obs_cap) {
+        PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+        cudaFree(h->d.obs);
+        h->obs_cap = k * 2;
+        PF_CUDA(cudaMalloc(&h->d.obs, h->obs_cap * 3 * sizeof(double)));
+    }
+    if (k > 0) PF_CUDA(cudaMemcpyAsync(h->d.obs, obs3, k * 3 * sizeof(double), cudaMemcpyHostToDevice, h->ctx.stream));
+    return 0;
+}
+static size_t pf_obs_smem(size_t k) { return (k ? k : 1) * 3 * sizeof(double); }
+
+template <bool P, bool W>
+static int pf_launch_main(pfgpu_pf* h, const double u[2], const double* obs3, size_t k) {
+    size_t smem = W ? pf_obs_smem(k) : 0;
+    const bool param = !W || k <= PF_PARAM_OBS;
+    PfObsParam po;
+    if (W && param) for (size_t j = 0; j < 3 * k; ++j) po.o[j] = obs3[j];
+    if (smem > 48 * 1024) {
+        PF_CUDA(cudaFuncSetAttribute((pf_predict_weight_kernel<P, W, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->timer.on) { PF_CUDA(cudaEventCreate(&e0)); PF_CUDA(cudaEventCreate(&e1)); PF_CUDA(cudaEventRecord(e0, h->ctx.stream)); }
+    if (param)
+        PF_LAUNCH(h->ctx, (pf_predict_weight_kernel<P, W, true>), cdiv_u(h->d.n, PF_NT), PF_NT, smem, h->d, po, u ? u[0] : 0.0, u ? u[1] : 0.0,
+                  h->cfg.velocity_noise, h->cfg.yaw_rate_noise, h->cfg.dt, h->seed, h->n_predict, (int)k, h->cfg.range_noise);
+    else
+        PF_LAUNCH(h->ctx, (pf_predict_weight_kernel<P, W, false>), cdiv_u(h->d.n, PF_NT), PF_NT, smem, h->d, po, u ? u[0] : 0.0, u ? u[1] : 0.0,
+                  h->cfg.velocity_noise, h->cfg.yaw_rate_noise, h->cfg.dt, h->seed, h->n_predict, (int)k, h->cfg.range_noise);
+    if (h->timer.on) { PF_CUDA(cudaEventRecord(e1, h->ctx.stream)); h->timer.pending.push_back({e0, e1}); }
+    return 0;
+}
+// normalize_weights: exact sequential sum of the raw weights, then the division pass
+static int pf_normalize(pfgpu_pf* h) {
+    int rc = xs_total(h->ctx, h->xs, XsValArray{h->d.w_raw}, h->d.n, h->d.n_global, 0.0, h->d.scal + 0);
+    if (rc) return rc;
+    PF_LAUNCH(h->ctx, pf_normalize_kernel, cdiv_u(h->d.n, PF_NT), PF_NT, 0, h->d);
+    return 0;
+}
+static int pf_resample_impl(pfgpu_pf* h) {
+    PfDev& d = h->d;
+    int rc = xs_total(h->ctx, h->xs, PfValWSq{d.w}, d.n, d.n_global, 0.0, d.scal + 1);        // calc_n_eff pf.rs:416-423
+    if (rc) return rc;
+    PF_LAUNCH(h->ctx, pf_gate_kernel, 1, 1, 0, d, h->cfg.resample_threshold, h->cfg.mode);
+    // cumulative weights (pf.rs:448-453), exact; the kernels below are no-ops when the gate is closed
+    h->xs.gate = d.gate;
+    rc = xs_scan(h->ctx, h->xs, XsValArray{d.w}, XsSinkStore{d.cum}, d.n, d.n_global, 0.0, d.scal + 2);
+    h->xs.gate = nullptr;
+    if (rc) return rc;
+    if (h->cfg.mode == 1) PF_LAUNCH(h->ctx, pf_force_last_kernel, 1, 1, 0, d);
+    PF_LAUNCH(h->ctx, pf_search_kernel, cdiv_u(d.n, PF_NT), PF_NT, 0, d, h->seed, h->cfg.mode);
+    PF_LAUNCH(h->ctx, pf_gather_kernel, cdiv_u(d.n, PF_NT), PF_NT, 0, d);
+    PF_LAUNCH(h->ctx, pf_flip_kernel, 1, 1, 0, d);
+    return 0;
+}
+// The resample draw counter (Philox "call" index) advances only when a resample happened; it lives on the
+// device (PfDev::counters[0]) next to the gate, so a step needs no host round trip.
+static int pf_read_gate(pfgpu_pf* h, int* gate) {
+    int* hp = reinterpret_cast<int*>(h->h_pin + 32);
+    PF_CUDA(cudaMemcpyAsync(hp, h->d.gate, sizeof(int), cudaMemcpyDeviceToHost, h->ctx.stream));
+    PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+    *gate = *hp;
+    return 0;
+}
+
+extern "C" int pfgpu_pf_predict(pfgpu_pf* h, const double u[2]) {
+    if (!h || !u) return PFGPU_ERR_INVALID;
+    if (!finite_d(u[0]) || !finite_d(u[1])) return PFGPU_ERR_INVALID;               // validate_control pf.rs:515-523
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    int rc = pf_launch_main<true, false>(h, u, nullptr, 0);
+    if (rc) return rc;
+    h->n_predict++;
+    return pf_refresh_cache(h);                                                      // pf.rs:299
+}
+extern "C" int pfgpu_pf_update(pfgpu_pf* h, const double* obs3, size_t k) {
+    if (!h || (k && !obs3)) return PFGPU_ERR_INVALID;
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    int rc = pf_stage_obs(h, obs3, k);
+    if (rc) return rc;
+    rc = pf_launch_main<false, true>(h, nullptr, obs3, k);
+    if (rc) return rc;
+    rc = pf_normalize(h);                                                            // pf.rs:331
+    if (rc) return rc;
+    return pf_refresh_cache(h);                                                      // pf.rs:332
+}
+extern "C" int pfgpu_pf_resample(pfgpu_pf* h, int* did) {
+    if (!h) return PFGPU_ERR_INVALID;
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    int rc = pf_resample_impl(h);
+    if (rc) return rc;
+    rc = pf_refresh_cache(h);                                                        // pf.rs:343 (same values when the gate was closed)
+    if (rc) return rc;
+    if (did) { int g = 0; rc = pf_read_gate(h, &g); if (rc) return rc; *did = g; }
+    return 0;
+}
+extern "C" int pfgpu_pf_step(pfgpu_pf* h, const double u[2], const double* obs3, size_t k, double est[4]) {
+    if (!h || !u || (k && !obs3)) return PFGPU_ERR_INVALID;
+    if (!finite_d(u[0]) || !finite_d(u[1])) return PFGPU_ERR_INVALID;
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    int rc = pf_stage_obs(h, obs3, k);
+    if (rc) return rc;
+    rc = pf_launch_main<true, true>(h, u, obs3, k);                                  // predict + likelihood, one pass
+    if (rc) return rc;
+    h->n_predict++;
+    rc = pf_normalize(h);
+    if (rc) return rc;
+    rc = pf_resample_impl(h);
+    if (rc) return rc;
+    rc = pf_refresh_cache(h);
+    if (rc) return rc;
+    h->steps++;
+    if (est) {
+        PF_CUDA(cudaMemcpyAsync(h->h_pin, h->d.scal + 4, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->ctx.stream));
+        PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+        for (int a = 0; a < 4; ++a) est[a] = h->h_pin[a];
+    }
+    return 0;
+}
+extern "C" int pfgpu_pf_estimate(pfgpu_pf* h, double est[4], double cov_cm[16]) {
+    if (!h) return PFGPU_ERR_INVALID;
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    PF_CUDA(cudaMemcpyAsync(h->h_pin, h->d.scal + 4, 20 * sizeof(double), cudaMemcpyDeviceToHost, h->ctx.stream));
+    PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+    if (est) for (int a = 0; a < 4; ++a) est[a] = h->h_pin[a];
+    if (cov_cm) for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) cov_cm[b * 4 + a] = h->h_pin[4 + a * 4 + b];
+    return 0;
+}
+extern "C" int pfgpu_pf_neff(pfgpu_pf* h, double* neff) {
+    if (!h || !neff) return PFGPU_ERR_INVALID;
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    int rc = xs_total(h->ctx, h->xs, PfValWSq{h->d.w}, h->d.n, h->d.n_global, 0.0, h->d.scal + 1);
+    if (rc) return rc;
+    PF_CUDA(cudaMemcpyAsync(h->h_pin, h->d.scal + 1, sizeof(double), cudaMemcpyDeviceToHost, h->ctx.stream));
+    PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+    double Q = h->h_pin[0];
+    *neff = Q > 0.0 ? 1.0 / Q : 0.0;
+    return 0;
+}
+extern "C" int pfgpu_pf_set_range_noise(pfgpu_pf* h, double s) {
+    if (!h || !finite_d(s) || s <= 0.0) return PFGPU_ERR_INVALID;                   // pf.rs:228-236
+    h->cfg.range_noise = s;
+    return 0;
+}
+extern "C" int pfgpu_pf_last_indices(pfgpu_pf* h, uint32_t* idx, size_t cap, size_t* n) {
+    if (!h || !idx) return PFGPU_ERR_INVALID;
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    size_t c = cap < h->d.n ? cap : h->d.n;
+    PF_CUDA(cudaMemcpyAsync(idx, h->d.idx, c * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->ctx.stream));
+    PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+    if (n) *n = h->d.n;
+    return 0;
+}
+
+static void timer_drain(KernelTimer& t) {
+    for (auto& p : t.pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) { t.ms_sum += ms; t.count++; }
+        cudaEventDestroy(p.first); cudaEventDestroy(p.second);
+    }
+    t.pending.clear();
+}
+static int read_xs_flags(Ctx& ctx, XsWork& xs, pfgpu_stats* s) {
+    int f[4] = {0, 0, 0, 0};
+    PF_CUDA(cudaMemcpy(f, xs.flags + 4, 4 * sizeof(int), cudaMemcpyDeviceToHost));
+    s->serial_fallbacks = (uint64_t)f[0];
+    s->xsum_dirty_last = (uint64_t)(f[1] < 0 ? 0 : f[1]);
+    (void)ctx;
+    return 0;
+}
+extern "C" int pfgpu_pf_stats(pfgpu_pf* h, pfgpu_stats* s) {
+    if (!h || !s) return PFGPU_ERR_INVALID;
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+    memset(s, 0, sizeof(*s));
+    timer_drain(h->timer);
+    unsigned int cnt = 0;
+    PF_CUDA(cudaMemcpy(&cnt, h->d.counters, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    s->kernel_launches = h->ctx.launches; s->steps = h->steps; s->resamples = cnt;
+    s->main_kernel_ms_sum = h->timer.ms_sum; s->main_kernel_count = h->timer.count;
+    return read_xs_flags(h->ctx, h->xs, s);
+}
+extern "C" int pfgpu_pf_time_main_kernel(pfgpu_pf* h, int on) {
+    if (!h) return PFGPU_ERR_INVALID;
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+    timer_drain(h->timer);
+    h->timer.on = on != 0; h->timer.ms_sum = 0.0; h->timer.count = 0;
+    return 0;
+}
+
+// ====================================================================================================
+// FastSLAM 1.0
+// ====================================================================================================
+struct pfgpu_fs {
+    Ctx ctx;
+    pfgpu_fs_config cfg;
+    uint64_t seed = 0;
+    FsDev d;
+    XsWork xs;
+    size_t obs_cap = 0;
+    int best_blocks = 0;
+    uint32_t n_step = 0, n_resample = 0;
+    uint64_t steps = 0;
+    int world = 1, rank = 0;
+    KernelTimer timer;
+    Marks marks;
+    double* h_pin = nullptr;
+    FsObsDev* h_obs = nullptr;     // pinned staging for the observation list
+    size_t lm_bytes = 0;
+};
+
+extern "C" void pfgpu_fs_default_config(pfgpu_fs_config* c) {            // fs1.rs:13-23
+    c->dt = 0.1; c->max_range = 20.0; c->nth = 100.0 / 1.5; c->q00 = 0.3; c->q11 = 0.0305; c->r00 = 0.5; c->r11 = 0.0305;
+    c->init_weight = 1.0 / 100.0;
+}
+
+extern "C" int pfgpu_fs_create(const pfgpu_fs_config* cfg, size_t n, size_t m, uint64_t seed, int device, pfgpu_fs** out) {
+    if (!out) return PFGPU_ERR_INVALID;
+    *out = nullptr;
+    if (!cfg || n == 0 || n > 0xFFFFFFFFull) return PFGPU_ERR_INVALID;
+    pfgpu_fs* h = new (std::nothrow) pfgpu_fs();
+    if (!h) return PFGPU_ERR_CUDA;
+    int rc = ctx_open(h->ctx, device);
+    if (rc) { delete h; return rc; }
+    h->cfg = *cfg; h->seed = seed;
+    FsDev& d = h->d;
+    d.n = d.n_global = n; d.offset = 0; d.m = m;
+    h->lm_bytes = (m ? m : 1) * 6 * n * sizeof(double);
+    auto fail = [&](int code) { pfgpu_fs_destroy(h); return code; };
+#define FS_TRY(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { snprintf(g_pfgpu_err, sizeof(g_pfgpu_err), "%s -> %s", #x, cudaGetErrorString(e__)); return fail(PFGPU_ERR_CUDA); } } while (0)
+    for (int b = 0; b < 2; ++b) {
+        FS_TRY(cudaMalloc(&d.px[b], n * sizeof(double))); FS_TRY(cudaMalloc(&d.py[b], n * sizeof(double)));
+        FS_TRY(cudaMalloc(&d.pyaw[b], n * sizeof(double))); FS_TRY(cudaMalloc(&d.lm[b], h->lm_bytes));
+    }
+    FS_TRY(cudaMalloc(&d.cur, sizeof(int))); FS_TRY(cudaMemset(d.cur, 0, sizeof(int)));
+    FS_TRY(cudaMalloc(&d.w, n * sizeof(double))); FS_TRY(cudaMalloc(&d.w_raw, n * sizeof(double)));
+    FS_TRY(cudaMalloc(&d.cum, n * sizeof(double))); FS_TRY(cudaMalloc(&d.rcomb, n * sizeof(double)));
+    FS_TRY(cudaMalloc(&d.idx, n * sizeof(uint32_t)));
+    FS_TRY(cudaMalloc(&d.scal, 16 * sizeof(double))); FS_TRY(cudaMemset(d.scal, 0, 16 * sizeof(double)));
+    FS_TRY(cudaMalloc(&d.gate, sizeof(int))); FS_TRY(cudaMemset(d.gate, 0, sizeof(int)));
+    FS_TRY(cudaMalloc(&d.counters, 4 * sizeof(unsigned int))); FS_TRY(cudaMemset(d.counters, 0, 4 * sizeof(unsigned int)));
+    h->obs_cap = FS_MAX_OBS;
+    FS_TRY(cudaMalloc(&d.obs, h->obs_cap * sizeof(FsObsDev)));
+    h->best_blocks = (int)std::min<size_t>((size_t)h->ctx.num_sms * 2, cdiv_u(n, 256));
+    FS_TRY(cudaMalloc(&d.best_w, h->best_blocks * sizeof(double)));
+    FS_TRY(cudaMalloc(&d.best_i, h->best_blocks * sizeof(unsigned long long)));
+    FS_TRY(cudaMallocHost(&h->h_pin, (64 + 2 * (size_t)h->best_blocks) * sizeof(double)));
+    FS_TRY(cudaMallocHost(&h->h_obs, h->obs_cap * sizeof(FsObsDev)));
+#undef FS_TRY
+    rc = xs_work_alloc(h->xs, n);
+    if (rc) return fail(rc);
+    fs_init_kernel<<<cdiv_u(n, 256), 256, 0, h->ctx.stream>>>(d, cfg->init_weight);
+    h->ctx.launches++;
+    if (cudaStreamSynchronize(h->ctx.stream) != cudaSuccess) return fail(PFGPU_ERR_CUDA);
+    *out = h;
+    return PFGPU_OK;
+}
+extern "C" int pfgpu_fs_create_sharded(const pfgpu_fs_config*, size_t, size_t, uint64_t, int, const void*, int, int, pfgpu_fs** out) {
+    if (out) *out = nullptr;
+    return PFGPU_ERR_UNSUPPORTED;
+}
+extern "C" void pfgpu_fs_destroy(pfgpu_fs* h) {
+    if (!h) return;
+    cudaSetDevice(h->ctx.device);
+    if (h->ctx.stream) cudaStreamSynchronize(h->ctx.stream);
+    FsDev& d = h->d;
+    for (int b = 0; b < 2; ++b) { cudaFree(d.px[b]); cudaFree(d.py[b]); cudaFree(d.pyaw[b]); cudaFree(d.lm[b]); }
+    cudaFree(d.cur); cudaFree(d.w); cudaFree(d.w_raw); cudaFree(d.cum); cudaFree(d.rcomb); cudaFree(d.idx); cudaFree(d.scal);
+    cudaFree(d.gate); cudaFree(d.obs); cudaFree(d.best_w); cudaFree(d.best_i); cudaFree(d.counters);
+    if (h->h_pin) cudaFreeHost(h->h_pin);
+    if (h->h_obs) cudaFreeHost(h->h_obs);
+    marks_free(h->marks);
+    xs_work_free(h->xs);
+    for (auto& p : h->timer.pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    if (h->ctx.stream) cudaStreamDestroy(h->ctx.stream);
+    delete h;
+}
+extern "C" int pfgpu_fs_sync(pfgpu_fs* h) {
+    if (!h) return PFGPU_ERR_INVALID;
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+    return 0;
+}
+extern "C" int pfgpu_fs_count(pfgpu_fs* h, size_t* nl, size_t* ng, size_t* m) {
+    if (!h) return PFGPU_ERR_INVALID;
+    if (nl) *nl = h->d.n;
+    if (ng) *ng = h->d.n_global;
+    if (m) *m = h->d.m;
+    return 0;
+}
+static const size_t FS_XFER_CHUNK_BYTES = (size_t)256 << 20;   // staging chunk for AoS<->SoA conversion
+extern "C" int pfgpu_fs_upload(pfgpu_fs* h, const double* pose_w, const double* lm, size_t n) {
+    if (!h || !pose_w || n != h->d.n) return PFGPU_ERR_INVALID;
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    FsDev& d = h->d;
+    double* tmp = nullptr;
+    PF_CUDA(cudaMalloc(&tmp, n * 4 * sizeof(double)));
+    PF_CUDA(cudaMemcpyAsync(tmp, pose_w, n * 4 * sizeof(double), cudaMemcpyHostToDevice, h->ctx.stream));
+    PF_LAUNCH(h->ctx, fs_unpack_pose_kernel, cdiv_u(n, 256), 256, 0, d, tmp);
+    PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+    cudaFree(tmp);
+    if (lm && d.m) {
+        size_t per = d.m * 6 * sizeof(double);
+        size_t chunk = std::max<size_t>(1, FS_XFER_CHUNK_BYTES / per);
+        if (chunk > n) chunk = n;
+        PF_CUDA(cudaMalloc(&tmp, chunk * per));
+        for (size_t i0 = 0; i0 < n; i0 += chunk) {
+            size_t cnt = std::min(chunk, n - i0);
+            PF_CUDA(cudaMemcpyAsync(tmp, lm + i0 * d.m * 6, cnt * per, cudaMemcpyHostToDevice, h->ctx.stream));
+            PF_LAUNCH(h->ctx, fs_unpack_lm_kernel, cdiv_u(cnt * d.m * 6, 256), 256, 0, d, tmp, i0, cnt);
+            PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+        }
+        cudaFree(tmp);
+    }
+    return 0;
+}
+extern "C" int pfgpu_fs_download(pfgpu_fs* h, double* pose_w, double* lm, size_t n) {
+    if (!h || n != h->d.n) return PFGPU_ERR_INVALID;
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    FsDev& d = h->d;
+    double* tmp = nullptr;
+    if (pose_w) {
+        PF_CUDA(cudaMalloc(&tmp, n * 4 * sizeof(double)));
+        PF_LAUNCH(h->ctx, fs_pack_pose_kernel, cdiv_u(n, 256), 256, 0, d, tmp);
+        PF_CUDA(cudaMemcpyAsync(pose_w, tmp, n * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->ctx.stream));
+        PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+        cudaFree(tmp);
+    }
+    if (lm && d.m) {
+        size_t per = d.m * 6 * sizeof(double);
+        size_t chunk = std::max<size_t>(1, FS_XFER_CHUNK_BYTES / per);
+        if (chunk > n) chunk = n;
+        PF_CUDA(cudaMalloc(&tmp, chunk * per));
+        for (size_t i0 = 0; i0 < n; i0 += chunk) {
+            size_t cnt = std::min(chunk, n - i0);
+            PF_LAUNCH(h->ctx, fs_pack_lm_kernel, cdiv_u(cnt * d.m * 6, 256), 256, 0, d, tmp, i0, cnt);
+            PF_CUDA(cudaMemcpyAsync(lm + i0 * d.m * 6, tmp, cnt * per, cudaMemcpyDeviceToHost, h->ctx.stream));
+            PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+        }
+        cudaFree(tmp);
+    }
+    return 0;
+}
+
+extern "C" int pfgpu_fs_seed_map(pfgpu_fs* h, const double pose3[3], const double* lm_xy, size_t m, double sigma, double cov0) {
+    if (!h || !pose3 || (m && !lm_xy) || m != h->d.m) return PFGPU_ERR_INVALID;
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    FsDev& d = h->d;
+    PF_LAUNCH(h->ctx, fs_seed_pose_kernel, cdiv_u(d.n, 256), 256, 0, d, pose3[0], pose3[1], pose3[2]);
+    if (m) {
+        double* dxy = nullptr;
+        PF_CUDA(cudaMalloc(&dxy, m * 2 * sizeof(double)));
+        PF_CUDA(cudaMemcpyAsync(dxy, lm_xy, m * 2 * sizeof(double), cudaMemcpyHostToDevice, h->ctx.stream));
+        dim3 grid(cdiv_u(d.n, 256), (unsigned)m);
+        PF_LAUNCH(h->ctx, fs_seed_lm_kernel, grid, 256, 0, d, dxy, sigma, cov0, h->seed);
+        PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+        cudaFree(dxy);
+    }
+    return 0;
+}
+extern "C" int pfgpu_fs_step(pfgpu_fs* h, const double u[2], const pfgpu_fs_obs* z, size_t k, int* did) {
+    if (!h || !u || (k && !z)) return PFGPU_ERR_INVALID;
+    if (!finite_d(u[0]) || !finite_d(u[1])) return PFGPU_ERR_INVALID;
+    if (k > h->obs_cap) return PFGPU_ERR_UNSUPPORTED;
+    FsDev& d = h->d;
+    for (size_t j = 0; j < k; ++j) {
+        if (!finite_d(z[j].d) || !finite_d(z[j].angle)) return PFGPU_ERR_INVALID;
+        if (z[j].lm_id >= d.m) return PFGPU_ERR_INVALID;             // the reference would panic on the Vec index (fs1.rs:141)
+    }
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    const bool param = k <= FS_PARAM_OBS;
+    FsObsParam po;
+    if (param) {
+        for (size_t j = 0; j < k; ++j) { po.o[j].d = z[j].d; po.o[j].angle = z[j].angle; po.o[j].lm_id = (int)z[j].lm_id; po.o[j].pad = 0; }
+    } else {
+        // long lists go through one pinned staging slot: wait until the previous step's copy has left it
+        PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+        for (size_t j = 0; j < k; ++j) { h->h_obs[j].d = z[j].d; h->h_obs[j].angle = z[j].angle; h->h_obs[j].lm_id = (int)z[j].lm_id; h->h_obs[j].pad = 0; }
+        PF_CUDA(cudaMemcpyAsync(d.obs, h->h_obs, k * sizeof(FsObsDev), cudaMemcpyHostToDevice, h->ctx.stream));
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->timer.on) { PF_CUDA(cudaEventCreate(&e0)); PF_CUDA(cudaEventCreate(&e1)); PF_CUDA(cudaEventRecord(e0, h->ctx.stream)); }
+    if (param)
+        PF_LAUNCH(h->ctx, fs_step_kernel<true>, cdiv_u(d.n, FS_NT), FS_NT, (k ? k : 1) * sizeof(FsObsDev), d, po, u[0], u[1], h->cfg.dt,
+                  sqrt(h->cfg.q00), sqrt(h->cfg.q11), h->cfg.r00, h->cfg.r11, h->seed, h->n_step, (int)k);
+    else
+        PF_LAUNCH(h->ctx, fs_step_kernel<false>, cdiv_u(d.n, FS_NT), FS_NT, (k ? k : 1) * sizeof(FsObsDev), d, po, u[0], u[1], h->cfg.dt,
+                  sqrt(h->cfg.q00), sqrt(h->cfg.q11), h->cfg.r00, h->cfg.r11, h->seed, h->n_step, (int)k);
+    if (h->timer.on) { PF_CUDA(cudaEventRecord(e1, h->ctx.stream)); h->timer.pending.push_back({e0, e1}); }
+    h->n_step++;
+    // normalize_weights fs1.rs:259
+    int rc = xs_total(h->ctx, h->xs, XsValArray{d.w_raw}, d.n, d.n_global, 0.0, d.scal + 0);
+    if (rc) return rc;
+    PF_LAUNCH(h->ctx, fs_normalize_kernel, cdiv_u(d.n, 256), 256, 0, d);
+    // compute_neff fs1.rs:262 and the gate fs1.rs:263
+    rc = xs_total(h->ctx, h->xs, FsValWSq{d.w}, d.n, d.n_global, 0.0, d.scal + 1);
+    if (rc) return rc;
+    PF_LAUNCH(h->ctx, fs_gate_kernel, 1, 1, 0, d, h->cfg.nth);
+    // resample fs1.rs:206-234 (every kernel below returns at once when the gate is closed)
+    h->xs.gate = d.gate;
+    rc = xs_total(h->ctx, h->xs, XsValArray{d.w}, d.n, d.n_global, 0.0, d.scal + 2);                 // fs1.rs:207 re-normalise
+    if (!rc) rc = xs_scan(h->ctx, h->xs, FsValWNorm2{d.w, d.scal, d.gate}, XsSinkStore{d.cum}, d.n, d.n_global, 0.0, d.scal + 4);
+    if (!rc) {
+        PF_LAUNCH(h->ctx, fs_comb_kernel, 1, 1, 0, d, h->seed);      // the single uniform draw fs1.rs:219-220
+        rc = xs_scan(h->ctx, h->xs, FsValComb{d.scal, 1.0 / (double)d.n_global}, XsSinkStore{d.rcomb}, d.n, d.n_global, 0.0, d.scal + 5);
+    }
+    h->xs.gate = nullptr;
+    if (rc) return rc;
+    PF_LAUNCH(h->ctx, fs_search_kernel, cdiv_u(d.n, 256), 256, 0, d);
+    PF_LAUNCH(h->ctx, fs_gather_pose_kernel, cdiv_u(d.n, 256), 256, 0, d);
+    if (d.m) {
+        dim3 grid(cdiv_u(d.n, 256), cdiv_u(6 * d.m, FS_GATHER_ROWS));
+        PF_LAUNCH(h->ctx, fs_gather_lm_kernel, grid, 256, 0, d);
+    }
+    PF_LAUNCH(h->ctx, fs_flip_kernel, 1, 1, 0, d);
+    h->steps++;
+    if (did) {     // the gate and the resample draw counter live on the device; only a caller who asks pays a sync
+        int* hp = reinterpret_cast<int*>(h->h_pin + 32);
+        PF_CUDA(cudaMemcpyAsync(hp, d.gate, sizeof(int), cudaMemcpyDeviceToHost, h->ctx.stream));
+        PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+        *did = *hp;
+    }
+    return 0;
+}
+extern "C" int pfgpu_fs_best(pfgpu_fs* h, size_t* index, double pose_w4[4]) {
+    if (!h) return PFGPU_ERR_INVALID;
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    FsDev& d = h->d;
+    PF_LAUNCH(h->ctx, fs_best_kernel, h->best_blocks, 256, 0, d, h->best_blocks);
+    double* hw = h->h_pin + 64;
+    unsigned long long* hi = reinterpret_cast<unsigned long long*>(h->h_pin + 64 + h->best_blocks);
+    PF_CUDA(cudaMemcpyAsync(hw, d.best_w, h->best_blocks * sizeof(double), cudaMemcpyDeviceToHost, h->ctx.stream));
+    PF_CUDA(cudaMemcpyAsync(hi, d.best_i, h->best_blocks * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->ctx.stream));
+    PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+    size_t bi = 0; double bw = -1.0; bool have = false;
+    for (int b = 0; b < h->best_blocks; ++b)
+        if (!have || hw[b] > bw || (hw[b] == bw && hi[b] > bi)) { bw = hw[b]; bi = (size_t)hi[b]; have = true; }
+    if (index) *index = d.offset + bi;
+    if (pose_w4) {
+        int cur = 0;
+        PF_CUDA(cudaMemcpy(&cur, d.cur, sizeof(int), cudaMemcpyDeviceToHost));
+        pose_w4[0] = bw;
+        PF_CUDA(cudaMemcpy(&pose_w4[1], d.px[cur] + bi, sizeof(double), cudaMemcpyDeviceToHost));
+        PF_CUDA(cudaMemcpy(&pose_w4[2], d.py[cur] + bi, sizeof(double), cudaMemcpyDeviceToHost));
+        PF_CUDA(cudaMemcpy(&pose_w4[3], d.pyaw[cur] + bi, sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+extern "C" int pfgpu_fs_particle_landmarks(pfgpu_fs* h, size_t il, double* lm6) {
+    if (!h || !lm6 || il >= h->d.n) return PFGPU_ERR_INVALID;
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    FsDev& d = h->d;
+    if (!d.m) return 0;
+    double* tmp = nullptr;
+    PF_CUDA(cudaMalloc(&tmp, d.m * 6 * sizeof(double)));
+    PF_LAUNCH(h->ctx, fs_pack_lm_kernel, cdiv_u(d.m * 6, 256), 256, 0, d, tmp, il, (size_t)1);
+    PF_CUDA(cudaMemcpyAsync(lm6, tmp, d.m * 6 * sizeof(double), cudaMemcpyDeviceToHost, h->ctx.stream));
+    PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+    cudaFree(tmp);
+    return 0;
+}
+extern "C" int pfgpu_fs_last_indices(pfgpu_fs* h, uint32_t* idx, size_t cap, size_t* n) {
+    if (!h || !idx) return PFGPU_ERR_INVALID;
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    size_t c = cap < h->d.n ? cap : h->d.n;
+    PF_CUDA(cudaMemcpyAsync(idx, h->d.idx, c * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->ctx.stream));
+    PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+    if (n) *n = h->d.n;
+    return 0;
+}
+extern "C" int pfgpu_fs_last_neff(pfgpu_fs* h, double* neff) {
+    if (!h || !neff) return PFGPU_ERR_INVALID;
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    PF_CUDA(cudaMemcpyAsync(h->h_pin, h->d.scal + 3, sizeof(double), cudaMemcpyDeviceToHost, h->ctx.stream));
+    PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+    *neff = h->h_pin[0];
+    return 0;
+}
+extern "C" int pfgpu_fs_stats(pfgpu_fs* h, pfgpu_stats* s) {
+    if (!h || !s) return PFGPU_ERR_INVALID;
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+    memset(s, 0, sizeof(*s));
+    timer_drain(h->timer);
+    unsigned int cnt = 0;
+    PF_CUDA(cudaMemcpy(&cnt, h->d.counters, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    s->kernel_launches = h->ctx.launches; s->steps = h->steps; s->resamples = cnt;
+    s->main_kernel_ms_sum = h->timer.ms_sum; s->main_kernel_count = h->timer.count;
+    return read_xs_flags(h->ctx, h->xs, s);
+}
+extern "C" int pfgpu_fs_time_main_kernel(pfgpu_fs* h, int on) {
+    if (!h) return PFGPU_ERR_INVALID;
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+    timer_drain(h->timer);
+    h->timer.on = on != 0; h->timer.ms_sum = 0.0; h->timer.count = 0;
+    return 0;
+}
+
+extern "C" int pfgpu_pf_mark(pfgpu_pf* h, int slot) { if (!h) return PFGPU_ERR_INVALID; PF_CUDA(cudaSetDevice(h->ctx.device)); return marks_mark(h->ctx, h->marks, slot); }
+extern "C" int pfgpu_pf_elapsed_ms(pfgpu_pf* h, int a, int b, double* ms) { if (!h) return PFGPU_ERR_INVALID; PF_CUDA(cudaSetDevice(h->ctx.device)); return marks_elapsed(h->marks, a, b, ms); }
+extern "C" int pfgpu_fs_mark(pfgpu_fs* h, int slot) { if (!h) return PFGPU_ERR_INVALID; PF_CUDA(cudaSetDevice(h->ctx.device)); return marks_mark(h->ctx, h->marks, slot); }
+extern "C" int pfgpu_fs_elapsed_ms(pfgpu_fs* h, int a, int b, double* ms) { if (!h) return PFGPU_ERR_INVALID; PF_CUDA(cudaSetDevice(h->ctx.device)); return marks_elapsed(h->marks, a, b, ms); }
+extern "C" int pfgpu_pf_flush_l2(pfgpu_pf* h) { if (!h) return PFGPU_ERR_INVALID; PF_CUDA(cudaSetDevice(h->ctx.device)); return marks_flush(h->ctx, h->marks); }
+extern "C" int pfgpu_fs_flush_l2(pfgpu_fs* h) { if (!h) return PFGPU_ERR_INVALID; PF_CUDA(cudaSetDevice(h->ctx.device)); return marks_flush(h->ctx, h->marks); }
+
+extern "C" int pfgpu_nccl_unique_id(void* out128) { (void)out128; return PFGPU_ERR_UNSUPPORTED; }
+
+// ====================================================================================================
+// test hook: the exact scan on an arbitrary host array (used by tests/test_gpu_xsum.py)
+// ====================================================================================================
+extern "C" int pfgpu_test_xsum(const double* host_v, size_t n, double* host_scan, double* host_total, int* flags4, int device) {
+    Ctx ctx;
+    int rc = ctx_open(ctx, device);
+    if (rc) return rc;
+    XsWork xs;
+    rc = xs_work_alloc(xs, n);
+    if (rc) return rc;
+    double *dv = nullptr, *dc = nullptr, *dt = nullptr;
+    PF_CUDA(cudaMalloc(&dv, n * sizeof(double))); PF_CUDA(cudaMalloc(&dc, n * sizeof(double))); PF_CUDA(cudaMalloc(&dt, sizeof(double)));
+    PF_CUDA(cudaMemcpy(dv, host_v, n * sizeof(double), cudaMemcpyHostToDevice));
+    rc = xs_scan(ctx, xs, XsValArray{dv}, XsSinkStore{dc}, n, n, 0.0, dt);
+    if (rc) return rc;
+    PF_CUDA(cudaStreamSynchronize(ctx.stream));
+    if (host_scan) PF_CUDA(cudaMemcpy(host_scan, dc, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (host_total) PF_CUDA(cudaMemcpy(host_total, dt, sizeof(double), cudaMemcpyDeviceToHost));
+    if (flags4) PF_CUDA(cudaMemcpy(flags4, xs.flags, 4 * sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(dv); cudaFree(dc); cudaFree(dt);
+    xs_work_free(xs);
+    cudaStreamDestroy(ctx.stream);
+    return 0;
+}

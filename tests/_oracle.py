@@ -70,6 +70,7 @@ def load(libm=False):
     L.orc_fs_free.argtypes = [C.c_void_p]
     L.orc_fs_set_state.argtypes = [C.c_void_p, c_dp, c_dp]
     L.orc_fs_get_state.argtypes = [C.c_void_p, c_dp, c_dp]
+    L.orc_fs_seed_map.argtypes = [C.c_void_p, c_dp, c_dp, C.c_double, C.c_double]
     L.orc_fs_step.argtypes = [C.c_void_p, c_dp, C.POINTER(FsObs), C.c_size_t]
     L.orc_fs_step_with_noise.argtypes = [C.c_void_p, c_dp, C.POINTER(FsObs), C.c_size_t, c_dp, c_dp, C.c_double]
     L.orc_fs_best.restype = C.c_size_t
@@ -194,6 +195,10 @@ class OracleFS:
         else:
             l = f64(lm)
             self.L.orc_fs_set_state(self.h, _dp(p), _dp(l))
+
+    def seed_map(self, pose3, landmarks_xy, sigma=1.0, cov0=10.0):
+        p, l = f64(pose3), f64(landmarks_xy)
+        self.L.orc_fs_seed_map(self.h, _dp(p), _dp(l), float(sigma), float(cov0))
 
     def state(self):
         p = np.empty((self.n, 4))

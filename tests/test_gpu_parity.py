@@ -1,0 +1,353 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Bar (BASELINE.json north_star): resample indices bit-exact; pose / weight / covariance within 1e-6 relative.
+Because kernels and oracle share include/pf_contract_math.h and the device reproduces the reference's
+sequential f64 sums exactly (xsum), particles, weights, landmarks and indices are in fact compared for
+BIT EQUALITY; only estimate/covariance (tree-order sums on the device) use the 1e-6 tolerance.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import rust_robotics_b200 as rr
+from rust_robotics_b200 import scenarios
+from _oracle import OracleFS, OraclePF
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6   # north_star tolerance for floating-point summaries
+
+
+def assert_cov_close(got, want, what=""):
+    got, want = np.asarray(got).reshape(4, 4), np.asarray(want).reshape(4, 4)
+    scale = np.sqrt(np.abs(np.outer(np.diag(want), np.diag(want)))) + 1e-300
+    assert np.max(np.abs(got - want) / scale) < RTOL, f"covariance {what}: {np.max(np.abs(got - want) / scale)}"
+
+
+# ------------------------------------------------------------------------------------------------
+# exact scan primitive
+# ------------------------------------------------------------------------------------------------
+def _xsum_cases():
+    rng = np.random.default_rng(3)
+    yield "uniform_65536", np.full(65536, 1.0 / 65536)
+    yield "uniform_non_pow2", np.full(100003, 1.0 / 100003)
+    w = rng.uniform(size=1 << 20); yield "random_1M", w / w.sum()
+    w = np.exp(rng.normal(0, 12, 300000)); yield "lognormal_wide", w / w.sum()
+    w = np.exp(rng.normal(0, 40, 300000)); yield "collapse", w / w.sum()
+    w = np.full(50000, 2.0 ** -54); w[0] = 1.0; yield "ties", w
+    w = np.full(50000, 2.0 ** -60); w[0] = 1.0 - 2.0 ** -40; yield "crawl_edge", w
+    w = np.zeros(70000); w[35000:] = rng.uniform(size=35000); yield "leading_zeros", w
+    yield "all_zero", np.zeros(5000)
+    yield "subnormal", rng.uniform(size=30000) * 1e-310
+    yield "comb", np.concatenate([[0.37 / 65536], np.full(65535, 1.0 / 65536)])
+    yield "single", np.array([0.7])
+    yield "tiny_n", rng.uniform(size=17)
+    w = rng.uniform(size=4097); yield "tile_plus_one", w
+
+
+@pytest.mark.parametrize("name,v", list(_xsum_cases()), ids=[c[0] for c in _xsum_cases()])
+def test_xsum_device_bit_exact(name, v):
+    L = rr.load_library()
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    out = np.empty_like(v)
+    tot = C.c_double()
+    flags = (C.c_int * 4)()
+    rc = L.pfgpu_test_xsum(v.ctypes.data_as(rr.api.c_dp), v.size, out.ctypes.data_as(rr.api.c_dp), C.byref(tot), flags, 0)
+    assert rc == 0, L.pfgpu_last_error()
+    ref = np.add.accumulate(v)          # strictly sequential left-to-right accumulation
+    assert flags[0] == 0, "unexpected serial fallback"
+    assert flags[2] == 0, "emit-time certificate failure"
+    assert np.array_equal(out, ref), f"{name}: first diff at {np.flatnonzero(out != ref)[:5]}"
+    assert tot.value == ref[-1]
+
+
+def test_xsum_device_serial_fallback_on_bad_values():
+    L = rr.load_library()
+    v = np.random.default_rng(1).uniform(size=10000)
+    v[1234] = np.nan
+    out = np.empty_like(v)
+    tot = C.c_double()
+    flags = (C.c_int * 4)()
+    assert L.pfgpu_test_xsum(v.ctypes.data_as(rr.api.c_dp), v.size, out.ctypes.data_as(rr.api.c_dp), C.byref(tot), flags, 0) == 0
+    ref = np.add.accumulate(v)
+    assert flags[0] == 1
+    assert np.array_equal(out[:1234], ref[:1234]) and np.isnan(out[1234:]).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# ParticleFilterLocalizer / MonteCarloLocalizer
+# ------------------------------------------------------------------------------------------------
+def _pf_pair(oracle, n, thr=0.5, sigma=0.25, sv=2.0, sw=np.deg2rad(40.0), mode=0, seed=42, init=(5.0, 5.0, 0.0, 0.0)):
+    if mode == 0:
+        g = rr.ParticleFilterLocalizer.try_with_initial_state(
+            init, rr.ParticleFilterConfig(n, thr, sigma, sv, sw, 0.1), seed=seed)
+    else:
+        g = rr.MonteCarloLocalizer.try_with_initial_state(
+            init, rr.MonteCarloLocalizationConfig(n, n, 0.05, 2.326, sigma, sv, sw, 0.1), seed=seed)
+    o = OraclePF(oracle, n, threshold=thr, range_noise=sigma, velocity_noise=sv, yaw_rate_noise=sw, dt=0.1, seed=seed,
+                 mode=mode, max_particles=n)
+    o.L.orc_pf_set_fast_search(o.h, 1)
+    o.init_state(init)
+    return g, o
+
+
+def _pf_compare(g, o, what):
+    gp, op = g.get_particles(), o.particles()
+    assert np.array_equal(gp, op), f"{what}: particles differ at rows {np.flatnonzero((gp != op).any(axis=1))[:5]}"
+    ge, (oe, oc) = g.estimate(), o.estimate()
+    np.testing.assert_allclose(ge, oe, rtol=RTOL, atol=1e-9, err_msg=what)
+    assert_cov_close(g.calc_covariance().T.ravel(), oc, what)      # both column-major
+
+
+@pytest.mark.parametrize("n,thr,steps", [(1000, 0.5, 300), (1000, 1.0, 40), (4099, 0.5, 60), (65536, 0.5, 25), (1 << 18, 1.0, 6)])
+def test_pf_trajectory_bit_exact(oracle, n, thr, steps):
+    """C1 scenario (render_gif_particle_filter.rs:21-79) at several particle counts."""
+    sc = scenarios.PfScenario("c1", steps=steps)
+    g, o = _pf_pair(oracle, n, thr=thr)
+    _pf_compare(g, o, "init")
+    resamples = 0
+    for t in range(steps):
+        ge = g.try_step(sc.controls[t], sc.obs[t])
+        oe, did = o.step(sc.controls[t], sc.obs[t])
+        np.testing.assert_allclose(ge, oe, rtol=RTOL, atol=1e-9)
+        if did:
+            resamples += 1
+            assert np.array_equal(g.last_indices(), o.last_indices()), f"step {t}: resample indices"
+        if t % 10 == 0 or t == steps - 1:
+            _pf_compare(g, o, f"step {t}")
+    assert g.stats().resamples == resamples
+    assert resamples > 0
+    assert g.stats().serial_fallbacks == 0
+    # the reference's own assertions: finite estimate, sum w = 1 (pf.rs:621-635)
+    assert np.all(np.isfinite(g.estimate())) and abs(g.get_particles()[:, 4].sum() - 1.0) < 1e-3
+
+
+def test_pf_phase_api_matches_oracle(oracle):
+    """predict / update / resample called one by one (the StateEstimator route pf.rs:552-573): caches after each phase."""
+    sc = scenarios.PfScenario("c1", steps=12)
+    g, o = _pf_pair(oracle, 2048, thr=0.9)
+    for t in range(12):
+        g.try_predict_with_control(sc.controls[t]); o.predict(sc.controls[t])
+        _pf_compare(g, o, f"predict {t}")
+        g.try_update_with_observations(sc.obs[t]); o.update(sc.obs[t])
+        _pf_compare(g, o, f"update {t}")
+        assert g.n_eff() == o.neff()
+        assert g.resample() == bool(o.resample())
+        _pf_compare(g, o, f"resample {t}")
+
+
+def test_pf_edge_cases(oracle):
+    g, o = _pf_pair(oracle, 500)
+    # empty observation list (proptest_filters.rs:79-88): weight exactly 1 -> uniform -> no resample
+    for _ in range(5):
+        g.try_step([1.0, 0.5], np.zeros((0, 3))); o.step([1.0, 0.5], np.zeros((0, 3)))
+    _pf_compare(g, o, "empty obs")
+    assert g.stats().resamples == 0
+    # every likelihood underflows -> sum_w == 0 -> uniform fallback (pf.rs:433-438)
+    far = [[1.0e4, 0.0, 0.0], [1.0e4, 5.0, 5.0]]
+    g.try_step([1.0, 0.0], far); o.step([1.0, 0.0], far)
+    _pf_compare(g, o, "underflow")
+    assert np.all(g.get_particles()[:, 4] == 1.0 / 500)
+    # zero process noise (no draw at all when sigma == 0: pf.rs:259-276)
+    g2, o2 = _pf_pair(oracle, 300, sv=0.0, sw=0.0)
+    sc = scenarios.PfScenario("c1", steps=8)
+    for t in range(8):
+        g2.try_step(sc.controls[t], sc.obs[t]); o2.step(sc.controls[t], sc.obs[t])
+    _pf_compare(g2, o2, "zero noise")
+    # validation (pf.rs:515-549, 81-117)
+    with pytest.raises(rr.InvalidParameter):
+        g.try_step([np.nan, 0.0], far)
+    with pytest.raises(rr.InvalidParameter):
+        g.try_step([1.0, 0.0], [[-1.0, 0.0, 0.0]])
+    with pytest.raises(rr.InvalidParameter):
+        rr.ParticleFilterLocalizer(rr.ParticleFilterConfig(n_particles=0))
+    with pytest.raises(rr.InvalidParameter):
+        rr.ParticleFilterLocalizer(rr.ParticleFilterConfig(range_noise=0.0))
+    with pytest.raises(rr.InvalidParameter):
+        g.set_range_noise(-1.0)
+
+
+@pytest.mark.parametrize("n,k", [(4096, 4), (1 << 16, 360)])
+def test_mcl_fixed_n_bit_exact(oracle, n, k):
+    """MonteCarloLocalizer with min == max (BASELINE config 2 shape): resamples every step, last cumsum forced to 1."""
+    sc = scenarios.PfScenario("c2", steps=10)
+    g, o = _pf_pair(oracle, n, sigma=0.25, sv=0.05, sw=0.02, mode=1, init=(0.0, 0.0, 0.0, 1.0))
+    for t in range(10):
+        obs = sc.obs[t][:: 360 // k][:k]
+        ge = g.try_step(sc.controls[t], obs)
+        oe, _ = o.step(sc.controls[t], obs)
+        assert np.array_equal(g.last_indices(), o.last_indices()), f"step {t}"
+        np.testing.assert_allclose(ge, oe, rtol=RTOL, atol=1e-9)
+    _pf_compare(g, o, "mcl end")
+    assert g.particle_count() == n and g.stats().resamples == 10
+
+
+def test_mcl_converges_like_reference_test():
+    """mcl.rs:473-515: 60 steps, estimate within 1.0 m of the truth."""
+    g = rr.MonteCarloLocalizer.try_with_initial_state(
+        [0.0, 0.0, 0.0, 1.0], rr.MonteCarloLocalizationConfig(300, 300, 0.05, 2.326, 0.25, 0.05, 0.02, 0.1))
+    lms = [(10.0, 0.0), (0.0, 10.0), (-10.0, 0.0), (0.0, -10.0)]
+    x = np.zeros(3)
+    for _ in range(60):
+        x[0] += np.cos(x[2]) * 0.1; x[1] += np.sin(x[2]) * 0.1; x[2] += 0.03 * 0.1
+        est = g.try_step([1.0, 0.03], [[np.hypot(x[0] - lx, x[1] - ly), lx, ly] for lx, ly in lms])
+    assert np.hypot(est[0] - x[0], est[1] - x[1]) < 1.0
+
+
+def test_mcl_adaptive_is_reported_unsupported():
+    with pytest.raises(rr.InvalidParameter):
+        rr.MonteCarloLocalizer(rr.MonteCarloLocalizationConfig(100, 5000))
+
+
+# ------------------------------------------------------------------------------------------------
+# FastSLAM 1.0
+# ------------------------------------------------------------------------------------------------
+def _fs_compare(g, o, what, landmarks=True):
+    gp, gl = g.state(landmarks)
+    op, ol = o.state()
+    assert np.array_equal(gp, op), f"{what}: pose/weight rows {np.flatnonzero((gp != op).any(axis=1))[:5]}"
+    if landmarks:
+        assert np.array_equal(gl, ol), f"{what}: landmarks differ for particles {np.flatnonzero((gl != ol).any(axis=(1, 2)))[:5]}"
+
+
+@pytest.mark.parametrize("n,side,steps", [(64, 4, 30), (1000, 6, 25), (4096, 8, 20), (1 << 16, 16, 4)])
+def test_fastslam_trajectory_bit_exact(oracle, n, side, steps):
+    """C3-shaped runs (initialised map, nth = n/1.5): pose, weights, every landmark EKF state and the resample
+    ancestry equal the oracle's bit for bit."""
+    sc = scenarios.FastSlamScenario(side, (10.0 * side / 2 - 5.0, 10.0 * side / 2 - 5.0, 0.0), (1.0, 0.025), steps)
+    cfg = rr.FsConfig(nth=n / 1.5)
+    g = rr.FastSlam1(n, sc.m, cfg, seed=7)
+    o = OracleFS(oracle, n, sc.m, seed=7, nth=n / 1.5)
+    g.seed_map(sc.start, sc.landmarks); o.seed_map(sc.start, sc.landmarks)
+    _fs_compare(g, o, "seed")
+    resamples = 0
+    for t in range(steps):
+        did = g.fastslam_update(sc.control, sc.obs[t])
+        odid = o.step(sc.control, sc.obs[t])
+        assert did == bool(odid), f"step {t}: gate (neff gpu {g.last_neff()} oracle {o.last_neff()})"
+        assert g.last_neff() == o.last_neff()
+        if did:
+            resamples += 1
+            idx = g.last_indices()
+            assert np.array_equal(idx, o.last_indices()), f"step {t}: indices"
+            assert np.all(np.diff(idx.astype(np.int64)) >= 0)          # systematic resampling is monotone
+        if n <= 4096 or t == steps - 1:
+            _fs_compare(g, o, f"step {t}")
+        bi, bp = g.get_best_particle()
+        assert bi == o.best()
+    assert resamples > 0, "scenario never resampled"
+    assert g.stats().serial_fallbacks == 0
+
+
+def test_fastslam_reference_constants_and_fresh_particles(oracle):
+    """create_particles as shipped (fs1.rs:302-306, tests fs1.rs:362-398): cov stays 1000 I, weights untouched (App. B.3),
+    NTH = 66.67 so 20 particles resample every step."""
+    g = rr.FastSlam1(20, 3, seed=3)
+    o = OracleFS(oracle, 20, 3, seed=3)
+    p, l = g.state()
+    assert np.all(p[:, 0] == 0.01) and np.all(p[:, 1:] == 0.0)
+    assert np.all(l[:, :, 2] == 1000.0) and np.all(l[:, :, 5] == 1000.0) and np.all(l[:, :, :2] == 0.0)
+    lms = [(10.0, 0.0), (0.0, 10.0), (10.0, 10.0)]
+    rng = np.random.default_rng(0)
+    for t in range(5):
+        z = scenarios.get_observations([0.0, 0.0, 0.0], lms, rng)
+        assert g.fastslam_update([1.0, 0.1], z) == bool(o.step([1.0, 0.1], z))
+        _fs_compare(g, o, f"fresh {t}")
+    p, l = g.state()
+    assert p.shape[0] == 20 and np.all(l[:, :, 2] == 1000.0)
+
+
+def test_fastslam_edge_cases(oracle):
+    n, m = 256, 4
+    lm_xy = np.array([[5.0, 0.0], [0.0, 5.0], [5.0, 5.0], [-5.0, 2.0]])
+    g = rr.FastSlam1(n, m, rr.FsConfig(nth=n / 1.5), seed=11)
+    o = OracleFS(oracle, n, m, seed=11, nth=n / 1.5)
+    g.seed_map([0.0, 0.0, 0.0], lm_xy); o.seed_map([0.0, 0.0, 0.0], lm_xy)
+    # duplicate lm_id in one observation list: sequential EKF updates of the same landmark (App. A8)
+    z = [(5.1, 0.02, 0), (5.0, 1.55, 1), (4.9, -0.01, 0)]
+    assert g.fastslam_update([1.0, 0.1], z) == bool(o.step([1.0, 0.1], z))
+    _fs_compare(g, o, "duplicate ids")
+    # empty observation list
+    assert g.fastslam_update([1.0, 0.1], []) == bool(o.step([1.0, 0.1], []))
+    _fs_compare(g, o, "empty obs")
+    # all-zero weights: no normalisation, neff = 0 -> resample -> every slot clones particle n-1 (App. B.6)
+    p, l = g.state()
+    p[:, 0] = 0.0
+    g.set_state(p, l); o.set_state(p, l)
+    assert g.fastslam_update([1.0, 0.1], z[:2]) is True
+    assert o.step([1.0, 0.1], z[:2]) == 1
+    assert np.all(g.last_indices() == n - 1)
+    _fs_compare(g, o, "zero weights")
+    # mixed fresh (cov 1000) and initialised landmarks through upload
+    p, l = g.state()
+    l[:, 2, :] = [0.0, 0.0, 1000.0, 0.0, 0.0, 1000.0]
+    g.set_state(p, l); o.set_state(p, l)
+    z = [(7.0, 0.8, 2), (5.0, 0.1, 0)]
+    assert g.fastslam_update([1.0, 0.0], z) == bool(o.step([1.0, 0.0], z))
+    _fs_compare(g, o, "mixed fresh")
+    # validation: lm_id out of range (the reference would panic on the Vec index), non-finite control
+    with pytest.raises(rr.InvalidParameter):
+        g.fastslam_update([1.0, 0.0], [(1.0, 0.0, 99)])
+    with pytest.raises(rr.InvalidParameter):
+        g.fastslam_update([np.inf, 0.0], [])
+
+
+def test_fastslam_long_observation_list_uses_memcpy_path(oracle):
+    n, side = 512, 8
+    sc = scenarios.FastSlamScenario(side, (35.0, 35.0, 0.0), (1.0, 0.025), 3, max_range=60.0)   # sees all 64 landmarks
+    assert len(sc.obs[0]) > 48
+    g = rr.FastSlam1(n, sc.m, rr.FsConfig(nth=n / 1.5), seed=5)
+    o = OracleFS(oracle, n, sc.m, seed=5, nth=n / 1.5)
+    g.seed_map(sc.start, sc.landmarks); o.seed_map(sc.start, sc.landmarks)
+    for t in range(3):
+        assert g.fastslam_update(sc.control, sc.obs[t]) == bool(o.step(sc.control, sc.obs[t]))
+    _fs_compare(g, o, "long list")
+
+
+def test_fastslam_full_size_properties():
+    """BASELINE config 3 at full size (65 536 x 256): size-independent properties over a short run."""
+    n = 1 << 16
+    sc = scenarios.c3_scenario(steps=12)
+    g = rr.FastSlam1(n, sc.m, rr.FsConfig(nth=n / 1.5), seed=42)
+    g.seed_map(sc.start, sc.landmarks)
+    resampled = 0
+    for t in range(12):
+        before = g.state(landmarks=False)[0]
+        did = g.fastslam_update(sc.control, sc.obs[t])
+        p = g.state(landmarks=False)[0]
+        assert np.all(np.isfinite(p)) and np.all(p[:, 0] >= 0.0)
+        assert abs(p[:, 0].sum() - 1.0) < 1e-9                      # normalised
+        assert np.all(np.abs(p[:, 3]) <= np.pi + 1e-12)             # yaw wrapped every step (fs1.rs:75)
+        if did:
+            resampled += 1
+            idx = g.last_indices().astype(np.int64)
+            assert np.all(np.diff(idx) >= 0) and idx.min() >= 0 and idx.max() < n
+            assert np.all(p[:, 0] == 1.0 / n)                       # fs1.rs:228
+            # gather check on a sample: the clone carries its ancestor's whole map
+            for slot in (0, n // 3, n - 1):
+                a = g.particle_landmarks(slot)
+                assert np.all(np.isfinite(a))
+        else:
+            assert 1.0 / np.sum(p[:, 0] ** 2) >= n / 1.5 - 1e-6
+    assert resampled > 0
+    # determinism: same seed, same inputs -> identical state
+    g2 = rr.FastSlam1(n, sc.m, rr.FsConfig(nth=n / 1.5), seed=42)
+    g2.seed_map(sc.start, sc.landmarks)
+    for t in range(12):
+        g2.fastslam_update(sc.control, sc.obs[t], want_flag=False)
+    assert np.array_equal(g.state(landmarks=False)[0], g2.state(landmarks=False)[0])
+    assert np.array_equal(g.particle_landmarks(12345), g2.particle_landmarks(12345))
+
+
+def test_fastslam_full_size_matches_oracle(oracle):
+    """65 536 x 256, three steps, everything (805 MB of landmark state) compared bit for bit."""
+    n = 1 << 16
+    sc = scenarios.c3_scenario(steps=3)
+    g = rr.FastSlam1(n, sc.m, rr.FsConfig(nth=n / 1.5), seed=42)
+    o = OracleFS(oracle, n, sc.m, seed=42, nth=n / 1.5)
+    o.L.orc_fs_set_threads(o.h, 8)
+    g.seed_map(sc.start, sc.landmarks); o.seed_map(sc.start, sc.landmarks)
+    for t in range(3):
+        assert g.fastslam_update(sc.control, sc.obs[t]) == bool(o.step(sc.control, sc.obs[t]))
+    _fs_compare(g, o, "full size")

@@ -182,10 +182,16 @@ static void resample(orc_fs* f, double u01) {
     size_t j = 0;
     for (size_t t = 0; t < n; ++t) {
         while (r > cum[j + 1] && j < n - 1) j++;
-        f->w2[t] = 1.0 / (double)n; f->x2[t] = f->x[j]; f->y2[t] = f->y[j]; f->yaw2[t] = f->yaw[j];
-        memcpy(&f->lm2[t * m], &f->lm[j * m], m * sizeof(lm_t));     /* particles[j].clone() */
         f->last_idx[t] = (uint32_t)j;
         r += 1.0 / (double)n;
+    }
+    /* particles[j].clone(): the copies are independent, so the all-core baseline may do them in parallel */
+    long nn = (long)n;
+#pragma omp parallel for num_threads(f->threads) schedule(static) if (f->threads > 1)
+    for (long t = 0; t < nn; ++t) {
+        size_t jj = f->last_idx[t];
+        f->w2[t] = 1.0 / (double)n; f->x2[t] = f->x[jj]; f->y2[t] = f->y[jj]; f->yaw2[t] = f->yaw[jj];
+        memcpy(&f->lm2[(size_t)t * m], &f->lm[jj * m], m * sizeof(lm_t));
     }
     double* t; lm_t* tl;
     t = f->w; f->w = f->w2; f->w2 = t; t = f->x; f->x = f->x2; f->x2 = t;

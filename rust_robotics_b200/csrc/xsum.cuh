@@ -45,6 +45,7 @@ struct XsWork {
     double* s_after = nullptr; // [nt * XS_MAXD] exact prefix right after each dirty value (by ordinal)
     int*    flags = nullptr;   // [0] serial mode  [1] dirty total  [2] emit-time certificate failure  [3] bad value seen
                                // [4] cumulative serial fallbacks  [5] dirty total of the last chain  [6] cumulative emit failures
+                               // [7] cumulative overflow tiles (walked serially, still exact)
     double  approx_offset = 0.0;   // approximate sum of everything before this shard (multi-GPU)
     const int* gate = nullptr;     // device flag: when non-null and 0, every kernel of the pipeline returns at once
 };
@@ -200,7 +201,11 @@ __global__ void __launch_bounds__(XS_NT) xs_classify_tiles(F f, size_t n, double
     XsSeg carry = xs_block_seg_excl<XS_NT>(xs_seg_make(ts.tail, ts.nd > 0), &stot, sm_s);
     int ndtot;
     int doff = block_excl_scan_int<XS_NT>(ts.nd, &ndtot, sm_i);
-    if (ts.nd > 0) {   // rare: redo the pass and write this thread's dirty entries
+    // A tile with more than XS_MAXD dirty values (a long crawl along a level edge) is not itemised: it becomes
+    // ONE pseudo entry (pad = 1) that tells the chain to walk the whole tile with genuine FP adds; its tail
+    // transducer is the identity because the walk ends at the tile end.
+    const bool overflow = ndtot > XS_MAXD;
+    if (ts.nd > 0 && !overflow) {   // rare: redo the pass and write this thread's dirty entries
         xs_t run = carry.t;
         double running = 0.0, a_prev = toff + excl;
         int slot = doff;
@@ -222,9 +227,16 @@ __global__ void __launch_bounds__(XS_NT) xs_classify_tiles(F f, size_t n, double
         }
     }
     if (threadIdx.x == 0) {
-        w.ttail[b] = stot.t;
-        w.tnd[b] = ndtot;
-        if (ndtot > XS_MAXD || stot.t.lvl == XS_BAD) w.flags[0] = 1;
+        if (overflow) {
+            XsEntry e; e.d0 = 0; e.d1 = 0; e.lvl = XS_EMPTY; e.pad = 1; e.v = 0.0;
+            w.ent[(size_t)b * XS_MAXD] = e;
+            w.ttail[b] = xs_identity();
+            w.tnd[b] = -1;
+        } else {
+            w.ttail[b] = stot.t;
+            w.tnd[b] = ndtot;
+        }
+        if (stot.t.lvl == XS_BAD) w.flags[0] = 1;
     }
 }
 
@@ -250,6 +262,7 @@ __global__ void __launch_bounds__(XS_CHAIN_NT) xs_chain(F f, size_t n, unsigned 
     for (unsigned base = 0; base < nt; base += XS_CHAIN_NT) {
         unsigned b = base + tid;
         int nd = b < nt ? w.tnd[b] : 0;
+        if (nd < 0) nd = 1;                              // overflow tile: one pseudo entry
         xs_t tl = b < nt ? w.ttail[b] : xs_identity();
         XsSeg tot; int ndtot;
         XsSeg ex = xs_block_seg_excl<XS_CHAIN_NT>(xs_seg_make(tl, nd > 0), &tot, sm_s);
@@ -269,6 +282,7 @@ __global__ void __launch_bounds__(XS_CHAIN_NT) xs_chain(F f, size_t n, unsigned 
             for (unsigned b = tid; b < nt; b += XS_CHAIN_NT) {
                 int nd = w.tnd[b];
                 if (nd == 0) continue;
+                if (nd < 0) nd = 1;
                 int o0 = w.tdoff[b];
                 if (o0 >= cbase + XS_CHUNK || o0 + nd <= cbase) continue;
                 xs_t tinb = w.tin[b];
@@ -281,6 +295,7 @@ __global__ void __launch_bounds__(XS_CHAIN_NT) xs_chain(F f, size_t n, unsigned 
                         r = xs_compose(tinb, r);
                         en.d0 = r.d0; en.d1 = r.d1; en.lvl = r.lvl;
                     }
+                    if (en.pad == 1) en.v = (double)b;      // overflow marker carries its tile index
                     sm_ent[o] = en;
                 }
             }
@@ -291,7 +306,15 @@ __global__ void __launch_bounds__(XS_CHAIN_NT) xs_chain(F f, size_t n, unsigned 
                 for (int o = 0; o < cnt; ++o) {
                     xs_t r; r.d0 = sm_ent[o].d0; r.d1 = sm_ent[o].d1; r.lvl = sm_ent[o].lvl;
                     s = xs_apply(r, s, &ok);
-                    s = s + sm_ent[o].v;
+                    if (sm_ent[o].pad == 1) {               // overflow tile: walk it with genuine FP adds
+                        unsigned b = (unsigned)sm_ent[o].v;
+                        w.sbase[b] = s;
+                        size_t lo = (size_t)b * XS_TILE, hi = lo + XS_TILE < n ? lo + XS_TILE : n;
+                        for (size_t i = lo; i < hi; ++i) s = s + f(i);
+                        w.flags[7] += 1;
+                    } else {
+                        s = s + sm_ent[o].v;
+                    }
                     sm_after[o] = s;
                 }
                 s_run = s;
@@ -336,7 +359,7 @@ __global__ void __launch_bounds__(XS_NT) xs_emit_tiles(F f, S sink, size_t n, do
     __shared__ XsSeg sm_s[XS_NT / 32];
     XS_GATE(w);
     const unsigned b = blockIdx.x;
-    if (w.flags[0]) {      // serial mode: each tile is walked by one thread from its exact base
+    if (w.flags[0] || w.tnd[b] < 0) {      // serial mode / overflow tile: walked by one thread from its exact base
         if (threadIdx.x == 0) {
             double s = w.sbase[b];
             size_t lo = (size_t)b * XS_TILE, hi = lo + XS_TILE < n ? lo + XS_TILE : n;

@@ -21,8 +21,12 @@ RTOL = 1e-6   # north_star tolerance for floating-point summaries
 
 def assert_cov_close(got, want, what=""):
     got, want = np.asarray(got).reshape(4, 4), np.asarray(want).reshape(4, 4)
-    scale = np.sqrt(np.abs(np.outer(np.diag(want), np.diag(want)))) + 1e-300
-    assert np.max(np.abs(got - want) / scale) < RTOL, f"covariance {what}: {np.max(np.abs(got - want) / scale)}"
+    # relative to sqrt(var_i var_j); a state component without spread (e.g. v when velocity_noise == 0) has
+    # var ~ 1e-31 of pure rounding noise, so the scale is floored at 1e-9 of the largest variance
+    d = np.maximum(np.abs(np.diag(want)), 1e-9 * np.max(np.abs(np.diag(want))) + 1e-300)
+    scale = np.sqrt(np.outer(d, d))
+    err = np.max(np.abs(got - want) / scale)
+    assert err < RTOL, f"covariance {what}: {err}"
 
 
 # ------------------------------------------------------------------------------------------------

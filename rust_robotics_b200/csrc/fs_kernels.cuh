@@ -7,6 +7,14 @@
 //   lm[2][m][6][n]                     landmark EKF state: field-major columns x, y, c00, c01, c10, c11 of
 //                                      landmark l are 6 contiguous n-vectors, so one observed landmark is 6
 //                                      fully coalesced column segments for a warp of consecutive particles
+//   anc[2][m][n] (u32), lmstate[m]     LAZY CLONE.  The reference's resample deep-copies every particle's whole map
+//                                      (particles[j].clone(), fs1.rs:227: 48*m bytes per particle, 1.6 GB of traffic
+//                                      at 65 536 x 256).  Here a resample only composes, per landmark, an ancestry
+//                                      column: "particle i's copy of landmark l lives in column anc[l][i] of buffer
+//                                      lmstate[l]&1" (8 B per particle and landmark instead of 96).  The actual copy is
+//                                      folded into the next EKF update of that landmark: it reads through anc (systematic
+//                                      ancestries are monotone, so the gather stays nearly coalesced), writes column i of
+//                                      the other buffer and marks the landmark "identity" (lmstate[l]&2) again.
 //   cum[n], rcomb[n], idx[n]           exact cumulative weights, exact comb positions, ancestry
 #pragma once
 #include "common.cuh"
@@ -34,6 +42,10 @@ struct FsDev {
     FsObsDev* obs = nullptr;     // device copy of this step's observation list
     double* best_w = nullptr; unsigned long long* best_i = nullptr;   // per-block argmax partials
     unsigned int* counters = nullptr;   // device: [0] resamples done so far (= Philox call index of the next comb draw)
+    uint32_t* anc[2] = {nullptr, nullptr};   // [m][n] per-landmark ancestry columns (ping-pong across resamples)
+    int* anc_cur = nullptr;                  // device: live ancestry buffer
+    int* lmstate = nullptr;                  // device [m]: bit0 = buffer holding landmark l, bit1 = ancestry is the identity
+    int eager = 0;                           // 1 (sharded mode): maps are cloned eagerly; every landmark lives in buffer *cur
 };
 
 // Observation lists of up to FS_PARAM_OBS entries travel inside the kernel's launch parameters (no H2D copy).
@@ -45,6 +57,7 @@ __device__ __forceinline__ double* fs_px(const FsDev& d, int c) { return c ? d.p
 __device__ __forceinline__ double* fs_py(const FsDev& d, int c) { return c ? d.py[1] : d.py[0]; }
 __device__ __forceinline__ double* fs_pyaw(const FsDev& d, int c) { return c ? d.pyaw[1] : d.pyaw[0]; }
 __device__ __forceinline__ double* fs_lm(const FsDev& d, int c) { return c ? d.lm[1] : d.lm[0]; }
+__device__ __forceinline__ uint32_t* fs_anc(const FsDev& d, int c) { return c ? d.anc[1] : d.anc[0]; }
 __device__ __forceinline__ size_t lm_index(size_t n, size_t l, int f, size_t i) { return (l * 6 + (size_t)f) * n + i; }
 
 // normalize_angle fs1.rs:80-89.  The reference loops without bound (and would spin forever on +-inf); the
@@ -121,18 +134,18 @@ __device__ __forceinline__ double fs_update_landmark(FsLm& L, double px, double 
 template <bool PARAM_OBS>
 __global__ void __launch_bounds__(FS_NT) fs_step_kernel(FsDev d, const __grid_constant__ FsObsParam po, double u0, double u1,
                                                         double dt, double sq0, double sq1, double r00, double r11,
-                                                        uint64_t seed, uint32_t call, int k_obs) {
+                                                        uint64_t seed, uint32_t call, int k_obs, int do_predict) {
     extern __shared__ FsObsDev s_obs_fs[];
     for (int j = threadIdx.x; j < k_obs; j += FS_NT) s_obs_fs[j] = PARAM_OBS ? po.o[j] : d.obs[j];
     __syncthreads();
     const size_t i = (size_t)blockIdx.x * FS_NT + threadIdx.x;
     if (i >= d.n) return;
     const int cur = *d.cur;
-    double* __restrict__ lm = fs_lm(d, cur);
     double px = fs_px(d, cur)[i], py = fs_py(d, cur)[i], pyaw = fs_pyaw(d, cur)[i];
-    double z0, z1;
-    pfc_normal_pair(pfc_rng_block(seed, PFC_STREAM_FS_PREDICT, call, d.offset + i), &z0, &z1);
-    {   // predict_particle + motion_model fs1.rs:70-77,128-136
+    double w;
+    if (do_predict) {   // predict_particle + motion_model fs1.rs:70-77,128-136
+        double z0, z1;
+        pfc_normal_pair(pfc_rng_block(seed, PFC_STREAM_FS_PREDICT, call, d.offset + i), &z0, &z1);
         double un0 = u0 + z0 * sq0;
         double un1 = u1 + z1 * sq1;
         double s, c;
@@ -141,27 +154,114 @@ __global__ void __launch_bounds__(FS_NT) fs_step_kernel(FsDev d, const __grid_co
         double ny = py + un0 * dt * s;
         double nyaw = fs_normalize_angle(pyaw + un1 * dt);
         px = nx; py = ny; pyaw = nyaw;
+        w = d.w[i];
+    } else {
+        w = d.w_raw[i];       // continuation launch of the same step (observation list split at a repeated lm_id)
     }
-    double w = d.w[i];
     const size_t n = d.n;
+    const uint32_t* __restrict__ anc = fs_anc(d, *d.anc_cur);
     for (int j = 0; j < k_obs; ++j) {
         const size_t l = (size_t)s_obs_fs[j].lm_id;
         const double zd = s_obs_fs[j].d, za = s_obs_fs[j].angle;
+        const int st = d.lmstate[l];
+        const bool ident = (st & 2) != 0;
+        const double* __restrict__ src = fs_lm(d, st & 1);
+        double* __restrict__ dst = fs_lm(d, ident ? (st & 1) : ((st & 1) ^ 1));
+        const size_t col = ident ? i : (size_t)anc[l * n + i];       // lazy clone: read the ancestor's copy
         FsLm L;
-        L.x = lm[lm_index(n, l, 0, i)]; L.y = lm[lm_index(n, l, 1, i)];
-        L.c00 = lm[lm_index(n, l, 2, i)]; L.c01 = lm[lm_index(n, l, 3, i)];
-        L.c10 = lm[lm_index(n, l, 4, i)]; L.c11 = lm[lm_index(n, l, 5, i)];
+        L.x = src[lm_index(n, l, 0, col)]; L.y = src[lm_index(n, l, 1, col)];
+        L.c00 = src[lm_index(n, l, 2, col)]; L.c01 = src[lm_index(n, l, 3, col)];
+        L.c10 = src[lm_index(n, l, 4, col)]; L.c11 = src[lm_index(n, l, 5, col)];
         bool wrote_cov;
         double lik = fs_update_landmark(L, px, py, pyaw, zd, za, r00, r11, &wrote_cov);
-        lm[lm_index(n, l, 0, i)] = L.x; lm[lm_index(n, l, 1, i)] = L.y;
-        if (wrote_cov) {
-            lm[lm_index(n, l, 2, i)] = L.c00; lm[lm_index(n, l, 3, i)] = L.c01;
-            lm[lm_index(n, l, 4, i)] = L.c10; lm[lm_index(n, l, 5, i)] = L.c11;
-            w = w * lik;                                       // fs1.rs:181 (only when det_s > 0: lik == 1.0 otherwise)
+        dst[lm_index(n, l, 0, i)] = L.x; dst[lm_index(n, l, 1, i)] = L.y;
+        if (wrote_cov || !ident) {                             // a materialising write must carry the covariance too
+            dst[lm_index(n, l, 2, i)] = L.c00; dst[lm_index(n, l, 3, i)] = L.c01;
+            dst[lm_index(n, l, 4, i)] = L.c10; dst[lm_index(n, l, 5, i)] = L.c11;
         }
+        if (wrote_cov) w = w * lik;                            // fs1.rs:181 (only when det_s > 0: lik == 1.0 otherwise)
     }
     fs_px(d, cur)[i] = px; fs_py(d, cur)[i] = py; fs_pyaw(d, cur)[i] = pyaw;
     d.w_raw[i] = w;
+}
+// ---------------------------------------------------------------------------------------------------------------------
+// Observation-parallel form of the step: fs_predict_kernel + fs_ekf_kernel.  Same arithmetic, decomposed for latency:
+// the one-thread-per-particle kernel has only n/32 = 2048 warps for the whole chip (14 per SM), each carrying ~7 700
+// dependent instructions, so it idles on FP64 div/sqrt and load latency (profiles/r01a_summary.md).
+//   fs_predict_kernel : predict_particle (fs1.rs:123-137), one thread per particle, in place; also w_raw = w.
+//   fs_ekf_kernel     : a CTA owns 32 particles and runs one warp per observation (lanes = particles, so the six
+//                       landmark columns stay coalesced); every warp does one update_landmark (fs1.rs:140-183); then
+//                       warp 0 multiplies the likelihood factors into the weight IN OBSERVATION ORDER,
+//                       w = (((w*l_0)*l_1)...), exactly like the sequential loop fs1.rs:250-256.
+// Updates of different landmarks commute (a launch never holds the same lm_id twice; the host splits such lists).
+// ---------------------------------------------------------------------------------------------------------------------
+#define FS2_MAX_OBS 32
+__global__ void __launch_bounds__(256) fs_predict_kernel(FsDev d, double u0, double u1, double dt, double sq0, double sq1,
+                                                         uint64_t seed, uint32_t call) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= d.n) return;
+    const int cur = *d.cur;
+    double px = fs_px(d, cur)[i], py = fs_py(d, cur)[i], pyaw = fs_pyaw(d, cur)[i];
+    double z0, z1;
+    pfc_normal_pair(pfc_rng_block(seed, PFC_STREAM_FS_PREDICT, call, d.offset + i), &z0, &z1);
+    double un0 = u0 + z0 * sq0;                                // fs1.rs:129
+    double un1 = u1 + z1 * sq1;                                // fs1.rs:130
+    double s, c;
+    pfc_sincos(pyaw, &s, &c);
+    fs_px(d, cur)[i] = px + un0 * dt * c;                      // motion_model fs1.rs:73-75
+    fs_py(d, cur)[i] = py + un0 * dt * s;
+    fs_pyaw(d, cur)[i] = fs_normalize_angle(pyaw + un1 * dt);
+    d.w_raw[i] = d.w[i];
+}
+
+template <bool PARAM_OBS>
+__global__ void __launch_bounds__(1024, 1) fs_ekf_kernel(FsDev d, const __grid_constant__ FsObsParam po, double r00, double r11, int k_obs) {
+    extern __shared__ double s_v2[];
+    double* s_lik = s_v2;                                                          // [k_obs][32]
+    unsigned* s_mask = reinterpret_cast<unsigned*>(s_lik + (size_t)k_obs * 32);    // [k_obs]
+    const int lane = threadIdx.x & 31, wj = threadIdx.x >> 5;
+    const size_t i = (size_t)blockIdx.x * 32 + lane;
+    const bool valid = i < d.n;
+    const size_t n = d.n;
+    const int cur = *d.cur;
+    const FsObsDev ob = PARAM_OBS ? po.o[wj] : d.obs[wj];
+    const size_t l = (size_t)ob.lm_id;
+    const int st = d.lmstate[l];
+    const bool ident = (st & 2) != 0;
+    const double* __restrict__ src = fs_lm(d, st & 1) + l * 6 * n;
+    double* __restrict__ dst = fs_lm(d, ident ? (st & 1) : ((st & 1) ^ 1)) + l * 6 * n + i;
+    bool wrote_cov = false;
+    double lik = 1.0;
+    if (valid) {
+        const size_t col = ident ? i : (size_t)fs_anc(d, *d.anc_cur)[l * n + i];     // lazy clone: the ancestor's copy
+        const double* __restrict__ sp = src + col;
+        FsLm L;
+        L.x = sp[0]; L.y = sp[n]; L.c00 = sp[2 * n]; L.c01 = sp[3 * n]; L.c10 = sp[4 * n]; L.c11 = sp[5 * n];
+        const double px = fs_px(d, cur)[i], py = fs_py(d, cur)[i], pyaw = fs_pyaw(d, cur)[i];
+        lik = fs_update_landmark(L, px, py, pyaw, ob.d, ob.angle, r00, r11, &wrote_cov);
+        dst[0] = L.x; dst[n] = L.y;
+        if (wrote_cov || !ident) { dst[2 * n] = L.c00; dst[3 * n] = L.c01; dst[4 * n] = L.c10; dst[5 * n] = L.c11; }
+    }
+    s_lik[wj * 32 + lane] = lik;
+    const unsigned mask = __ballot_sync(0xffffffffu, wrote_cov);
+    if (lane == 0) s_mask[wj] = mask;
+    __syncthreads();
+    if (wj == 0 && valid) {
+        double w = d.w_raw[i];
+        for (int j = 0; j < k_obs; ++j)
+            if ((s_mask[j] >> lane) & 1u) w = w * s_lik[j * 32 + lane];              // fs1.rs:181, in observation order
+        d.w_raw[i] = w;
+    }
+}
+
+// after a step launch: every landmark it updated through its ancestry now lives in the other buffer, own columns
+template <bool PARAM_OBS>
+__global__ void fs_lmstate_after_step_kernel(FsDev d, const __grid_constant__ FsObsParam po, int k_obs) {
+    for (int j = threadIdx.x; j < k_obs; j += blockDim.x) {
+        int l = PARAM_OBS ? po.o[j].lm_id : d.obs[j].lm_id;
+        int st = d.lmstate[l];
+        if (!(st & 2)) d.lmstate[l] = ((st & 1) ^ 1) | 2;
+    }
 }
 
 // normalize_weights fs1.rs:196-203 (no uniform fallback)
@@ -213,6 +313,26 @@ __global__ void __launch_bounds__(256) fs_search_kernel(FsDev d) {
     d.idx[t] = (uint32_t)(lo < d.n ? lo : d.n - 1);
 }
 
+// index walk + pose clone in one pass (used after the fused post kernel)
+__global__ void __launch_bounds__(256) fs_search_pose_kernel(FsDev d) {
+    if (!*d.gate) return;
+    const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= d.n) return;
+    const double r = d.rcomb[t];
+    const double* __restrict__ c = d.cum;
+    size_t lo = 0, hi = d.n;
+    while (lo < hi) {
+        size_t mid = lo + ((hi - lo) >> 1);
+        if (c[mid] < r) lo = mid + 1; else hi = mid;
+    }
+    const size_t j = lo < d.n ? lo : d.n - 1;
+    d.idx[t] = (uint32_t)j;
+    const int cur = *d.cur;
+    fs_px(d, cur ^ 1)[t] = fs_px(d, cur)[j];
+    fs_py(d, cur ^ 1)[t] = fs_py(d, cur)[j];
+    fs_pyaw(d, cur ^ 1)[t] = fs_pyaw(d, cur)[j];
+    d.w[t] = 1.0 / (double)d.n_global;                      // fs1.rs:228
+}
 // particles[j].clone(): the pose columns and weight (fs1.rs:227-229)
 __global__ void __launch_bounds__(256) fs_gather_pose_kernel(FsDev d) {
     if (!*d.gate) return;
@@ -225,26 +345,30 @@ __global__ void __launch_bounds__(256) fs_gather_pose_kernel(FsDev d) {
     fs_pyaw(d, cur ^ 1)[t] = fs_pyaw(d, cur)[j];
     d.w[t] = 1.0 / (double)d.n_global;
 }
-// ... and the whole map: every one of the 6*m landmark columns is gathered through the same (monotone)
-// ancestry.  grid.x = particle chunks, grid.y = column groups of FS_GATHER_ROWS.
-#define FS_GATHER_ROWS 16
-__global__ void __launch_bounds__(256) fs_gather_lm_kernel(FsDev d) {
+// ... and the map: instead of copying 48*m bytes per particle, compose every landmark's ancestry column with this
+// resample's (monotone) ancestry idx: anc'[l][t] = anc[l][idx[t]]  (idx[t] itself where the landmark is identity-mapped).
+// grid.x = particle chunks, grid.y = groups of FS_COMPOSE_ROWS landmarks.
+#define FS_COMPOSE_ROWS 16
+__global__ void __launch_bounds__(256) fs_compose_anc_kernel(FsDev d) {
     if (!*d.gate) return;
     const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (t >= d.n) return;
-    const int cur = *d.cur;
-    const double* __restrict__ src = fs_lm(d, cur);
-    double* __restrict__ dst = fs_lm(d, cur ^ 1);
-    const size_t j = d.idx[t];
-    const size_t rows = 6 * d.m;
-    const size_t r0 = (size_t)blockIdx.y * FS_GATHER_ROWS;
+    const int ac = *d.anc_cur;
+    const uint32_t* __restrict__ src = fs_anc(d, ac);
+    uint32_t* __restrict__ dst = fs_anc(d, ac ^ 1);
+    const uint32_t j = d.idx[t];
+    const size_t l0 = (size_t)blockIdx.y * FS_COMPOSE_ROWS;
 #pragma unroll
-    for (int rr = 0; rr < FS_GATHER_ROWS; ++rr) {
-        size_t row = r0 + rr;
-        if (row < rows) dst[row * d.n + t] = src[row * d.n + j];
+    for (int rr = 0; rr < FS_COMPOSE_ROWS; ++rr) {
+        size_t l = l0 + rr;
+        if (l < d.m) dst[l * d.n + t] = (d.lmstate[l] & 2) ? j : src[l * d.n + j];
     }
 }
-__global__ void fs_flip_kernel(FsDev d) { if (*d.gate) { *d.cur ^= 1; d.counters[0] += 1; } }
+__global__ void fs_flip_kernel(FsDev d) {
+    if (!*d.gate) return;
+    for (size_t l = threadIdx.x; l < d.m; l += blockDim.x) d.lmstate[l] &= 1;     // no landmark is identity-mapped any more
+    if (threadIdx.x == 0) { *d.cur ^= 1; *d.anc_cur ^= 1; d.counters[0] += 1; }
+}
 
 // get_best_particle fs1.rs:269-274: max_by keeps the LAST maximum
 __global__ void __launch_bounds__(256) fs_best_kernel(FsDev d, int nblocks) {
@@ -287,7 +411,7 @@ __global__ void __launch_bounds__(256) fs_unpack_lm_kernel(FsDev d, const double
     if (e >= tot) return;
     size_t ip = e / (d.m * 6), rem = e % (d.m * 6);
     size_t l = rem / 6; int f = (int)(rem % 6);
-    fs_lm(d, *d.cur)[lm_index(d.n, l, f, i0 + ip)] = aos[e];
+    fs_lm(d, d.eager ? *d.cur : 0)[lm_index(d.n, l, f, i0 + ip)] = aos[e];
 }
 __global__ void __launch_bounds__(256) fs_pack_lm_kernel(FsDev d, double* aos, size_t i0, size_t cnt) {
     const size_t e = (size_t)blockIdx.x * 256 + threadIdx.x;
@@ -295,7 +419,13 @@ __global__ void __launch_bounds__(256) fs_pack_lm_kernel(FsDev d, double* aos, s
     if (e >= tot) return;
     size_t ip = e / (d.m * 6), rem = e % (d.m * 6);
     size_t l = rem / 6; int f = (int)(rem % 6);
-    aos[e] = fs_lm(d, *d.cur)[lm_index(d.n, l, f, i0 + ip)];
+    const int st = d.lmstate[l];
+    const size_t col = (st & 2) ? (i0 + ip) : (size_t)fs_anc(d, *d.anc_cur)[l * d.n + i0 + ip];   // materialise through the ancestry
+    aos[e] = fs_lm(d, st & 1)[lm_index(d.n, l, f, col)];
+}
+__global__ void fs_lmstate_reset_kernel(FsDev d) {     // every landmark identity-mapped in buffer 0 (eager mode: *cur) after init/upload/seed
+    const int buf = d.eager ? *d.cur : 0;
+    for (size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x; l < d.m; l += (size_t)gridDim.x * blockDim.x) d.lmstate[l] = buf | 2;
 }
 // create_particles fs1.rs:302-306: Particle::new (fs1.rs:54-62) with Landmark::new (fs1.rs:34-40)
 __global__ void __launch_bounds__(256) fs_init_kernel(FsDev d, double init_weight) {
@@ -322,7 +452,7 @@ __global__ void __launch_bounds__(256) fs_seed_lm_kernel(FsDev d, const double* 
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     const size_t l = blockIdx.y;
     if (i >= d.n) return;
-    double* lm = fs_lm(d, *d.cur);
+    double* lm = fs_lm(d, d.eager ? *d.cur : 0);
     double z0, z1;
     pfc_normal_pair(pfc_rng_block(seed, PFC_STREAM_INIT_A, 0, (d.offset + i) * d.m + l), &z0, &z1);
     lm[lm_index(d.n, l, 0, i)] = lm_xy[2 * l] + sigma * z0;

@@ -1,0 +1,341 @@
+// fs_post.cuh — everything fastslam_update does AFTER the per-particle work (fs1.rs:258-265 + resample fs1.rs:206-231),
+// fused into ONE cooperative kernel for particle counts that fit one co-resident wave of FX_TILE-particle CTAs:
+//
+//     S  = sum w_raw (exact, sequential order)            normalize_weights        fs1.rs:196-203
+//     w  = w_raw / S                                                                fs1.rs:200
+//     Q  = sum w^2  -> neff = 1/Q -> gate = neff < NTH     compute_neff + gate      fs1.rs:186-193, 262-263
+//     S2 = sum w ;  w2 = w / S2                           resample re-normalises   fs1.rs:207
+//     c  = cumsum(w2),  r_t = r0 + t/n accumulated        cum_sum + comb           fs1.rs:213-216, 219-230
+//   (j_t = first j with c_j >= r_t and the pose clone run in fs_search_pose_kernel, at full occupancy)
+//
+// Each CTA owns one tile of FX_TILE = 512 particles and keeps its values in REGISTERS across all phases; the
+// five exact sums run through the same tile-aggregate / chain scheme as xsum.cuh, but the chain (tens of entries) is
+// evaluated redundantly by every CTA, so an exact total costs 2 grid-wide barriers and no extra launches.  Q and S2
+// share their barriers, so do the two scans: 5 barriers for a step that does not resample, 7 for one that does
+// (instead of ~25 launches).
+#pragma once
+#include <cooperative_groups.h>
+#include "common.cuh"
+#include "xsum.cuh"
+#include "fs_kernels.cuh"
+
+namespace cg = cooperative_groups;
+
+#define FX_MAX_TILES 512
+#define FX_CHUNK 256
+#define FX_ITEMS 2                         // values per thread: small on purpose — the kernel is instruction-fetch bound, so
+#define FX_TILE (XS_NT * FX_ITEMS)         // short unrolled bodies on many CTAs (128 for 65 536 particles) beat long ones on few
+#define FX_SLOTS 5            // S, Q, S2, cum, comb
+
+struct FxSlot { double* tsum; xs_t* ttail; int* tnd; XsEntry* ent; };
+struct FxWork {
+    FxSlot slot[FX_SLOTS];
+    int* flags;               // [0] bad value seen (-> exact serial walk)  [1] cumulative serial walks  [2] cumulative certificate failures
+                              // [3] cumulative overflow tiles
+};
+
+struct FxShared {
+    double sm_d[XS_NT / 32];
+    int sm_i[XS_NT / 32];
+    XsSeg sm_s[XS_NT / 32];
+    XsSeg carry_seg;
+    int carry_nd;
+    xs_t tin[FX_MAX_TILES];
+    int tdoff[FX_MAX_TILES];
+    int tnd[FX_MAX_TILES];
+    XsEntry ent[FX_CHUNK];
+    double after_win[XS_MAXD + 2];     // exact prefixes right after the dirty values of MY tile (+ the one before it)
+    double total;
+    double s_run;
+    int ok;
+    int serial;
+    double r0;
+};
+
+struct FxTile {            // what a thread keeps between classify and emit
+    double toff, excl;
+    XsSeg carry;           // clean values of this tile before the thread since the last dirty one (flag: such a dirty value exists)
+    int doff;              // dirty values of this tile before the thread
+    int nd_tile;           // dirty values in the tile (-1: overflow)
+};
+
+// ---- phase 1: approximate tile sum -> global -------------------------------------------------------
+__device__ __forceinline__ void fx_tile_sum(const double (&v)[FX_ITEMS], const FxSlot& s, FxShared& sh, int* flags) {
+    double t = 0.0; bool bad = false;
+#pragma unroll
+    for (int k = 0; k < FX_ITEMS; ++k) { t += v[k]; if (!(v[k] >= 0.0) || !(v[k] <= 1.7976931348623157e308)) bad = true; }
+    if (bad) flags[0] = 1;
+    double tot = block_sum<XS_NT>(t, sh.sm_d);
+    if (threadIdx.x == 0) s.tsum[blockIdx.x] = tot;
+}
+
+// ---- phase 2 (after a grid barrier): classify the tile, publish its aggregate and dirty entries ----------------
+__device__ __forceinline__ FxTile fx_classify(const double (&v)[FX_ITEMS], const FxSlot& s, FxShared& sh, double rel) {
+    const unsigned b = blockIdx.x;
+    FxTile c;
+    double part = 0.0;
+    for (unsigned t = threadIdx.x; t < b; t += XS_NT) part += s.tsum[t];
+    double toff_b = block_sum<XS_NT>(part, sh.sm_d);
+    __syncthreads();
+    if (threadIdx.x == 0) sh.total = toff_b;
+    __syncthreads();
+    c.toff = sh.total;
+    double tsum = 0.0;
+#pragma unroll
+    for (int k = 0; k < FX_ITEMS; ++k) tsum += v[k];
+    double btot;
+    c.excl = block_excl_scan<XS_NT>(tsum, &btot, sh.sm_d);
+    XsThreadScan ts = xs_thread_scan(v, c.toff, c.excl, rel);
+    XsSeg stot;
+    XsSeg carry = xs_block_seg_excl<XS_NT>(xs_seg_make(ts.tail, ts.nd > 0), &stot, sh.sm_s);
+    int ndtot;
+    c.doff = block_excl_scan_int<XS_NT>(ts.nd, &ndtot, sh.sm_i);
+    c.carry = carry;
+    const bool overflow = ndtot > XS_MAXD;
+    c.nd_tile = overflow ? -1 : ndtot;
+    if (ts.nd > 0 && !overflow) {
+        xs_t run = carry.t;
+        double running = 0.0, a_prev = c.toff + c.excl;
+        int slot = c.doff;
+#pragma unroll
+        for (int k = 0; k < FX_ITEMS; ++k) {
+            running += v[k];
+            double a_cur = c.toff + (c.excl + running);
+            xs_t t;
+            if (xs_classify(v[k], a_prev, a_cur, rel, &t)) run = xs_compose(run, t);
+            else {
+                XsEntry e; e.inc = run.inc; e.lvl = run.lvl; e.pad = 0; e.v = v[k];
+                s.ent[(size_t)b * XS_MAXD + slot] = e;
+                slot++;
+                run = xs_identity();
+            }
+            a_prev = a_cur;
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (overflow) {
+            XsEntry e; e.inc = 0; e.lvl = XS_EMPTY; e.pad = 1; e.v = 0.0;
+            s.ent[(size_t)b * XS_MAXD] = e;
+            s.ttail[b] = xs_identity();
+            s.tnd[b] = -1;
+        } else {
+            s.ttail[b] = stot.t;
+            s.tnd[b] = ndtot;
+        }
+    }
+    return c;
+}
+
+// ---- phase 3 (after a grid barrier): every CTA evaluates the whole chain; results land in shared memory ---------
+// sh.total = exact total; sh.tin[blockIdx.x], sh.tdoff[blockIdx.x], sh.after_win[] serve fx_emit for this tile.
+template <class F>
+__device__ __noinline__ void fx_chain(const FxSlot& s, unsigned nt, F f, size_t n, FxShared& sh, int* flags) {
+    const int tid = threadIdx.x;
+    const unsigned me = blockIdx.x;
+    __syncthreads();
+    if (tid == 0) { sh.carry_seg = xs_seg_make(xs_identity(), 0); sh.carry_nd = 0; sh.s_run = 0.0; sh.ok = 1; sh.serial = flags[0]; }
+    __syncthreads();
+    for (unsigned base = 0; base < nt; base += XS_NT) {
+        unsigned b = base + tid;
+        int nd = b < nt ? s.tnd[b] : 0;
+        int nde = nd < 0 ? 1 : nd;
+        xs_t tl = b < nt ? s.ttail[b] : xs_identity();
+        XsSeg tot; int ndtot;
+        XsSeg ex = xs_block_seg_excl<XS_NT>(xs_seg_make(tl, nde > 0), &tot, sh.sm_s);
+        int dex = block_excl_scan_int<XS_NT>(nde, &ndtot, sh.sm_i);
+        XsSeg cs = sh.carry_seg; int cn = sh.carry_nd;
+        if (b < nt) { sh.tin[b] = xs_seg_op(cs, ex).t; sh.tdoff[b] = cn + dex; sh.tnd[b] = nd; }
+        __syncthreads();
+        if (tid == 0) { sh.carry_seg = xs_seg_op(cs, tot); sh.carry_nd = cn + ndtot; }
+        __syncthreads();
+    }
+    const int D = sh.carry_nd;
+    if (tid == 0 && sh.carry_seg.t.lvl == XS_BAD) sh.serial = 1;
+    __syncthreads();
+    const int my_o0 = sh.tdoff[me];                         // window of ordinals fx_emit needs: [my_o0 - 1, my_o0 + nd_me)
+    if (!sh.serial) {
+        for (int cbase = 0; cbase < D; cbase += FX_CHUNK) {
+            for (unsigned b = tid; b < nt; b += XS_NT) {
+                int nd = sh.tnd[b];
+                if (nd == 0) continue;
+                if (nd < 0) nd = 1;
+                int o0 = sh.tdoff[b];
+                if (o0 >= cbase + FX_CHUNK || o0 + nd <= cbase) continue;
+                for (int e = 0; e < nd; ++e) {
+                    int o = o0 + e - cbase;
+                    if (o < 0 || o >= FX_CHUNK) continue;
+                    XsEntry en = s.ent[(size_t)b * XS_MAXD + e];
+                    if (e == 0) {
+                        xs_t r; r.inc = en.inc; r.lvl = en.lvl;
+                        r = xs_compose(sh.tin[b], r);
+                        en.inc = r.inc; en.lvl = r.lvl;
+                    }
+                    if (en.pad == 1) en.v = (double)b;
+                    sh.ent[o] = en;
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double sacc = sh.s_run; int ok = 1;
+                int cnt = D - cbase < FX_CHUNK ? D - cbase : FX_CHUNK;
+                for (int o = 0; o < cnt; ++o) {
+                    xs_t r; r.inc = sh.ent[o].inc; r.lvl = sh.ent[o].lvl;
+                    sacc = xs_apply(r, sacc, &ok);
+                    if (sh.ent[o].pad == 1) {               // overflow tile: genuine FP adds over the whole tile
+                        unsigned b = (unsigned)sh.ent[o].v;
+                        if (b == me) sh.after_win[0] = sacc;            // my own tile is an overflow tile: keep its exact base
+                        size_t lo = (size_t)b * FX_TILE, hi = lo + FX_TILE < n ? lo + FX_TILE : n;
+                        for (size_t i = lo; i < hi; ++i) sacc = sacc + f(i);
+                        if (me == 0) flags[3] += 1;
+                    } else {
+                        sacc = sacc + sh.ent[o].v;
+                    }
+                    int og = cbase + o;                      // global ordinal
+                    int wi = og - (my_o0 - 1);
+                    if (wi >= 0 && wi < XS_MAXD + 2 && !(sh.tnd[me] < 0 && wi == 0)) sh.after_win[wi] = sacc;
+                }
+                sh.s_run = sacc;
+                if (!ok) sh.ok = 0;
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            int ok = sh.ok;
+            double tot = xs_apply(sh.carry_seg.t, sh.s_run, &ok);
+            if (!ok) { sh.serial = 1; if (me == 0) flags[2] += 1; }
+            else sh.total = tot;
+        }
+        __syncthreads();
+    }
+    if (sh.serial) {      // exact by construction: one thread, left to right; also yields this tile's base
+        if (tid == 0) {
+            double sacc = 0.0;
+            size_t mylo = (size_t)me * FX_TILE;
+            for (size_t i = 0; i < n; ++i) { if (i == mylo) sh.after_win[0] = sacc; sacc = sacc + f(i); }
+            sh.total = sacc;
+            if (me == 0) flags[1] += 1;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- phase 4: exact inclusive prefix of this thread's 8 values ------------------------------------------------------
+template <class F>
+__device__ __forceinline__ void fx_emit(const double (&v)[FX_ITEMS], const FxTile& c, FxShared& sh, F f, size_t n, double rel,
+                                        double (&out)[FX_ITEMS], int* flags, double* gscratch /* [n], this tile's slice is ours */) {
+    const unsigned me = blockIdx.x;
+    const size_t first = (size_t)me * FX_TILE + (size_t)threadIdx.x * FX_ITEMS;
+    if (sh.serial || sh.tnd[me] < 0) {          // serial walk / overflow tile: thread 0 walks the tile from its exact base
+        if (threadIdx.x == 0) {
+            double sacc = sh.after_win[0];
+            size_t lo = (size_t)me * FX_TILE, hi = lo + FX_TILE < n ? lo + FX_TILE : n;
+            for (size_t i = lo; i < hi; ++i) { sacc = sacc + f(i); gscratch[i] = sacc; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < FX_ITEMS; ++k) out[k] = first + k < n ? gscratch[first + k] : 0.0;
+        __syncthreads();
+        return;
+    }
+    xs_t run = xs_seg_op(xs_seg_make(sh.tin[me], 0), c.carry).t;   // the carry-in counts only if no dirty value precedes in the tile
+    // after_win[0] = exact prefix right after the last dirty value BEFORE my tile (ordinal tdoff-1), [1+e] = after my e-th
+    int w = c.doff;                                        // dirty values of my tile before this thread
+    double base_s = (sh.tdoff[me] + w > 0) ? sh.after_win[w] : 0.0;
+    double running = 0.0, a_prev = c.toff + c.excl;
+    int ok = 1;
+#pragma unroll
+    for (int k = 0; k < FX_ITEMS; ++k) {
+        running += v[k];
+        double a_cur = c.toff + (c.excl + running);
+        xs_t t;
+        if (xs_classify(v[k], a_prev, a_cur, rel, &t)) { run = xs_compose(run, t); out[k] = xs_apply(run, base_s, &ok); }
+        else { w++; base_s = sh.after_win[w]; out[k] = base_s; run = xs_identity(); }
+        a_prev = a_cur;
+    }
+    (void)first;
+    if (!ok) flags[2] += 1;
+}
+
+struct FxValW2 {      // w / S2 recomputed on the fly for the rare global walks (overflow tiles / serial mode)
+    const double* w; double S2;
+    __device__ __forceinline__ double operator()(size_t i) const { double x = w[i]; return S2 > 0.0 ? x / S2 : x; }
+};
+struct FxValComb { double r0, inv; __device__ __forceinline__ double operator()(size_t i) const { return i == 0 ? r0 : inv; } };
+
+// =====================================================================================================================
+__global__ void __launch_bounds__(XS_NT, 2) fs_post_kernel(FsDev d, FxWork fw, double nth, uint64_t seed, unsigned nt, double rel) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ FxShared sh;
+    const unsigned b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const size_t first = (size_t)b * FX_TILE + (size_t)tid * FX_ITEMS;
+    const size_t n = d.n;
+    if (b == 0 && tid == 0) fw.flags[0] = 0;
+    double v[FX_ITEMS];
+#pragma unroll
+    for (int k = 0; k < FX_ITEMS; ++k) { size_t i = first + k; v[k] = i < n ? d.w_raw[i] : 0.0; }
+    grid.sync();                                               // flags[0] reset is visible before anyone raises it
+    // ---------------- S = sum w_raw; w = w_raw / S (fs1.rs:196-203) ----------------
+    fx_tile_sum(v, fw.slot[0], sh, fw.flags);
+    grid.sync();
+    fx_classify(v, fw.slot[0], sh, rel);
+    grid.sync();
+    fx_chain(fw.slot[0], nt, XsValArray{d.w_raw}, n, sh, fw.flags);
+    const double S = sh.total;
+    double q[FX_ITEMS];
+#pragma unroll
+    for (int k = 0; k < FX_ITEMS; ++k) {
+        size_t i = first + k;
+        if (S > 0.0) v[k] = v[k] / S;
+        if (i < n) d.w[i] = v[k];
+        q[k] = v[k] * v[k];
+    }
+    // ---------------- Q = sum w^2 and S2 = sum w, sharing their barriers ----------------
+    fx_tile_sum(q, fw.slot[1], sh, fw.flags);
+    fx_tile_sum(v, fw.slot[2], sh, fw.flags);
+    grid.sync();
+    fx_classify(q, fw.slot[1], sh, rel);
+    fx_classify(v, fw.slot[2], sh, rel);
+    grid.sync();
+    fx_chain(fw.slot[1], nt, FsValWSq{d.w}, n, sh, fw.flags);
+    const double Q = sh.total;
+    fx_chain(fw.slot[2], nt, XsValArray{d.w}, n, sh, fw.flags);
+    const double S2 = sh.total;
+    const double neff = Q > 0.0 ? 1.0 / Q : 0.0;               // compute_neff fs1.rs:186-193
+    const int gate = neff < nth ? 1 : 0;                       // fs1.rs:263
+    if (b == 0 && tid == 0) {
+        d.scal[0] = S; d.scal[1] = Q; d.scal[2] = S2; d.scal[3] = neff;
+        *d.gate = gate;
+    }
+    if (!gate) return;                                         // the whole grid takes the same branch (Q is bit-identical everywhere)
+    // ---------------- resample (fs1.rs:206-231) ----------------
+    const double inv = 1.0 / (double)d.n_global;
+    if (tid == 0) {
+        double u01 = pfc_u01_52(pfc_blk_u64(pfc_rng_block(seed, PFC_STREAM_FS_RESAMPLE, d.counters[0], 0), 0));
+        sh.r0 = u01 * (inv - 0.0) + 0.0;                       // Uniform::new(0, 1/n).sample
+    }
+    __syncthreads();
+    const double r0 = sh.r0;
+    double cv[FX_ITEMS];
+#pragma unroll
+    for (int k = 0; k < FX_ITEMS; ++k) {
+        size_t i = first + k;
+        if (S2 > 0.0) v[k] = v[k] / S2;                        // normalize_weights inside resample() fs1.rs:207
+        cv[k] = i < n ? (i == 0 ? r0 : inv) : 0.0;
+    }
+    fx_tile_sum(v, fw.slot[3], sh, fw.flags);
+    fx_tile_sum(cv, fw.slot[4], sh, fw.flags);
+    grid.sync();
+    FxTile tc = fx_classify(v, fw.slot[3], sh, rel);
+    FxTile tr = fx_classify(cv, fw.slot[4], sh, rel);
+    grid.sync();
+    double c[FX_ITEMS], r[FX_ITEMS];
+    fx_chain(fw.slot[3], nt, FxValW2{d.w, S2}, n, sh, fw.flags);
+    fx_emit(v, tc, sh, FxValW2{d.w, S2}, n, rel, c, fw.flags, d.cum);
+    fx_chain(fw.slot[4], nt, FxValComb{r0, inv}, n, sh, fw.flags);
+    fx_emit(cv, tr, sh, FxValComb{r0, inv}, n, rel, r, fw.flags, d.rcomb);
+#pragma unroll
+    for (int k = 0; k < FX_ITEMS; ++k) { size_t i = first + k; if (i < n) { d.cum[i] = c[k]; d.rcomb[i] = r[k]; } }
+    // the index walk (fs1.rs:224-226) and the pose clone (fs1.rs:227-229) need every slice of cum: they run in the
+    // next, full-occupancy launch (fs_search_pose_kernel), gated on *d.gate
+}

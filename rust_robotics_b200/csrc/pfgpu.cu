@@ -4,9 +4,13 @@
 #include "xsum.cuh"
 #include "pf_kernels.cuh"
 #include "fs_kernels.cuh"
+#include "fs_post.cuh"
+#include "fs_sharded.cuh"
+#include <cstdlib>
 #include <new>
 #include <vector>
 #include <cmath>
+#include <algorithm>
 
 thread_local char g_pfgpu_err[512] = {0};
 
@@ -47,9 +51,18 @@ static int ctx_open(Ctx& ctx, int device) {
 }
 
 #define PF_MARK_SLOTS 16384
+__global__ void pf_l2_read_kernel(const double4* __restrict__ p, size_t n4, double* sink) {
+    double acc = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        double4 v = p[i];
+        acc += v.x + v.y + v.z + v.w;
+    }
+    if (acc == 123.456) *sink = acc;      // never true: keeps the loads alive
+}
 struct Marks {
     std::vector<cudaEvent_t> ev = std::vector<cudaEvent_t>(PF_MARK_SLOTS, nullptr);
     void* l2buf = nullptr;
+    void* l2buf_rd = nullptr;
     size_t l2bytes = (size_t)256 << 20;      // > 126 MB L2
 };
 static int marks_mark(Ctx& ctx, Marks& m, int slot) {
@@ -67,13 +80,21 @@ static int marks_elapsed(Marks& m, int a, int b, double* ms) {
     return 0;
 }
 static int marks_flush(Ctx& ctx, Marks& m) {
-    if (!m.l2buf) PF_CUDA(cudaMalloc(&m.l2buf, m.l2bytes));
+    if (!m.l2buf) {
+        PF_CUDA(cudaMalloc(&m.l2buf, m.l2bytes));
+        PF_CUDA(cudaMalloc(&m.l2buf_rd, m.l2bytes));
+        PF_CUDA(cudaMemsetAsync(m.l2buf_rd, 0, m.l2bytes, ctx.stream));
+    }
+    // write a buffer larger than L2 (evicts everything), then stream a second one through it so that the cache is left
+    // full of CLEAN lines: the timed kernel then starts cold without inheriting the flush's own write-backs
     PF_CUDA(cudaMemsetAsync(m.l2buf, 0, m.l2bytes, ctx.stream));
-    return 0;
+    pf_l2_read_kernel<<<ctx.num_sms * 8, 256, 0, ctx.stream>>>((const double4*)m.l2buf_rd, m.l2bytes / 32, (double*)m.l2buf);
+    return cudaGetLastError() == cudaSuccess ? 0 : PFGPU_ERR_CUDA;
 }
 static void marks_free(Marks& m) {
     for (auto e : m.ev) if (e) cudaEventDestroy(e);
     if (m.l2buf) cudaFree(m.l2buf);
+    if (m.l2buf_rd) cudaFree(m.l2buf_rd);
 }
 
 struct KernelTimer {
@@ -454,6 +475,13 @@ static void timer_drain(KernelTimer& t) {
     }
     t.pending.clear();
 }
+static int read_fx_flags(FxWork& fx, bool on, pfgpu_stats* s) {
+    if (!on) return 0;
+    int f[4] = {0, 0, 0, 0};
+    PF_CUDA(cudaMemcpy(f, fx.flags, 4 * sizeof(int), cudaMemcpyDeviceToHost));
+    s->serial_fallbacks += (uint64_t)f[1] + (uint64_t)f[2];
+    return 0;
+}
 static int read_xs_flags(Ctx& ctx, XsWork& xs, pfgpu_stats* s) {
     int f[4] = {0, 0, 0, 0};
     PF_CUDA(cudaMemcpy(f, xs.flags + 4, 4 * sizeof(int), cudaMemcpyDeviceToHost));
@@ -502,6 +530,11 @@ struct pfgpu_fs {
     double* h_pin = nullptr;
     FsObsDev* h_obs = nullptr;     // pinned staging for the observation list
     size_t lm_bytes = 0;
+    FxWork fx;                     // workspace of the fused post-step kernel
+    bool fused_post = false;
+    unsigned fx_nt = 0;
+    bool step_v2 = true;           // observation-parallel step kernel (PFGPU_STEP_V2=0 selects the one-thread-per-particle form)
+    FsShard sh;                    // multi-GPU state (world == 1: unused)
 };
 
 extern "C" void pfgpu_fs_default_config(pfgpu_fs_config* c) {            // fs1.rs:13-23
@@ -509,17 +542,18 @@ extern "C" void pfgpu_fs_default_config(pfgpu_fs_config* c) {            // fs1.
     c->init_weight = 1.0 / 100.0;
 }
 
-extern "C" int pfgpu_fs_create(const pfgpu_fs_config* cfg, size_t n, size_t m, uint64_t seed, int device, pfgpu_fs** out) {
+static int fs_create_impl(const pfgpu_fs_config* cfg, size_t n, size_t n_global, size_t offset, size_t m, uint64_t seed, int device,
+                          const void* uid, int rank, int world, pfgpu_fs** out) {
     if (!out) return PFGPU_ERR_INVALID;
     *out = nullptr;
-    if (!cfg || n == 0 || n > 0xFFFFFFFFull) return PFGPU_ERR_INVALID;
+    if (!cfg || n == 0 || n_global > 0xFFFFFFFFull) return PFGPU_ERR_INVALID;
     pfgpu_fs* h = new (std::nothrow) pfgpu_fs();
     if (!h) return PFGPU_ERR_CUDA;
     int rc = ctx_open(h->ctx, device);
     if (rc) { delete h; return rc; }
-    h->cfg = *cfg; h->seed = seed;
+    h->cfg = *cfg; h->seed = seed; h->world = world; h->rank = rank;
     FsDev& d = h->d;
-    d.n = d.n_global = n; d.offset = 0; d.m = m;
+    d.n = n; d.n_global = n_global; d.offset = offset; d.m = m; d.eager = world > 1 ? 1 : 0;
     h->lm_bytes = (m ? m : 1) * 6 * n * sizeof(double);
     auto fail = [&](int code) { pfgpu_fs_destroy(h); return code; };
 #define FS_TRY(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { snprintf(g_pfgpu_err, sizeof(g_pfgpu_err), "%s -> %s", #x, cudaGetErrorString(e__)); return fail(PFGPU_ERR_CUDA); } } while (0)
@@ -533,6 +567,9 @@ extern "C" int pfgpu_fs_create(const pfgpu_fs_config* cfg, size_t n, size_t m, u
     FS_TRY(cudaMalloc(&d.idx, n * sizeof(uint32_t)));
     FS_TRY(cudaMalloc(&d.scal, 16 * sizeof(double))); FS_TRY(cudaMemset(d.scal, 0, 16 * sizeof(double)));
     FS_TRY(cudaMalloc(&d.gate, sizeof(int))); FS_TRY(cudaMemset(d.gate, 0, sizeof(int)));
+    for (int b = 0; b < 2; ++b) FS_TRY(cudaMalloc(&d.anc[b], (m ? m : 1) * n * sizeof(uint32_t)));
+    FS_TRY(cudaMalloc(&d.anc_cur, sizeof(int))); FS_TRY(cudaMemset(d.anc_cur, 0, sizeof(int)));
+    FS_TRY(cudaMalloc(&d.lmstate, (m ? m : 1) * sizeof(int)));
     FS_TRY(cudaMalloc(&d.counters, 4 * sizeof(unsigned int))); FS_TRY(cudaMemset(d.counters, 0, 4 * sizeof(unsigned int)));
     h->obs_cap = FS_MAX_OBS;
     FS_TRY(cudaMalloc(&d.obs, h->obs_cap * sizeof(FsObsDev)));
@@ -544,15 +581,66 @@ extern "C" int pfgpu_fs_create(const pfgpu_fs_config* cfg, size_t n, size_t m, u
 #undef FS_TRY
     rc = xs_work_alloc(h->xs, n);
     if (rc) return fail(rc);
+    { const char* e2 = getenv("PFGPU_STEP_V2"); h->step_v2 = !(e2 && e2[0] == '0'); }
+    {   // fused post-step kernel: usable when one co-resident wave covers all tiles
+        unsigned nt = cdiv_u(n, FX_TILE);
+        int nb = 0;
+        const char* env = getenv("PFGPU_FUSED_POST");
+        bool want = !(env && env[0] == '0') && world == 1;
+        if (want && nt <= FX_MAX_TILES &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fs_post_kernel, XS_NT, 0) == cudaSuccess &&
+            (size_t)nb * (size_t)h->ctx.num_sms >= nt) {
+            int coop = 0;
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+            if (coop) {
+                bool okalloc = true;
+                for (int sl = 0; sl < FX_SLOTS && okalloc; ++sl) {
+                    okalloc = cudaMalloc(&h->fx.slot[sl].tsum, nt * sizeof(double)) == cudaSuccess &&
+                              cudaMalloc(&h->fx.slot[sl].ttail, nt * sizeof(xs_t)) == cudaSuccess &&
+                              cudaMalloc(&h->fx.slot[sl].tnd, nt * sizeof(int)) == cudaSuccess &&
+                              cudaMalloc(&h->fx.slot[sl].ent, (size_t)nt * XS_MAXD * sizeof(XsEntry)) == cudaSuccess;
+                }
+                okalloc = okalloc && cudaMalloc(&h->fx.flags, 8 * sizeof(int)) == cudaSuccess &&
+                          cudaMemset(h->fx.flags, 0, 8 * sizeof(int)) == cudaSuccess;
+                if (!okalloc) return fail(PFGPU_ERR_CUDA);
+                h->fused_post = true; h->fx_nt = nt;
+            }
+        }
+    }
+    if (world > 1) {
+        FsShard& sh = h->sh;
+        sh.rank = rank; sh.world = world;
+        ncclUniqueId id;
+        memcpy(&id, uid, sizeof(id));
+        ncclResult_t nr = ncclCommInitRank(&sh.comm, world, id, rank);
+        if (nr != ncclSuccess) { snprintf(g_pfgpu_err, sizeof(g_pfgpu_err), "ncclCommInitRank: %s", ncclGetErrorString(nr)); return fail(PFGPU_ERR_NCCL); }
+#define SH_TRY(x) do { if ((x) != cudaSuccess) { snprintf(g_pfgpu_err, sizeof(g_pfgpu_err), "%s failed", #x); return fail(PFGPU_ERR_CUDA); } } while (0)
+        SH_TRY(cudaMalloc(&sh.t_loc, sizeof(double))); SH_TRY(cudaMalloc(&sh.t_all, world * sizeof(double)));
+        SH_TRY(cudaMalloc(&sh.approx_off, sizeof(double))); SH_TRY(cudaMalloc(&sh.sum_loc, sizeof(ShardSummary)));
+        SH_TRY(cudaMalloc(&sh.sum_all, world * sizeof(ShardSummary))); SH_TRY(cudaMalloc(&sh.s_start, sizeof(double)));
+        SH_TRY(cudaMalloc(&sh.err, sizeof(int))); SH_TRY(cudaMemset(sh.err, 0, sizeof(int)));
+        SH_TRY(cudaMalloc(&sh.cum_all, n_global * sizeof(double))); SH_TRY(cudaMalloc(&sh.idx_all, n_global * sizeof(uint32_t)));
+        SH_TRY(cudaMalloc(&sh.pose_all, 3 * n_global * sizeof(double))); SH_TRY(cudaMallocHost(&sh.h_idx, n_global * sizeof(uint32_t)));
+        SH_TRY(cudaMalloc(&sh.best_loc, 8 * sizeof(double))); SH_TRY(cudaMalloc(&sh.best_all, 8 * world * sizeof(double)));
+#undef SH_TRY
+    }
     fs_init_kernel<<<cdiv_u(n, 256), 256, 0, h->ctx.stream>>>(d, cfg->init_weight);
-    h->ctx.launches++;
+    fs_lmstate_reset_kernel<<<1, 256, 0, h->ctx.stream>>>(d);
+    h->ctx.launches += 2;
     if (cudaStreamSynchronize(h->ctx.stream) != cudaSuccess) return fail(PFGPU_ERR_CUDA);
     *out = h;
     return PFGPU_OK;
 }
-extern "C" int pfgpu_fs_create_sharded(const pfgpu_fs_config*, size_t, size_t, uint64_t, int, const void*, int, int, pfgpu_fs** out) {
+extern "C" int pfgpu_fs_create(const pfgpu_fs_config* cfg, size_t n, size_t m, uint64_t seed, int device, pfgpu_fs** out) {
+    return fs_create_impl(cfg, n, n, 0, m, seed, device, nullptr, 0, 1, out);
+}
+extern "C" int pfgpu_fs_create_sharded(const pfgpu_fs_config* cfg, size_t n_global, size_t m, uint64_t seed, int device,
+                                       const void* uid, int rank, int world, pfgpu_fs** out) {
     if (out) *out = nullptr;
-    return PFGPU_ERR_UNSUPPORTED;
+    if (!uid || world < 1 || world > SH_MAX_WORLD || rank < 0 || rank >= world || n_global == 0 || n_global % (size_t)world != 0)
+        return PFGPU_ERR_INVALID;
+    size_t nl = n_global / (size_t)world;
+    return fs_create_impl(cfg, nl, n_global, (size_t)rank * nl, m, seed, device, uid, rank, world, out);
 }
 extern "C" void pfgpu_fs_destroy(pfgpu_fs* h) {
     if (!h) return;
@@ -562,6 +650,17 @@ extern "C" void pfgpu_fs_destroy(pfgpu_fs* h) {
     for (int b = 0; b < 2; ++b) { cudaFree(d.px[b]); cudaFree(d.py[b]); cudaFree(d.pyaw[b]); cudaFree(d.lm[b]); }
     cudaFree(d.cur); cudaFree(d.w); cudaFree(d.w_raw); cudaFree(d.cum); cudaFree(d.rcomb); cudaFree(d.idx); cudaFree(d.scal);
     cudaFree(d.gate); cudaFree(d.obs); cudaFree(d.best_w); cudaFree(d.best_i); cudaFree(d.counters);
+    cudaFree(d.anc[0]); cudaFree(d.anc[1]); cudaFree(d.anc_cur); cudaFree(d.lmstate);
+    for (int sl = 0; sl < FX_SLOTS; ++sl) { cudaFree(h->fx.slot[sl].tsum); cudaFree(h->fx.slot[sl].ttail); cudaFree(h->fx.slot[sl].tnd); cudaFree(h->fx.slot[sl].ent); }
+    cudaFree(h->fx.flags);
+    {
+        FsShard& sh = h->sh;
+        cudaFree(sh.t_loc); cudaFree(sh.t_all); cudaFree(sh.approx_off); cudaFree(sh.sum_loc); cudaFree(sh.sum_all); cudaFree(sh.s_start);
+        cudaFree(sh.err); cudaFree(sh.cum_all); cudaFree(sh.idx_all); cudaFree(sh.pose_all); cudaFree(sh.sendbuf); cudaFree(sh.recvbuf);
+        cudaFree(sh.best_loc); cudaFree(sh.best_all);
+        if (sh.h_idx) cudaFreeHost(sh.h_idx);
+        if (sh.comm) ncclCommDestroy(sh.comm);
+    }
     if (h->h_pin) cudaFreeHost(h->h_pin);
     if (h->h_obs) cudaFreeHost(h->h_obs);
     marks_free(h->marks);
@@ -605,6 +704,7 @@ extern "C" int pfgpu_fs_upload(pfgpu_fs* h, const double* pose_w, const double* 
             PF_LAUNCH(h->ctx, fs_unpack_lm_kernel, cdiv_u(cnt * d.m * 6, 256), 256, 0, d, tmp, i0, cnt);
             PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
         }
+        PF_LAUNCH(h->ctx, fs_lmstate_reset_kernel, 1, 256, 0, d);
         cudaFree(tmp);
     }
     return 0;
@@ -648,9 +748,99 @@ extern "C" int pfgpu_fs_seed_map(pfgpu_fs* h, const double pose3[3], const doubl
         PF_CUDA(cudaMemcpyAsync(dxy, lm_xy, m * 2 * sizeof(double), cudaMemcpyHostToDevice, h->ctx.stream));
         dim3 grid(cdiv_u(d.n, 256), (unsigned)m);
         PF_LAUNCH(h->ctx, fs_seed_lm_kernel, grid, 256, 0, d, dxy, sigma, cov0, h->seed);
+        PF_LAUNCH(h->ctx, fs_lmstate_reset_kernel, 1, 256, 0, d);
         PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
         cudaFree(dxy);
     }
+    return 0;
+}
+// Post-step pipeline of the sharded mode (see fs_sharded.cuh).  One host sync per step (the gate decides which
+// collectives follow; every rank computes the same gate from the same exact global sums).
+static int sh_grow(double** buf, size_t* cap, size_t need) {
+    if (need <= *cap) return 0;
+    if (*buf) cudaFree(*buf);
+    *cap = need + need / 4 + 1024;
+    PF_CUDA(cudaMalloc(buf, *cap * sizeof(double)));
+    return 0;
+}
+static int fs_post_sharded(pfgpu_fs* h) {
+    FsDev& d = h->d; FsShard& sh = h->sh; Ctx& ctx = h->ctx;
+    const size_t nl = d.n, ng = d.n_global, rows = 6 * d.m;
+    int rc = xs_total_sharded(ctx, h->xs, sh, XsValArray{d.w_raw}, nl, ng, d.scal + 0);              // fs1.rs:259
+    if (rc) return rc;
+    PF_LAUNCH(ctx, fs_normalize_kernel, cdiv_u(nl, 256), 256, 0, d);
+    rc = xs_total_sharded(ctx, h->xs, sh, FsValWSq{d.w}, nl, ng, d.scal + 1);                        // fs1.rs:262
+    if (rc) return rc;
+    PF_LAUNCH(ctx, fs_gate_kernel, 1, 1, 0, d, h->cfg.nth);
+    int* hp = reinterpret_cast<int*>(h->h_pin + 32);
+    PF_CUDA(cudaMemcpyAsync(hp, d.gate, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+    PF_CUDA(cudaMemcpyAsync(hp + 1, sh.err, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+    PF_CUDA(cudaStreamSynchronize(ctx.stream));
+    if (hp[1]) { snprintf(g_pfgpu_err, sizeof(g_pfgpu_err), "sharded exact sum: a shard was not summarisable (degenerate weights)"); return PFGPU_ERR_UNSUPPORTED; }
+    if (!*hp) return 0;
+    // ---------------- resample fs1.rs:206-234 ----------------
+    rc = xs_total_sharded(ctx, h->xs, sh, XsValArray{d.w}, nl, ng, d.scal + 2);                      // fs1.rs:207
+    if (!rc) rc = xs_scan_sharded(ctx, h->xs, sh, FsValWNorm2{d.w, d.scal, d.gate}, XsSinkStore{d.cum}, nl, ng, d.scal + 4);
+    if (rc) return rc;
+    PF_LAUNCH(ctx, fs_comb_kernel, 1, 1, 0, d, h->seed);
+    rc = xs_scan_sharded(ctx, h->xs, sh, FsValCombG{d.scal, 1.0 / (double)ng, d.offset}, XsSinkStore{d.rcomb}, nl, ng, d.scal + 5);
+    if (rc) return rc;
+    PF_NCCL(ncclAllGather(d.cum, sh.cum_all, nl, ncclDouble, sh.comm, ctx.stream));
+    PF_LAUNCH(ctx, sh_search_kernel, cdiv_u(nl, 256), 256, 0, d, sh.cum_all);
+    PF_NCCL(ncclAllGather(d.idx, sh.idx_all, nl, ncclUint32, sh.comm, ctx.stream));
+    // poses: everyone needs any ancestor's pose; 24 B per particle
+    rc = sh_grow(&sh.sendbuf, &sh.send_cap, 3 * nl);
+    if (rc) return rc;
+    PF_LAUNCH(ctx, sh_pack_pose_kernel, cdiv_u(nl, 256), 256, 0, d, sh.sendbuf);
+    PF_NCCL(ncclAllGather(sh.sendbuf, sh.pose_all, 3 * nl, ncclDouble, sh.comm, ctx.stream));
+    PF_LAUNCH(ctx, sh_gather_pose_kernel, cdiv_u(nl, 256), 256, 0, d, sh.pose_all);
+    // maps: contiguous runs of slots per (source, destination) pair
+    PF_CUDA(cudaMemcpyAsync(sh.h_idx, sh.idx_all, ng * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx.stream));
+    PF_CUDA(cudaMemcpyAsync(hp + 1, sh.err, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+    PF_CUDA(cudaStreamSynchronize(ctx.stream));
+    if (hp[1]) { snprintf(g_pfgpu_err, sizeof(g_pfgpu_err), "sharded exact scan: a shard was not summarisable (degenerate weights)"); return PFGPU_ERR_UNSUPPORTED; }
+    const int G = sh.world, me = sh.rank;
+    // slots [lo, hi) of destination block dst whose ancestor lives on rank src
+    auto run_of = [&](int dst, int src, size_t* lo, size_t* hi) {
+        const uint32_t* a = sh.h_idx + (size_t)dst * nl;
+        size_t b0 = std::lower_bound(a, a + nl, (uint32_t)((size_t)src * nl)) - a;
+        size_t b1 = std::lower_bound(a, a + nl, (uint32_t)((size_t)(src + 1) * nl)) - a;
+        if ((size_t)(src + 1) * nl > 0xFFFFFFFFull) b1 = nl;
+        *lo = (size_t)dst * nl + b0; *hi = (size_t)dst * nl + b1;
+    };
+    size_t send_tot = 0, recv_tot = 0;
+    size_t s_lo[SH_MAX_WORLD], s_hi[SH_MAX_WORLD], r_lo[SH_MAX_WORLD], r_hi[SH_MAX_WORLD];
+    for (int g = 0; g < G; ++g) {
+        s_lo[g] = s_hi[g] = r_lo[g] = r_hi[g] = 0;
+        if (g == me) continue;
+        run_of(g, me, &s_lo[g], &s_hi[g]);           // what I send to g
+        run_of(me, g, &r_lo[g], &r_hi[g]);           // what I receive from g
+        send_tot += (s_hi[g] - s_lo[g]) * rows; recv_tot += (r_hi[g] - r_lo[g]) * rows;
+    }
+    rc = sh_grow(&sh.sendbuf, &sh.send_cap, send_tot > 3 * nl ? send_tot : 3 * nl);
+    if (!rc) rc = sh_grow(&sh.recvbuf, &sh.recv_cap, recv_tot + 1);
+    if (rc) return rc;
+    ShRecvTable tab;
+    size_t soff[SH_MAX_WORLD], so = 0, ro = 0;
+    for (int g = 0; g < G; ++g) {
+        tab.t0[g] = r_lo[g]; tab.base[g] = ro; ro += (r_hi[g] - r_lo[g]) * rows;
+        soff[g] = so; so += (s_hi[g] - s_lo[g]) * rows;
+        size_t cnt = s_hi[g] - s_lo[g];
+        if (cnt && rows) PF_LAUNCH(ctx, sh_pack_map_kernel, cdiv_u(cnt * rows, 256), 256, 0, d, sh.idx_all, s_lo[g], cnt, me, sh.sendbuf + soff[g]);
+    }
+    if (rows) {
+        PF_NCCL(ncclGroupStart());
+        for (int g = 0; g < G; ++g) {
+            if (g == me) continue;
+            size_t sc = (s_hi[g] - s_lo[g]) * rows, rcn = (r_hi[g] - r_lo[g]) * rows;
+            if (sc) PF_NCCL(ncclSend(sh.sendbuf + soff[g], sc, ncclDouble, g, sh.comm, ctx.stream));
+            if (rcn) PF_NCCL(ncclRecv(sh.recvbuf + tab.base[g], rcn, ncclDouble, g, sh.comm, ctx.stream));
+        }
+        PF_NCCL(ncclGroupEnd());
+        dim3 grid(cdiv_u(nl, 256), cdiv_u(rows, 16));
+        PF_LAUNCH(ctx, sh_clone_map_kernel, grid, 256, 0, d, sh.recvbuf, tab, me);
+    }
+    PF_LAUNCH(ctx, sh_flip_kernel, 1, 256, 0, d);
     return 0;
 }
 extern "C" int pfgpu_fs_step(pfgpu_fs* h, const double u[2], const pfgpu_fs_obs* z, size_t k, int* did) {
@@ -663,26 +853,72 @@ extern "C" int pfgpu_fs_step(pfgpu_fs* h, const double u[2], const pfgpu_fs_obs*
         if (z[j].lm_id >= d.m) return PFGPU_ERR_INVALID;             // the reference would panic on the Vec index (fs1.rs:141)
     }
     PF_CUDA(cudaSetDevice(h->ctx.device));
-    const bool param = k <= FS_PARAM_OBS;
-    FsObsParam po;
-    if (param) {
-        for (size_t j = 0; j < k; ++j) { po.o[j].d = z[j].d; po.o[j].angle = z[j].angle; po.o[j].lm_id = (int)z[j].lm_id; po.o[j].pad = 0; }
-    } else {
-        // long lists go through one pinned staging slot: wait until the previous step's copy has left it
-        PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
-        for (size_t j = 0; j < k; ++j) { h->h_obs[j].d = z[j].d; h->h_obs[j].angle = z[j].angle; h->h_obs[j].lm_id = (int)z[j].lm_id; h->h_obs[j].pad = 0; }
-        PF_CUDA(cudaMemcpyAsync(d.obs, h->h_obs, k * sizeof(FsObsDev), cudaMemcpyHostToDevice, h->ctx.stream));
+    // The lazy-clone bookkeeping (lmstate) is per launch, so one launch must not see the same lm_id twice: the list is
+    // cut before every repeated id and the pieces run as consecutive launches (same per-particle order as fs1.rs:250-256).
+    std::vector<size_t> cuts;
+    cuts.push_back(0);
+    {
+        std::vector<uint64_t> seen;
+        for (size_t j = 0; j < k; ++j) {
+            bool dup = false;
+            for (uint64_t v : seen) if (v == z[j].lm_id) { dup = true; break; }
+            if (dup) { cuts.push_back(j); seen.clear(); }
+            seen.push_back(z[j].lm_id);
+        }
     }
+    cuts.push_back(k);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->timer.on) { PF_CUDA(cudaEventCreate(&e0)); PF_CUDA(cudaEventCreate(&e1)); PF_CUDA(cudaEventRecord(e0, h->ctx.stream)); }
-    if (param)
-        PF_LAUNCH(h->ctx, fs_step_kernel<true>, cdiv_u(d.n, FS_NT), FS_NT, (k ? k : 1) * sizeof(FsObsDev), d, po, u[0], u[1], h->cfg.dt,
-                  sqrt(h->cfg.q00), sqrt(h->cfg.q11), h->cfg.r00, h->cfg.r11, h->seed, h->n_step, (int)k);
-    else
-        PF_LAUNCH(h->ctx, fs_step_kernel<false>, cdiv_u(d.n, FS_NT), FS_NT, (k ? k : 1) * sizeof(FsObsDev), d, po, u[0], u[1], h->cfg.dt,
-                  sqrt(h->cfg.q00), sqrt(h->cfg.q11), h->cfg.r00, h->cfg.r11, h->seed, h->n_step, (int)k);
+    for (size_t seg = 0; seg + 1 < cuts.size(); ++seg) {
+        const size_t j0 = cuts[seg], kk = cuts[seg + 1] - cuts[seg];
+        const int do_predict = seg == 0 ? 1 : 0;
+        const bool param = kk <= FS_PARAM_OBS;
+        FsObsParam po;
+        if (param) {
+            for (size_t j = 0; j < kk; ++j) { po.o[j].d = z[j0 + j].d; po.o[j].angle = z[j0 + j].angle; po.o[j].lm_id = (int)z[j0 + j].lm_id; po.o[j].pad = 0; }
+            if (h->step_v2 && kk <= FS2_MAX_OBS) {
+                // observation-parallel form: predict at full occupancy, then 32 particles x kk warps per CTA
+                if (do_predict)
+                    PF_LAUNCH(h->ctx, fs_predict_kernel, cdiv_u(d.n, 256), 256, 0, d, u[0], u[1], h->cfg.dt, sqrt(h->cfg.q00),
+                              sqrt(h->cfg.q11), h->seed, h->n_step);
+                if (kk) {
+                    size_t smem = kk * 32 * sizeof(double) + kk * sizeof(unsigned) + 8;
+                    PF_LAUNCH(h->ctx, fs_ekf_kernel<true>, cdiv_u(d.n, 32), (unsigned)(32 * kk), smem, d, po, h->cfg.r00, h->cfg.r11, (int)kk);
+                }
+            } else
+            PF_LAUNCH(h->ctx, fs_step_kernel<true>, cdiv_u(d.n, FS_NT), FS_NT, (kk ? kk : 1) * sizeof(FsObsDev), d, po, u[0], u[1], h->cfg.dt,
+                      sqrt(h->cfg.q00), sqrt(h->cfg.q11), h->cfg.r00, h->cfg.r11, h->seed, h->n_step, (int)kk, do_predict);
+            if (kk) PF_LAUNCH(h->ctx, fs_lmstate_after_step_kernel<true>, 1, 64, 0, d, po, (int)kk);
+        } else {
+            // long lists go through one pinned staging slot: wait until the previous copy has left it
+            PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+            for (size_t j = 0; j < kk; ++j) { h->h_obs[j].d = z[j0 + j].d; h->h_obs[j].angle = z[j0 + j].angle; h->h_obs[j].lm_id = (int)z[j0 + j].lm_id; h->h_obs[j].pad = 0; }
+            PF_CUDA(cudaMemcpyAsync(d.obs, h->h_obs, kk * sizeof(FsObsDev), cudaMemcpyHostToDevice, h->ctx.stream));
+            PF_LAUNCH(h->ctx, fs_step_kernel<false>, cdiv_u(d.n, FS_NT), FS_NT, kk * sizeof(FsObsDev), d, po, u[0], u[1], h->cfg.dt,
+                      sqrt(h->cfg.q00), sqrt(h->cfg.q11), h->cfg.r00, h->cfg.r11, h->seed, h->n_step, (int)kk, do_predict);
+            PF_LAUNCH(h->ctx, fs_lmstate_after_step_kernel<false>, 1, 64, 0, d, po, (int)kk);
+        }
+    }
     if (h->timer.on) { PF_CUDA(cudaEventRecord(e1, h->ctx.stream)); h->timer.pending.push_back({e0, e1}); }
     h->n_step++;
+    if (h->world > 1) {
+        int rcs = fs_post_sharded(h);
+        if (rcs) return rcs;
+        h->steps++;
+        if (did) {
+            int* hp = reinterpret_cast<int*>(h->h_pin + 32);
+            *did = *hp;                                   // fs_post_sharded already brought the gate to the host
+        }
+        return 0;
+    }
+    if (h->fused_post) {
+        // normalise, N_eff gate and (when it opens) the whole index computation + pose clone: one cooperative launch
+        double nth = h->cfg.nth; uint64_t seed = h->seed; unsigned nt = h->fx_nt; double rel = xs_margin(d.n_global);
+        void* args[] = { (void*)&d, (void*)&h->fx, (void*)&nth, (void*)&seed, (void*)&nt, (void*)&rel };
+        PF_CUDA(cudaLaunchCooperativeKernel((void*)fs_post_kernel, dim3(nt), dim3(XS_NT), args, 0, h->ctx.stream));
+        h->ctx.launches++;
+        PF_LAUNCH(h->ctx, fs_search_pose_kernel, cdiv_u(d.n, 256), 256, 0, d);
+    } else {
     // normalize_weights fs1.rs:259
     int rc = xs_total(h->ctx, h->xs, XsValArray{d.w_raw}, d.n, d.n_global, 0.0, d.scal + 0);
     if (rc) return rc;
@@ -703,11 +939,12 @@ extern "C" int pfgpu_fs_step(pfgpu_fs* h, const double u[2], const pfgpu_fs_obs*
     if (rc) return rc;
     PF_LAUNCH(h->ctx, fs_search_kernel, cdiv_u(d.n, 256), 256, 0, d);
     PF_LAUNCH(h->ctx, fs_gather_pose_kernel, cdiv_u(d.n, 256), 256, 0, d);
-    if (d.m) {
-        dim3 grid(cdiv_u(d.n, 256), cdiv_u(6 * d.m, FS_GATHER_ROWS));
-        PF_LAUNCH(h->ctx, fs_gather_lm_kernel, grid, 256, 0, d);
     }
-    PF_LAUNCH(h->ctx, fs_flip_kernel, 1, 1, 0, d);
+    if (d.m) {
+        dim3 grid(cdiv_u(d.n, 256), cdiv_u(d.m, FS_COMPOSE_ROWS));
+        PF_LAUNCH(h->ctx, fs_compose_anc_kernel, grid, 256, 0, d);      // lazy clone: ancestry columns instead of the map
+    }
+    PF_LAUNCH(h->ctx, fs_flip_kernel, 1, 256, 0, d);
     h->steps++;
     if (did) {     // the gate and the resample draw counter live on the device; only a caller who asks pays a sync
         int* hp = reinterpret_cast<int*>(h->h_pin + 32);
@@ -730,15 +967,30 @@ extern "C" int pfgpu_fs_best(pfgpu_fs* h, size_t* index, double pose_w4[4]) {
     size_t bi = 0; double bw = -1.0; bool have = false;
     for (int b = 0; b < h->best_blocks; ++b)
         if (!have || hw[b] > bw || (hw[b] == bw && hi[b] > bi)) { bw = hw[b]; bi = (size_t)hi[b]; have = true; }
-    if (index) *index = d.offset + bi;
-    if (pose_w4) {
+    double pw[4] = {bw, 0.0, 0.0, 0.0};
+    if (pose_w4 || h->world > 1) {
         int cur = 0;
         PF_CUDA(cudaMemcpy(&cur, d.cur, sizeof(int), cudaMemcpyDeviceToHost));
-        pose_w4[0] = bw;
-        PF_CUDA(cudaMemcpy(&pose_w4[1], d.px[cur] + bi, sizeof(double), cudaMemcpyDeviceToHost));
-        PF_CUDA(cudaMemcpy(&pose_w4[2], d.py[cur] + bi, sizeof(double), cudaMemcpyDeviceToHost));
-        PF_CUDA(cudaMemcpy(&pose_w4[3], d.pyaw[cur] + bi, sizeof(double), cudaMemcpyDeviceToHost));
+        PF_CUDA(cudaMemcpy(&pw[1], d.px[cur] + bi, sizeof(double), cudaMemcpyDeviceToHost));
+        PF_CUDA(cudaMemcpy(&pw[2], d.py[cur] + bi, sizeof(double), cudaMemcpyDeviceToHost));
+        PF_CUDA(cudaMemcpy(&pw[3], d.pyaw[cur] + bi, sizeof(double), cudaMemcpyDeviceToHost));
     }
+    size_t gi = d.offset + bi;
+    if (h->world > 1) {     // every rank contributes its shard's best; the LAST maximum in global order wins (fs1.rs:269-274)
+        FsShard& sh = h->sh;
+        double loc[8] = {pw[0], (double)gi, pw[1], pw[2], pw[3], 0.0, 0.0, 0.0};
+        PF_CUDA(cudaMemcpyAsync(sh.best_loc, loc, sizeof(loc), cudaMemcpyHostToDevice, h->ctx.stream));
+        PF_NCCL(ncclAllGather(sh.best_loc, sh.best_all, 8, ncclDouble, sh.comm, h->ctx.stream));
+        std::vector<double> all(8 * (size_t)sh.world);
+        PF_CUDA(cudaMemcpyAsync(all.data(), sh.best_all, all.size() * sizeof(double), cudaMemcpyDeviceToHost, h->ctx.stream));
+        PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+        int bg = 0;
+        for (int g = 1; g < sh.world; ++g) if (all[8 * g] >= all[8 * bg]) bg = g;
+        gi = (size_t)all[8 * bg + 1];
+        pw[0] = all[8 * bg]; pw[1] = all[8 * bg + 2]; pw[2] = all[8 * bg + 3]; pw[3] = all[8 * bg + 4];
+    }
+    if (index) *index = gi;
+    if (pose_w4) for (int a = 0; a < 4; ++a) pose_w4[a] = pw[a];
     return 0;
 }
 extern "C" int pfgpu_fs_particle_landmarks(pfgpu_fs* h, size_t il, double* lm6) {
@@ -781,7 +1033,9 @@ extern "C" int pfgpu_fs_stats(pfgpu_fs* h, pfgpu_stats* s) {
     PF_CUDA(cudaMemcpy(&cnt, h->d.counters, sizeof(unsigned int), cudaMemcpyDeviceToHost));
     s->kernel_launches = h->ctx.launches; s->steps = h->steps; s->resamples = cnt;
     s->main_kernel_ms_sum = h->timer.ms_sum; s->main_kernel_count = h->timer.count;
-    return read_xs_flags(h->ctx, h->xs, s);
+    int rcx = read_xs_flags(h->ctx, h->xs, s);
+    if (rcx) return rcx;
+    return read_fx_flags(h->fx, h->fused_post, s);
 }
 extern "C" int pfgpu_fs_time_main_kernel(pfgpu_fs* h, int on) {
     if (!h) return PFGPU_ERR_INVALID;
@@ -799,7 +1053,14 @@ extern "C" int pfgpu_fs_elapsed_ms(pfgpu_fs* h, int a, int b, double* ms) { if (
 extern "C" int pfgpu_pf_flush_l2(pfgpu_pf* h) { if (!h) return PFGPU_ERR_INVALID; PF_CUDA(cudaSetDevice(h->ctx.device)); return marks_flush(h->ctx, h->marks); }
 extern "C" int pfgpu_fs_flush_l2(pfgpu_fs* h) { if (!h) return PFGPU_ERR_INVALID; PF_CUDA(cudaSetDevice(h->ctx.device)); return marks_flush(h->ctx, h->marks); }
 
-extern "C" int pfgpu_nccl_unique_id(void* out128) { (void)out128; return PFGPU_ERR_UNSUPPORTED; }
+extern "C" int pfgpu_nccl_unique_id(void* out128) {
+    if (!out128) return PFGPU_ERR_INVALID;
+    ncclUniqueId id;
+    PF_NCCL(ncclGetUniqueId(&id));
+    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(out128, &id, sizeof(id));
+    return 0;
+}
 
 // ====================================================================================================
 // test hook: the exact scan on an arbitrary host array (used by tests/test_gpu_xsum.py)

@@ -8,7 +8,7 @@
 // Pipeline (tiles of XS_TILE = 256 threads x 8 consecutive values):
 //   A  xs_tile_sums      approximate tile sums (tree order)                         read 8 B/value
 //   B  xs_scan_tiles     exclusive scan of the tile sums (1 CTA)                    tiny
-//   C  xs_classify_tiles per value: clean (2-state integer transducer) or dirty (needs a real FP add);
+//   C  xs_classify_tiles per value: clean (an integer mantissa increment) or dirty (needs a real FP add);
 //                        segmented transducer scan inside the tile -> tile aggregate + its dirty entries
 //                                                                                   read 8 B/value
 //   D  xs_chain          segmented scan of tile aggregates (parallel), then ONE thread applies the
@@ -28,7 +28,7 @@
 #define XS_CHAIN_NT 256
 #define XS_CHUNK  1024
 
-struct __align__(8) XsEntry { long long d0, d1; int lvl; int pad; double v; };
+struct __align__(8) XsEntry { long long inc; int lvl; int pad; double v; };
 struct XsSeg { xs_t t; int flag; };
 
 struct XsWork {
@@ -47,6 +47,8 @@ struct XsWork {
                                // [4] cumulative serial fallbacks  [5] dirty total of the last chain  [6] cumulative emit failures
                                // [7] cumulative overflow tiles (walked serially, still exact)
     double  approx_offset = 0.0;   // approximate sum of everything before this shard (multi-GPU)
+    const double* approx_offset_ptr = nullptr;   // ... or the same on the device (sharded mode)
+    const double* s_start_ptr = nullptr;         // exact prefix at the shard start, on the device (sharded mode)
     const int* gate = nullptr;     // device flag: when non-null and 0, every kernel of the pipeline returns at once
 };
 #define XS_GATE(w) do { if ((w).gate != nullptr && *(w).gate == 0) return; } while (0)
@@ -84,8 +86,7 @@ __device__ __forceinline__ XsSeg xs_seg_op(const XsSeg a, const XsSeg b) {   // 
 }
 __device__ __forceinline__ XsSeg xs_seg_shfl_up(const XsSeg s, int o) {
     XsSeg r;
-    r.t.d0 = __shfl_up_sync(0xffffffffu, s.t.d0, o);
-    r.t.d1 = __shfl_up_sync(0xffffffffu, s.t.d1, o);
+    r.t.inc = __shfl_up_sync(0xffffffffu, s.t.inc, o);
     r.t.lvl = __shfl_up_sync(0xffffffffu, s.t.lvl, o);
     r.flag = __shfl_up_sync(0xffffffffu, s.flag, o);
     return r;
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(1024) xs_scan_tiles(unsigned nt, XsWork w) {
     __shared__ double sm[32];
     __shared__ double carry_s;
     XS_GATE(w);
-    if (threadIdx.x == 0) { carry_s = w.approx_offset; w.flags[0] = w.flags[3]; w.flags[1] = 0; w.flags[2] = 0; }
+    if (threadIdx.x == 0) { carry_s = w.approx_offset_ptr ? *w.approx_offset_ptr : w.approx_offset; w.flags[0] = w.flags[3]; w.flags[1] = 0; w.flags[2] = 0; }
     __syncthreads();
     for (unsigned base = 0; base < nt; base += 1024) {
         unsigned b = base + threadIdx.x;
@@ -163,11 +164,12 @@ __global__ void __launch_bounds__(1024) xs_scan_tiles(unsigned nt, XsWork w) {
 // per-thread pass over its XS_ITEMS values: counts dirty values and builds the tail transducer.
 // a0 = approximate prefix before the thread's first value.  Must be evaluated IDENTICALLY in C and E.
 struct XsThreadScan { xs_t tail; int nd; };
-__device__ __forceinline__ XsThreadScan xs_thread_scan(const double (&v)[XS_ITEMS], double toff, double excl, double rel) {
+template <int ITEMS>
+__device__ __forceinline__ XsThreadScan xs_thread_scan(const double (&v)[ITEMS], double toff, double excl, double rel) {
     XsThreadScan r; r.tail = xs_identity(); r.nd = 0;
     double running = 0.0, a_prev = toff + excl;
 #pragma unroll
-    for (int k = 0; k < XS_ITEMS; ++k) {
+    for (int k = 0; k < ITEMS; ++k) {
         running += v[k];
         double a_cur = toff + (excl + running);
         xs_t t;
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(XS_NT) xs_classify_tiles(F f, size_t n, double
             if (xs_classify(v[k], a_prev, a_cur, rel, &t)) run = xs_compose(run, t);
             else {
                 if (slot < XS_MAXD) {
-                    XsEntry e; e.d0 = run.d0; e.d1 = run.d1; e.lvl = run.lvl; e.pad = 0; e.v = v[k];
+                    XsEntry e; e.inc = run.inc; e.lvl = run.lvl; e.pad = 0; e.v = v[k];
                     w.ent[(size_t)b * XS_MAXD + slot] = e;
                 }
                 slot++;
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(XS_NT) xs_classify_tiles(F f, size_t n, double
     }
     if (threadIdx.x == 0) {
         if (overflow) {
-            XsEntry e; e.d0 = 0; e.d1 = 0; e.lvl = XS_EMPTY; e.pad = 1; e.v = 0.0;
+            XsEntry e; e.inc = 0; e.lvl = XS_EMPTY; e.pad = 1; e.v = 0.0;
             w.ent[(size_t)b * XS_MAXD] = e;
             w.ttail[b] = xs_identity();
             w.tnd[b] = -1;
@@ -291,9 +293,9 @@ __global__ void __launch_bounds__(XS_CHAIN_NT) xs_chain(F f, size_t n, unsigned 
                     if (o < 0 || o >= XS_CHUNK) continue;
                     XsEntry en = w.ent[(size_t)b * XS_MAXD + e];
                     if (e == 0) {
-                        xs_t r; r.d0 = en.d0; r.d1 = en.d1; r.lvl = en.lvl;
+                        xs_t r; r.inc = en.inc; r.lvl = en.lvl;
                         r = xs_compose(tinb, r);
-                        en.d0 = r.d0; en.d1 = r.d1; en.lvl = r.lvl;
+                        en.inc = r.inc; en.lvl = r.lvl;
                     }
                     if (en.pad == 1) en.v = (double)b;      // overflow marker carries its tile index
                     sm_ent[o] = en;
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(XS_CHAIN_NT) xs_chain(F f, size_t n, unsigned 
                 double s = s_run; int ok = 1;
                 int cnt = D - cbase < XS_CHUNK ? D - cbase : XS_CHUNK;
                 for (int o = 0; o < cnt; ++o) {
-                    xs_t r; r.d0 = sm_ent[o].d0; r.d1 = sm_ent[o].d1; r.lvl = sm_ent[o].lvl;
+                    xs_t r; r.inc = sm_ent[o].inc; r.lvl = sm_ent[o].lvl;
                     s = xs_apply(r, s, &ok);
                     if (sm_ent[o].pad == 1) {               // overflow tile: walk it with genuine FP adds
                         unsigned b = (unsigned)sm_ent[o].v;
@@ -381,7 +383,7 @@ __global__ void __launch_bounds__(XS_NT) xs_emit_tiles(F f, S sink, size_t n, do
     carry = xs_seg_op(xs_seg_make(w.tin[b], 0), carry);
     int ndtot;
     int ord = w.tdoff[b] + block_excl_scan_int<XS_NT>(ts.nd, &ndtot, sm_i);
-    double base_s = ord > 0 ? w.s_after[ord - 1] : s_start;
+    double base_s = ord > 0 ? w.s_after[ord - 1] : (w.s_start_ptr ? *w.s_start_ptr : s_start);
     xs_t run = carry.t;
     double running = 0.0, a_prev = toff + excl;
     int ok = 1;

@@ -15,17 +15,17 @@
  * c = m*u with an integer mantissa m.  Then
  *       fl(c + v) = (m + q + round_bit) * u,   v = q*u + f, 0 <= f < u,
  *       round_bit = [f > u/2] + [f == u/2 and (m + q) odd]          (round-half-to-even)
- * i.e. adding v is an integer increment d(p) that depends on the state only through the PARITY p of m.
- * An element is therefore a 2-state transducer (d(0), d(1)); transducers compose associatively:
- *       (A then B)(p) = A(p) + B(p xor (A(p) & 1))
- * so any run of elements that provably stays inside one level is summed EXACTLY by an ordinary parallel
- * scan over pairs of int64, and is applied to an exact double by adding d(p) to its raw bit pattern.
+ * Unless f is EXACTLY u/2 (a tie), adding v is the integer increment q + [f > u/2] of the mantissa, independent of the
+ * state.  So any run of tie-free elements that provably stays inside one level is summed EXACTLY by an ordinary
+ * parallel prefix sum over int64 increments, and is applied to an exact double by adding the increment to its raw
+ * bit pattern.  (A tie would need the parity of m; ties are rare — the bits of v below u must be exactly 100...0 —
+ * and are simply treated like the other "dirty" elements below.)
  *
  * Which level an element sees is decided from an APPROXIMATE prefix sum a_i (plain parallel scan) with a
  * rigorous margin: |c_i - a_i| <= rel * a_i for every summation order of n non-negative terms, rel =
  * 4(n+64)2^-53.  Elements whose approximate prefix (before or after the add) comes within the margin of a
- * level edge are "dirty": they are applied with one genuine FP add, in order, by a short sequential chain
- * (there are ~log2(n) + a few of them).  Everything else is "clean" and goes through the scan.
+ * level edge, and ties, are "dirty": they are applied with one genuine FP add, in order, by a short sequential
+ * chain (there are ~log2(n) + a few of them).  Everything else is "clean" and goes through the scan.
  */
 #ifndef XSUM_CORE_H
 #define XSUM_CORE_H
@@ -35,9 +35,9 @@
 #define XS_EMPTY  (-100000)   /* level of the identity transducer          */
 #define XS_BAD    (-100001)   /* composition of two different levels: bug   */
 
-typedef struct { long long d0, d1; int lvl; } xs_t;
+typedef struct { long long inc; int lvl; } xs_t;    /* mantissa increment of a clean run at level lvl */
 
-PFC_HD xs_t xs_identity(void) { xs_t t; t.d0 = 0; t.d1 = 0; t.lvl = XS_EMPTY; return t; }
+PFC_HD xs_t xs_identity(void) { xs_t t; t.inc = 0; t.lvl = XS_EMPTY; return t; }
 
 /* level of a non-negative finite double: unbiased exponent, clamped so that subnormals and the first
  * normal binade (same ulp) form one level */
@@ -48,9 +48,10 @@ PFC_HD int xs_level(double s) {
 PFC_HD double xs_level_lo(int lvl) { return lvl <= -1022 ? 0.0 : pfc_pow2i(lvl); }
 PFC_HD double xs_level_hi(int lvl) { return lvl >= 1023 ? pfc_u2d(0x7FF0000000000000ull) : pfc_pow2i(lvl + 1); }
 
-/* transducer of "add v" while the running sum is in level `lvl`.  ok=0 if v cannot be a clean element. */
+/* increment of "add v" while the running sum is in level `lvl`.  ok=0 if v cannot be a clean element
+ * (negative / non-finite / larger than the level / an exact tie). */
 PFC_HD xs_t xs_elem(double v, int lvl, int* ok) {
-    xs_t t; t.lvl = lvl; t.d0 = 0; t.d1 = 0;
+    xs_t t; t.lvl = lvl; t.inc = 0;
     uint64_t bits = pfc_d2u(v);
     int be = (int)((bits >> 52) & 0x7FF);
     if ((bits >> 63) || be == 0x7FF) { *ok = 0; return t; }            /* negative / inf / nan */
@@ -60,28 +61,22 @@ PFC_HD xs_t xs_elem(double v, int lvl, int* ok) {
     int sh = lvl - ev;
     if (sh < 0) { *ok = 0; return t; }
     if (sh >= 64) return t;                                            /* v < u/2^11: no effect */
-    if (sh == 0) { t.d0 = t.d1 = (long long)mant; return t; }          /* exact multiple of u  */
+    if (sh == 0) { t.inc = (long long)mant; return t; }                /* exact multiple of u  */
     uint64_t q = mant >> sh;
     uint64_t rem = mant & ((1ull << sh) - 1ull);
     uint64_t half = 1ull << (sh - 1);
-    long long up = rem > half ? 1 : 0;
-    long long tie = rem == half ? 1 : 0;
-    t.d0 = (long long)q + up + (tie & (long long)(q & 1ull));          /* p = 0: (p + q) odd <=> q odd  */
-    t.d1 = (long long)q + up + (tie & (long long)((q & 1ull) ^ 1ull)); /* p = 1: (p + q) odd <=> q even */
+    if (rem == half) { *ok = 0; return t; }                            /* tie: needs the parity of the sum -> dirty */
+    t.inc = (long long)q + (rem > half ? 1 : 0);
     return t;
 }
 
 /* A first, then B */
 PFC_HD xs_t xs_compose(const xs_t a, const xs_t b) {
-    if (a.lvl == XS_EMPTY) return b;
-    if (b.lvl == XS_EMPTY) return a;
     xs_t r;
-    r.lvl = (a.lvl == b.lvl) ? a.lvl : XS_BAD;
     const long long CAP = 1ll << 60;
-    long long x0 = a.d0 + ((a.d0 & 1) ? b.d1 : b.d0);
-    long long x1 = a.d1 + ((a.d1 & 1) ? b.d0 : b.d1);
-    r.d0 = x0 > CAP ? CAP : x0;
-    r.d1 = x1 > CAP ? CAP : x1;
+    long long x = a.inc + b.inc;
+    r.inc = x > CAP ? CAP : x;
+    r.lvl = (a.lvl == XS_EMPTY) ? b.lvl : ((b.lvl == XS_EMPTY || b.lvl == a.lvl) ? a.lvl : XS_BAD);
     return r;
 }
 
@@ -90,11 +85,10 @@ PFC_HD double xs_apply(const xs_t t, double s, int* ok) {
     if (t.lvl == XS_EMPTY) return s;
     if (t.lvl == XS_BAD || xs_level(s) != t.lvl) { *ok = 0; return s; }
     uint64_t bits = pfc_d2u(s);
-    long long d = (bits & 1ull) ? t.d1 : t.d0;
-    uint64_t nb = bits + (uint64_t)d;
+    uint64_t nb = bits + (uint64_t)t.inc;
     /* must stay in level: same exponent field, except the lowest level may move from exp 0 to exp 1 */
     int e0 = (int)(bits >> 52), e1 = (int)(nb >> 52);
-    if (d < 0 || d >= (1ll << 53) || !(e1 == e0 || (t.lvl == -1022 && e1 <= 1))) { *ok = 0; return s; }
+    if (t.inc < 0 || t.inc >= (1ll << 53) || !(e1 == e0 || (t.lvl == -1022 && e1 <= 1))) { *ok = 0; return s; }
     return pfc_u2d(nb);
 }
 

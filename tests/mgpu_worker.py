@@ -1,0 +1,52 @@
+"""Worker of tests/test_gpu_multi.py: one process per GPU (torchrun); the sharded engine against the full-size oracle."""
+import os
+import sys
+
+import numpy as np
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import rust_robotics_b200 as rr  # noqa: E402
+from rust_robotics_b200 import dist as rdist, scenarios  # noqa: E402
+import _oracle  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    n_global, side, steps = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+    dist.init_process_group("gloo", init_method="env://")
+    uid = rdist.broadcast_unique_id(dist, rdist.nccl_unique_id, rank)
+    sc = scenarios.FastSlamScenario(side, (10.0 * side / 2 - 5.0, 10.0 * side / 2 - 5.0, 0.0), (1.0, 0.025), steps)
+    g = rr.FastSlam1(n_global, sc.m, rr.FsConfig(nth=n_global / 1.5), seed=9, device=local, shard=(uid, rank, world))
+    L = _oracle.load(libm=False)
+    o = _oracle.OracleFS(L, n_global, sc.m, seed=9, nth=n_global / 1.5)
+    g.seed_map(sc.start, sc.landmarks)
+    o.seed_map(sc.start, sc.landmarks)
+    lo, hi = rdist.shard_bounds(n_global, rank, world)
+    resamples = 0
+    for t in range(steps):
+        did = g.fastslam_update(sc.control, sc.obs[t])
+        odid = bool(o.step(sc.control, sc.obs[t]))
+        assert did == odid, f"rank {rank} step {t}: gate {did} vs oracle {odid}"
+        assert g.last_neff() == o.last_neff(), f"rank {rank} step {t}: neff"
+        if did:
+            resamples += 1
+            assert np.array_equal(g.last_indices(), o.last_indices()[lo:hi]), f"rank {rank} step {t}: indices"
+        bi, bp = g.get_best_particle()
+        assert bi == o.best(), f"rank {rank} step {t}: best {bi} vs {o.best()}"
+    gp, gl = g.state()
+    op, ol = o.state()
+    assert np.array_equal(gp, op[lo:hi]), f"rank {rank}: pose/weights differ"
+    assert np.array_equal(gl, ol[lo:hi]), f"rank {rank}: landmarks differ"
+    assert resamples > 0
+    dist.barrier()
+    if rank == 0:
+        print(f"MGPU_OK world={world} n={n_global} resamples={resamples}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

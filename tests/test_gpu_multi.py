@@ -1,0 +1,28 @@
+"""Sharded (multi-GPU) FastSLAM: every rank's shard must equal the corresponding slice of the single-process oracle,
+bit for bit (global exact sums, global ancestry, cross-rank map exchange).  Needs >= 2 GPUs."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def n_gpus():
+    import rust_robotics_b200 as rr
+    c = C.c_int()
+    rr.load_library().pfgpu_device_count(C.byref(c))
+    return c.value
+
+
+@pytest.mark.parametrize("world,n,side,steps", [(2, 4096, 6, 16), (2, 1 << 16, 8, 6)])
+def test_sharded_fastslam_matches_oracle(world, n, side, steps):
+    if n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(ROOT, "tests", "mgpu_worker.py"), str(n), str(side), str(steps)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

@@ -135,7 +135,7 @@ def pick_threads(sc, n):
 
 def cpu_baseline(sc, budget_s, max_steps):
     """bounded sample of the same workload: same map, same observation stream, fewer particles / steps"""
-    n = 8192
+    n = 32768
     threads, per_step = pick_threads(sc, n)
     steps = int(max(4, min(max_steps, len(sc.obs) - 4, budget_s / max(per_step, 1e-6))))
     dt, res = cpu_run(sc, n, steps, 2, threads)
@@ -237,6 +237,8 @@ def run_ours(args, rank, world, local_rank):
     first = step
     for t in range(K):
         g.flush_l2()
+        if dist is not None:
+            barrier()            # ranks enter the timed step together: a peer still flushing would otherwise be billed to the step
         g.mark(2 * t)
         g.fastslam_update(sc.control, sc.obs[step], want_flag=False, obs_array=arrs[step]); step += 1
         g.mark(2 * t + 1)
@@ -268,7 +270,7 @@ def run_ours(args, rank, world, local_rank):
         did = g.fastslam_update(sc.control, z, want_flag=True); step += 1          # builds the C array from host data, syncs
         idx, pose = g.get_best_particle()                                          # D2H of the step's result
         h2d += 16 + 24 * len(z)
-        d2h += 4 + 8 * 4 + 16 * 296
+        d2h += 4 + 4 + 8 * 3 + 16 * min(296, N_PARTICLES // 256)      # gate, cur, pose of the best, per-block argmax partials
     barrier()
     t_e2e = maxr(time.perf_counter() - t0)
     clocks = sampler.stop() if sampler else None
@@ -285,7 +287,7 @@ def run_ours(args, rank, world, local_rank):
                 "e2e": {"value": n_global * K / t_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d / K,
                         "d2h_bytes_per_step": d2h / K},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "kernel": "fs_step_kernel (predict + per-observation EKF)", "achieved": achieved,
+                "roofline": {"bound": "hbm", "kernel": "fs_predict_kernel + fs_ekf_kernel (predict + per-observation EKF, fs1.rs:245-256)", "achieved": achieved,
                              "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                              "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": kernel_ms},
                 "clocks": clocks, "serial_fallbacks": int(st1.serial_fallbacks)}

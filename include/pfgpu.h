@@ -5,7 +5,7 @@
  * boundary is the public Rust API of rust_robotics_localization::{ParticleFilterLocalizer,
  * MonteCarloLocalizer} and rust_robotics_slam::fastslam1.  A Rust shim (rust_robotics_b200/rust/, shown in
  * INTEGRATION.md) keeps those type and method names and forwards each method body to ONE entry point below;
- * the C++ mirror (rust_robotics_b200/host/*.hpp) and the Python mirror (rust_robotics_b200/api.py) do the same.
+ * the C++ mirror (rust_robotics_b200/host/ headers) and the Python mirror (rust_robotics_b200/api.py) do the same.
  * Each entry point cites the reference item it replaces ("pf.rs" = crates/rust_robotics_localization/src/
  * particle_filter.rs, "mcl.rs" = .../monte_carlo_localization.rs, "fs1.rs" = crates/rust_robotics_slam/src/
  * fastslam1.rs).

@@ -1,0 +1,9 @@
+//! rust_robotics_gpu — drop-in for the hot path of rust_robotics_localization / rust_robotics_slam.
+//!
+//! Same type and method names as the reference (crates/rust_robotics_localization/src/particle_filter.rs,
+//! crates/rust_robotics_slam/src/fastslam1.rs); every method body is ONE call into libpfgpu.so.  A downstream crate
+//! switches by changing `use rust_robotics_localization::ParticleFilterLocalizer` to
+//! `use rust_robotics_gpu::ParticleFilterLocalizer`.  NOT COMPILED HERE (no Rust toolchain in the build image).
+pub mod fastslam1;
+pub mod particle_filter;
+pub use particle_filter::{ParticleFilterConfig, ParticleFilterLocalizer};

@@ -275,6 +275,17 @@ def run_ours(args, rank, world, local_rank):
     t_e2e = maxr(time.perf_counter() - t0)
     clocks = sampler.stop() if sampler else None
 
+    if rank == 0 and os.environ.get("PFGPU_POST_TRACE"):
+        import ctypes as C
+        out = (C.c_ulonglong * 32)()
+        g.L.pfgpu_fs_post_trace(g.h, out)
+        nl = max(out[31], 1)
+        names = ["init+sync", "S tilesum", "sync", "S classify", "sync", "S chain", "norm+Q/S2 tilesums", "sync", "Q approx", "Q exact (border)",
+                 "S2 classify+sync+chain", "cum/comb tilesum", "sync", "cum/comb classify", "sync", "chains+emit"]
+        sys.stderr.write("fs_post_kernel phase times (us per launch, CTA 0): " +
+                         ", ".join(f"{nm}={out[k] / nl / 1e3:.2f}" for k, nm in enumerate(names)) + f"  launches={out[31]}\n")
+        sys.stderr.write("  S chain detail (us): segscan=%.2f staging=%.2f walk=%.2f verify+final=%.2f  mean dirty=%.1f\n" %
+                         (out[16] / nl / 1e3, out[17] / nl / 1e3, out[18] / nl / 1e3, out[19] / nl / 1e3, out[22] / nl))
     if rank == 0:
         peak, peak_src = load_peaks()
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9

@@ -149,6 +149,8 @@ typedef struct {
 } pfgpu_stats;
 int  pfgpu_pf_stats(pfgpu_pf*, pfgpu_stats*);
 int  pfgpu_fs_stats(pfgpu_fs*, pfgpu_stats*);
+/* debug (PFGPU_POST_TRACE=1): accumulated per-phase times [ns] of the fused post-step kernel; out32[31] = launches */
+int  pfgpu_fs_post_trace(pfgpu_fs*, unsigned long long* out32);
 int  pfgpu_pf_time_main_kernel(pfgpu_pf*, int on);
 int  pfgpu_fs_time_main_kernel(pfgpu_fs*, int on);
 /* CUDA events on the handle's own stream (bench.py times steps with these): mark(slot 0..16383) records an

@@ -61,7 +61,7 @@ EXPORTS = [
     "pfgpu_fs_last_indices", "pfgpu_fs_last_neff", "pfgpu_fs_count", "pfgpu_fs_sync",
     "pfgpu_nccl_unique_id", "pfgpu_pf_stats", "pfgpu_fs_stats", "pfgpu_pf_time_main_kernel",
     "pfgpu_fs_time_main_kernel", "pfgpu_pf_mark", "pfgpu_pf_elapsed_ms", "pfgpu_fs_mark", "pfgpu_fs_elapsed_ms",
-    "pfgpu_pf_flush_l2", "pfgpu_fs_flush_l2",
+    "pfgpu_pf_flush_l2", "pfgpu_fs_flush_l2", "pfgpu_fs_post_trace",
 ]
 
 
@@ -126,6 +126,8 @@ def load_library():
         getattr(L, f"pfgpu_{k}_mark").argtypes = [vp, C.c_int]
         getattr(L, f"pfgpu_{k}_elapsed_ms").argtypes = [vp, C.c_int, C.c_int, c_dp]
         getattr(L, f"pfgpu_{k}_flush_l2").argtypes = [vp]
+    L.pfgpu_fs_post_trace.argtypes = [vp, C.POINTER(C.c_ulonglong)]
+    L.pfgpu_test_div.argtypes = [C.c_ulonglong, C.c_uint64, C.POINTER(C.c_ulonglong), C.c_int]
     L.pfgpu_test_xsum.argtypes = [c_dp, C.c_size_t, c_dp, c_dp, C.POINTER(C.c_int), C.c_int]
     _LIB = L
     return L

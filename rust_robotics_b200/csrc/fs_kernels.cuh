@@ -46,6 +46,7 @@ struct FsDev {
     int* anc_cur = nullptr;                  // device: live ancestry buffer
     int* lmstate = nullptr;                  // device [m]: bit0 = buffer holding landmark l, bit1 = ancestry is the identity
     int eager = 0;                           // 1 (sharded mode): maps are cloned eagerly; every landmark lives in buffer *cur
+    int anc16 = 0;                           // 1: ancestry columns hold u16 (n <= 65 536)
 };
 
 // Observation lists of up to FS_PARAM_OBS entries travel inside the kernel's launch parameters (no H2D copy).
@@ -58,6 +59,11 @@ __device__ __forceinline__ double* fs_py(const FsDev& d, int c) { return c ? d.p
 __device__ __forceinline__ double* fs_pyaw(const FsDev& d, int c) { return c ? d.pyaw[1] : d.pyaw[0]; }
 __device__ __forceinline__ double* fs_lm(const FsDev& d, int c) { return c ? d.lm[1] : d.lm[0]; }
 __device__ __forceinline__ uint32_t* fs_anc(const FsDev& d, int c) { return c ? d.anc[1] : d.anc[0]; }
+// ancestry columns are stored as u16 when every index fits (n <= 65 536: half the traffic of a resample), else u32
+__device__ __forceinline__ size_t fs_anc_load(const FsDev& d, int c, size_t k) {
+    const uint32_t* p = fs_anc(d, c);
+    return d.anc16 ? (size_t)reinterpret_cast<const unsigned short*>(p)[k] : (size_t)p[k];
+}
 __device__ __forceinline__ size_t lm_index(size_t n, size_t l, int f, size_t i) { return (l * 6 + (size_t)f) * n + i; }
 
 // normalize_angle fs1.rs:80-89.  The reference loops without bound (and would spin forever on +-inf); the
@@ -92,7 +98,9 @@ __device__ __forceinline__ double fs_update_landmark(FsLm& L, double px, double 
     double zp1 = fs_normalize_angle(pfc_atan2(dy, dx) - pyaw);
     double y0 = z0 - d, y1 = fs_normalize_angle(z1 - zp1);     // innovation fs1.rs:155
     // compute_jacobian fs1.rs:102-110
-    double h00 = dx / d, h01 = dy / d, h10 = -dy / d2, h11 = dx / d2;
+    // four IEEE quotients over two denominators: one correctly rounded reciprocal each (pf_contract_math.h, PFC_DIV)
+    const pfc_rcp_t rd = pfc_rcp_make(d), rd2 = pfc_rcp_make(d2);
+    double h00 = pfc_div_by(dx, rd), h01 = pfc_div_by(dy, rd), h10 = pfc_div_by(-dy, rd2), h11 = pfc_div_by(dx, rd2);
     double p00 = L.c00, p01 = L.c01, p10 = L.c10, p11 = L.c11;
     // S = H P H^T + R  fs1.rs:161
     double a00 = h00 * p00 + h01 * p10, a01 = h00 * p01 + h01 * p11;
@@ -105,7 +113,10 @@ __device__ __forceinline__ double fs_update_landmark(FsLm& L, double px, double 
     double det = s00 * s11 - s10 * s01;
     double i00, i01, i10, i11;
     if (det == 0.0) { i00 = 1.0; i01 = 0.0; i10 = 0.0; i11 = 1.0; }
-    else { i00 = s11 / det; i01 = -s01 / det; i10 = -s10 / det; i11 = s00 / det; }
+    else {
+        const pfc_rcp_t rdet = pfc_rcp_make(det);
+        i00 = pfc_div_by(s11, rdet); i01 = pfc_div_by(-s01, rdet); i10 = pfc_div_by(-s10, rdet); i11 = pfc_div_by(s00, rdet);
+    }
     // K = P H^T S^-1 fs1.rs:165
     double b00 = p00 * h00 + p01 * h01, b01 = p00 * h10 + p01 * h11;
     double b10 = p10 * h00 + p11 * h01, b11 = p10 * h10 + p11 * h11;
@@ -123,7 +134,7 @@ __device__ __forceinline__ double fs_update_landmark(FsLm& L, double px, double 
     if (det_s > 0.0) {
         double t0 = y0 * i00 + y1 * i10, t1 = y0 * i01 + y1 * i11;
         double mahal = t0 * y0 + t1 * y1;
-        return pfc_exp(-0.5 * mahal) / (2.0 * PFC_PI * sqrt(det_s));
+        return PFC_DIV(pfc_exp(-0.5 * mahal), 2.0 * PFC_PI * sqrt(det_s));
     }
     return 1.0;
 }
@@ -159,7 +170,7 @@ __global__ void __launch_bounds__(FS_NT) fs_step_kernel(FsDev d, const __grid_co
         w = d.w_raw[i];       // continuation launch of the same step (observation list split at a repeated lm_id)
     }
     const size_t n = d.n;
-    const uint32_t* __restrict__ anc = fs_anc(d, *d.anc_cur);
+    const int anc_c = *d.anc_cur;
     for (int j = 0; j < k_obs; ++j) {
         const size_t l = (size_t)s_obs_fs[j].lm_id;
         const double zd = s_obs_fs[j].d, za = s_obs_fs[j].angle;
@@ -167,7 +178,7 @@ __global__ void __launch_bounds__(FS_NT) fs_step_kernel(FsDev d, const __grid_co
         const bool ident = (st & 2) != 0;
         const double* __restrict__ src = fs_lm(d, st & 1);
         double* __restrict__ dst = fs_lm(d, ident ? (st & 1) : ((st & 1) ^ 1));
-        const size_t col = ident ? i : (size_t)anc[l * n + i];       // lazy clone: read the ancestor's copy
+        const size_t col = ident ? i : fs_anc_load(d, anc_c, l * n + i);       // lazy clone: read the ancestor's copy
         FsLm L;
         L.x = src[lm_index(n, l, 0, col)]; L.y = src[lm_index(n, l, 1, col)];
         L.c00 = src[lm_index(n, l, 2, col)]; L.c01 = src[lm_index(n, l, 3, col)];
@@ -214,8 +225,10 @@ __global__ void __launch_bounds__(256) fs_predict_kernel(FsDev d, double u0, dou
     d.w_raw[i] = d.w[i];
 }
 
-template <bool PARAM_OBS>
-__global__ void __launch_bounds__(1024, 1) fs_ekf_kernel(FsDev d, const __grid_constant__ FsObsParam po, double r00, double r11, int k_obs) {
+// MAXT/MINB: launch bounds = register budget.  (1024,1): 64 registers, any k_obs <= 32; (448,2): 72 registers, two CTAs of
+// <= 14 warps per SM; (448,1): up to 128 registers, one CTA per SM.  Chosen at run time by the host (PFGPU_EKF_VARIANT).
+template <bool PARAM_OBS, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) fs_ekf_kernel(FsDev d, const __grid_constant__ FsObsParam po, double r00, double r11, int k_obs) {
     extern __shared__ double s_v2[];
     double* s_lik = s_v2;                                                          // [k_obs][32]
     unsigned* s_mask = reinterpret_cast<unsigned*>(s_lik + (size_t)k_obs * 32);    // [k_obs]
@@ -233,7 +246,7 @@ __global__ void __launch_bounds__(1024, 1) fs_ekf_kernel(FsDev d, const __grid_c
     bool wrote_cov = false;
     double lik = 1.0;
     if (valid) {
-        const size_t col = ident ? i : (size_t)fs_anc(d, *d.anc_cur)[l * n + i];     // lazy clone: the ancestor's copy
+        const size_t col = ident ? i : fs_anc_load(d, *d.anc_cur, l * n + i);     // lazy clone: the ancestor's copy
         const double* __restrict__ sp = src + col;
         FsLm L;
         L.x = sp[0]; L.y = sp[n]; L.c00 = sp[2 * n]; L.c01 = sp[3 * n]; L.c10 = sp[4 * n]; L.c11 = sp[5 * n];
@@ -349,20 +362,52 @@ __global__ void __launch_bounds__(256) fs_gather_pose_kernel(FsDev d) {
 // resample's (monotone) ancestry idx: anc'[l][t] = anc[l][idx[t]]  (idx[t] itself where the landmark is identity-mapped).
 // grid.x = particle chunks, grid.y = groups of FS_COMPOSE_ROWS landmarks.
 #define FS_COMPOSE_ROWS 16
+template <class AncT>
 __global__ void __launch_bounds__(256) fs_compose_anc_kernel(FsDev d) {
     if (!*d.gate) return;
     const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (t >= d.n) return;
     const int ac = *d.anc_cur;
-    const uint32_t* __restrict__ src = fs_anc(d, ac);
-    uint32_t* __restrict__ dst = fs_anc(d, ac ^ 1);
-    const uint32_t j = d.idx[t];
+    const AncT* __restrict__ src = reinterpret_cast<const AncT*>(fs_anc(d, ac));
+    AncT* __restrict__ dst = reinterpret_cast<AncT*>(fs_anc(d, ac ^ 1));
+    const AncT j = (AncT)d.idx[t];
     const size_t l0 = (size_t)blockIdx.y * FS_COMPOSE_ROWS;
 #pragma unroll
     for (int rr = 0; rr < FS_COMPOSE_ROWS; ++rr) {
         size_t l = l0 + rr;
         if (l < d.m) dst[l * d.n + t] = (d.lmstate[l] & 2) ? j : src[l * d.n + j];
     }
+}
+// Everything a resample does once the exact CDF and comb are known, one pass per particle slot t (gated):
+//   index walk (fs1.rs:224-226) as a lower bound, pose clone + weight (fs1.rs:227-229), and the lazy map clone: compose
+//   each landmark's ancestry column with this resample's ancestry (see fs_compose_anc_kernel).  A CTA = 256 slots, all m
+//   landmarks (coalesced 2 or 4 B per particle and landmark in each direction).
+template <class AncT>
+__global__ void __launch_bounds__(256) fs_resample_apply_kernel(FsDev d) {
+    if (!*d.gate) return;
+    const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= d.n) return;
+    const double r = d.rcomb[t];
+    const double* __restrict__ c = d.cum;
+    size_t lo = 0, hi = d.n;
+    while (lo < hi) {
+        size_t mid = lo + ((hi - lo) >> 1);
+        if (c[mid] < r) lo = mid + 1; else hi = mid;
+    }
+    const size_t j = lo < d.n ? lo : d.n - 1;
+    d.idx[t] = (uint32_t)j;
+    const int cur = *d.cur;
+    fs_px(d, cur ^ 1)[t] = fs_px(d, cur)[j];
+    fs_py(d, cur ^ 1)[t] = fs_py(d, cur)[j];
+    fs_pyaw(d, cur ^ 1)[t] = fs_pyaw(d, cur)[j];
+    d.w[t] = 1.0 / (double)d.n_global;                      // fs1.rs:228
+    const int ac = *d.anc_cur;
+    const AncT* __restrict__ src = reinterpret_cast<const AncT*>(fs_anc(d, ac));
+    AncT* __restrict__ dst = reinterpret_cast<AncT*>(fs_anc(d, ac ^ 1));
+    const size_t n = d.n;
+#pragma unroll 4
+    for (size_t l = 0; l < d.m; ++l)
+        dst[l * n + t] = (d.lmstate[l] & 2) ? (AncT)j : src[l * n + j];
 }
 __global__ void fs_flip_kernel(FsDev d) {
     if (!*d.gate) return;
@@ -420,7 +465,7 @@ __global__ void __launch_bounds__(256) fs_pack_lm_kernel(FsDev d, double* aos, s
     size_t ip = e / (d.m * 6), rem = e % (d.m * 6);
     size_t l = rem / 6; int f = (int)(rem % 6);
     const int st = d.lmstate[l];
-    const size_t col = (st & 2) ? (i0 + ip) : (size_t)fs_anc(d, *d.anc_cur)[l * d.n + i0 + ip];   // materialise through the ancestry
+    const size_t col = (st & 2) ? (i0 + ip) : fs_anc_load(d, *d.anc_cur, l * d.n + i0 + ip);   // materialise through the ancestry
     aos[e] = fs_lm(d, st & 1)[lm_index(d.n, l, f, col)];
 }
 __global__ void fs_lmstate_reset_kernel(FsDev d) {     // every landmark identity-mapped in buffer 0 (eager mode: *cur) after init/upload/seed

@@ -11,7 +11,7 @@
 // Each CTA owns one tile of FX_TILE = 512 particles and keeps its values in REGISTERS across all phases; the
 // five exact sums run through the same tile-aggregate / chain scheme as xsum.cuh, but the chain (tens of entries) is
 // evaluated redundantly by every CTA, so an exact total costs 2 grid-wide barriers and no extra launches.  Q and S2
-// share their barriers, so do the two scans: 5 barriers for a step that does not resample, 7 for one that does
+// share their barriers, so do the two scans: 4 barriers for a step that does not resample, 8 for one that does
 // (instead of ~25 launches).
 #pragma once
 #include <cooperative_groups.h>
@@ -29,6 +29,7 @@ namespace cg = cooperative_groups;
 
 struct FxSlot { double* tsum; xs_t* ttail; int* tnd; XsEntry* ent; };
 struct FxWork {
+    unsigned long long* dbg;  // [32] phase timestamps of CTA 0 (ns, %globaltimer): [k] accumulates t_k - t_{k-1}; [31] = launches
     FxSlot slot[FX_SLOTS];
     int* flags;               // [0] bad value seen (-> exact serial walk)  [1] cumulative serial walks  [2] cumulative certificate failures
                               // [3] cumulative overflow tiles
@@ -40,10 +41,15 @@ struct FxShared {
     XsSeg sm_s[XS_NT / 32];
     XsSeg carry_seg;
     int carry_nd;
+    int ndl;                           // number of tiles holding dirty values
+    unsigned short dl_tile[FX_MAX_TILES];   // ... their ids, in order
+    int dl_off[FX_MAX_TILES];          // ... and the ordinal of their first dirty value
     xs_t tin[FX_MAX_TILES];
     int tdoff[FX_MAX_TILES];
     int tnd[FX_MAX_TILES];
     XsEntry ent[FX_CHUNK];
+    double before[FX_CHUNK];           // exact running sum in front of / right after each staged dirty value
+    double after[FX_CHUNK];
     double after_win[XS_MAXD + 2];     // exact prefixes right after the dirty values of MY tile (+ the one before it)
     double total;
     double s_run;
@@ -128,74 +134,118 @@ __device__ __forceinline__ FxTile fx_classify(const double (&v)[FX_ITEMS], const
 
 // ---- phase 3 (after a grid barrier): every CTA evaluates the whole chain; results land in shared memory ---------
 // sh.total = exact total; sh.tin[blockIdx.x], sh.tdoff[blockIdx.x], sh.after_win[] serve fx_emit for this tile.
+#define FXC_STAMP(k) do { if (dbg && me == 0 && tid == 0) { unsigned long long t__; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t__)); dbg[k] += t__ - tp; tp = t__; } } while (0)
 template <class F>
-__device__ __noinline__ void fx_chain(const FxSlot& s, unsigned nt, F f, size_t n, FxShared& sh, int* flags) {
+__device__ __noinline__ void fx_chain(const FxSlot& s, unsigned nt, F f, size_t n, FxShared& sh, int* flags, unsigned long long* dbg = nullptr) {
     const int tid = threadIdx.x;
     const unsigned me = blockIdx.x;
+    unsigned long long tp = 0;
+    if (dbg) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tp));
     __syncthreads();
-    if (tid == 0) { sh.carry_seg = xs_seg_make(xs_identity(), 0); sh.carry_nd = 0; sh.s_run = 0.0; sh.ok = 1; sh.serial = flags[0]; }
+    // ---- tile-level segmented scan: all threads fetch the aggregates (coalesced), ONE warp scans them from shared memory
+    // (nt <= FX_MAX_TILES = 16 tiles per lane), no block-wide scan primitives on this path
+    for (unsigned b = tid; b < nt; b += XS_NT) { sh.tnd[b] = s.tnd[b]; sh.tin[b] = s.ttail[b]; }
+    if (tid == 0) { sh.s_run = 0.0; sh.ok = 1; sh.serial = flags[0]; }
     __syncthreads();
-    for (unsigned base = 0; base < nt; base += XS_NT) {
-        unsigned b = base + tid;
-        int nd = b < nt ? s.tnd[b] : 0;
-        int nde = nd < 0 ? 1 : nd;
-        xs_t tl = b < nt ? s.ttail[b] : xs_identity();
-        XsSeg tot; int ndtot;
-        XsSeg ex = xs_block_seg_excl<XS_NT>(xs_seg_make(tl, nde > 0), &tot, sh.sm_s);
-        int dex = block_excl_scan_int<XS_NT>(nde, &ndtot, sh.sm_i);
-        XsSeg cs = sh.carry_seg; int cn = sh.carry_nd;
-        if (b < nt) { sh.tin[b] = xs_seg_op(cs, ex).t; sh.tdoff[b] = cn + dex; sh.tnd[b] = nd; }
-        __syncthreads();
-        if (tid == 0) { sh.carry_seg = xs_seg_op(cs, tot); sh.carry_nd = cn + ndtot; }
-        __syncthreads();
+    if (tid < 32) {
+        const unsigned per = (nt + 31) / 32;
+        const unsigned b0 = tid * per, b1 = (b0 + per < nt) ? b0 + per : nt;
+        XsSeg run = xs_seg_make(xs_identity(), 0);
+        int ndrun = 0, ntl = 0;                                // dirty values / dirty tiles in my lane's tiles
+        for (unsigned b = b0; b < b1; ++b) {                   // pass 1: lane totals
+            int nd = sh.tnd[b]; int nde = nd < 0 ? 1 : nd;
+            run = xs_seg_op(run, xs_seg_make(sh.tin[b], nde > 0));
+            ndrun += nde; ntl += nde > 0 ? 1 : 0;
+        }
+        XsSeg inc = run; int ndinc = ndrun, ntinc = ntl;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            XsSeg y = xs_seg_shfl_up(inc, o);
+            int yn = __shfl_up_sync(0xffffffffu, ndinc, o), yt = __shfl_up_sync(0xffffffffu, ntinc, o);
+            if (tid >= o) { inc = xs_seg_op(y, inc); ndinc += yn; ntinc += yt; }
+        }
+        XsSeg ex = xs_seg_shfl_up(inc, 1);
+        int ndex = __shfl_up_sync(0xffffffffu, ndinc, 1), ntex = __shfl_up_sync(0xffffffffu, ntinc, 1);
+        if (tid == 0) { ex = xs_seg_make(xs_identity(), 0); ndex = 0; ntex = 0; }
+        for (unsigned b = b0; b < b1; ++b) {                   // pass 2: exclusive prefixes per tile + compact dirty-tile list
+            int nd = sh.tnd[b]; int nde = nd < 0 ? 1 : nd;
+            xs_t tl = sh.tin[b];
+            sh.tin[b] = ex.t; sh.tdoff[b] = ndex;
+            if (nde > 0) { sh.dl_tile[ntex] = (unsigned short)b; sh.dl_off[ntex] = ndex; ntex++; }
+            ex = xs_seg_op(ex, xs_seg_make(tl, nde > 0));
+            ndex += nde;
+        }
+        if (tid == 31) { sh.carry_seg = inc; sh.carry_nd = ndinc; sh.ndl = ntinc; }
     }
+    __syncthreads();
     const int D = sh.carry_nd;
     if (tid == 0 && sh.carry_seg.t.lvl == XS_BAD) sh.serial = 1;
     __syncthreads();
+    FXC_STAMP(0);
     const int my_o0 = sh.tdoff[me];                         // window of ordinals fx_emit needs: [my_o0 - 1, my_o0 + nd_me)
     if (!sh.serial) {
         for (int cbase = 0; cbase < D; cbase += FX_CHUNK) {
-            for (unsigned b = tid; b < nt; b += XS_NT) {
-                int nd = sh.tnd[b];
-                if (nd == 0) continue;
-                if (nd < 0) nd = 1;
-                int o0 = sh.tdoff[b];
-                if (o0 >= cbase + FX_CHUNK || o0 + nd <= cbase) continue;
-                for (int e = 0; e < nd; ++e) {
-                    int o = o0 + e - cbase;
-                    if (o < 0 || o >= FX_CHUNK) continue;
-                    XsEntry en = s.ent[(size_t)b * XS_MAXD + e];
-                    if (e == 0) {
-                        xs_t r; r.inc = en.inc; r.lvl = en.lvl;
-                        r = xs_compose(sh.tin[b], r);
-                        en.inc = r.inc; en.lvl = r.lvl;
-                    }
-                    if (en.pad == 1) en.v = (double)b;
-                    sh.ent[o] = en;
+            const int cnt = D - cbase < FX_CHUNK ? D - cbase : FX_CHUNK;
+            // stage exactly the dirty entries: thread o finds its (tile, slot) in the compact dirty-tile list
+            for (int o = tid; o < cnt; o += XS_NT) {
+                const int og = cbase + o;
+                int lo = 0, hi = sh.ndl - 1;
+                while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (sh.dl_off[mid] <= og) lo = mid; else hi = mid - 1; }
+                const unsigned b = sh.dl_tile[lo];
+                const int e = og - sh.dl_off[lo];
+                XsEntry en = s.ent[(size_t)b * XS_MAXD + e];
+                if (e == 0) {
+                    xs_t r; r.inc = en.inc; r.lvl = en.lvl;
+                    r = xs_compose(sh.tin[b], r);
+                    en.inc = r.inc; en.lvl = r.lvl;
                 }
+                if (en.pad == 1) en.v = (double)b;
+                sh.ent[o] = en;
             }
             __syncthreads();
+            FXC_STAMP(1);
+            if (dbg && me == 0 && tid == 0) dbg[6] += (unsigned long long)D;
+            // Serial part, kept minimal (a lone GPU thread retires ~1 dependent instruction per 6-8 cycles): per entry one
+            // 64-bit integer add on the bit pattern and one FP add.  The certificate checks run afterwards, in parallel.
             if (tid == 0) {
-                double sacc = sh.s_run; int ok = 1;
-                int cnt = D - cbase < FX_CHUNK ? D - cbase : FX_CHUNK;
-                for (int o = 0; o < cnt; ++o) {
-                    xs_t r; r.inc = sh.ent[o].inc; r.lvl = sh.ent[o].lvl;
-                    sacc = xs_apply(r, sacc, &ok);
+                double sacc = sh.s_run;
+                int o = 0;
+                for (; o + 4 <= cnt; o += 4) {              // 4 entries per trip: their operands are fetched up front
+                    const long long i0 = sh.ent[o].inc, i1 = sh.ent[o + 1].inc, i2 = sh.ent[o + 2].inc, i3 = sh.ent[o + 3].inc;
+                    const double v0 = sh.ent[o].v, v1 = sh.ent[o + 1].v, v2 = sh.ent[o + 2].v, v3 = sh.ent[o + 3].v;
+                    const int anypad = sh.ent[o].pad | sh.ent[o + 1].pad | sh.ent[o + 2].pad | sh.ent[o + 3].pad;
+                    if (anypad) break;
+                    sh.before[o] = sacc;     sacc = pfc_u2d(pfc_d2u(sacc) + (unsigned long long)i0) + v0; sh.after[o] = sacc;
+                    sh.before[o + 1] = sacc; sacc = pfc_u2d(pfc_d2u(sacc) + (unsigned long long)i1) + v1; sh.after[o + 1] = sacc;
+                    sh.before[o + 2] = sacc; sacc = pfc_u2d(pfc_d2u(sacc) + (unsigned long long)i2) + v2; sh.after[o + 2] = sacc;
+                    sh.before[o + 3] = sacc; sacc = pfc_u2d(pfc_d2u(sacc) + (unsigned long long)i3) + v3; sh.after[o + 3] = sacc;
+                }
+                for (; o < cnt; ++o) {
+                    sh.before[o] = sacc;
+                    sacc = pfc_u2d(pfc_d2u(sacc) + (unsigned long long)sh.ent[o].inc);
                     if (sh.ent[o].pad == 1) {               // overflow tile: genuine FP adds over the whole tile
                         unsigned b = (unsigned)sh.ent[o].v;
-                        if (b == me) sh.after_win[0] = sacc;            // my own tile is an overflow tile: keep its exact base
+                        if (b == me) sh.after_win[0] = sacc;
                         size_t lo = (size_t)b * FX_TILE, hi = lo + FX_TILE < n ? lo + FX_TILE : n;
                         for (size_t i = lo; i < hi; ++i) sacc = sacc + f(i);
                         if (me == 0) flags[3] += 1;
                     } else {
                         sacc = sacc + sh.ent[o].v;
                     }
-                    int og = cbase + o;                      // global ordinal
-                    int wi = og - (my_o0 - 1);
-                    if (wi >= 0 && wi < XS_MAXD + 2 && !(sh.tnd[me] < 0 && wi == 0)) sh.after_win[wi] = sacc;
+                    sh.after[o] = sacc;
                 }
                 sh.s_run = sacc;
+            }
+            __syncthreads();
+            FXC_STAMP(2);
+            for (int o = tid; o < cnt; o += XS_NT) {
+                // certificate of entry o: the run in front of it really was at the level it was classified for and stayed there
+                xs_t r; r.inc = sh.ent[o].inc; r.lvl = sh.ent[o].lvl;
+                int ok = 1;
+                (void)xs_apply(r, sh.before[o], &ok);
                 if (!ok) sh.ok = 0;
+                const int wi = cbase + o - (my_o0 - 1);
+                if (wi >= 0 && wi < XS_MAXD + 2 && !(sh.tnd[me] < 0 && wi == 0)) sh.after_win[wi] = sh.after[o];
             }
             __syncthreads();
         }
@@ -206,6 +256,7 @@ __device__ __noinline__ void fx_chain(const FxSlot& s, unsigned nt, F f, size_t 
             else sh.total = tot;
         }
         __syncthreads();
+        FXC_STAMP(3);
     }
     if (sh.serial) {      // exact by construction: one thread, left to right; also yields this tile's base
         if (tid == 0) {
@@ -256,6 +307,9 @@ __device__ __forceinline__ void fx_emit(const double (&v)[FX_ITEMS], const FxTil
     if (!ok) flags[2] += 1;
 }
 
+__device__ __forceinline__ unsigned long long fx_now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define FX_STAMP(k) do { if (b == 0 && tid == 0 && fw.dbg) { unsigned long long t__ = fx_now(); fw.dbg[k] += t__ - t_prev; t_prev = t__; } } while (0)
+
 struct FxValW2 {      // w / S2 recomputed on the fly for the rare global walks (overflow tiles / serial mode)
     const double* w; double S2;
     __device__ __forceinline__ double operator()(size_t i) const { double x = w[i]; return S2 > 0.0 ? x / S2 : x; }
@@ -263,24 +317,37 @@ struct FxValW2 {      // w / S2 recomputed on the fly for the rare global walks 
 struct FxValComb { double r0, inv; __device__ __forceinline__ double operator()(size_t i) const { return i == 0 ? r0 : inv; } };
 
 // =====================================================================================================================
-__global__ void __launch_bounds__(XS_NT, 2) fs_post_kernel(FsDev d, FxWork fw, double nth, uint64_t seed, unsigned nt, double rel) {
+__global__ void __launch_bounds__(XS_NT, 2) fs_post_kernel(FsDev d, FxWork fw, double nth, uint64_t seed, unsigned nt, double rel,
+                                                           const __grid_constant__ FsObsParam po, int k_obs) {
     cg::grid_group grid = cg::this_grid();
     __shared__ FxShared sh;
     const unsigned b = blockIdx.x;
     const int tid = threadIdx.x;
     const size_t first = (size_t)b * FX_TILE + (size_t)tid * FX_ITEMS;
     const size_t n = d.n;
-    if (b == 0 && tid == 0) fw.flags[0] = 0;
+    unsigned long long t_prev = fx_now();
+    if (b == 0 && tid == 0) { fw.flags[0] = 0; if (fw.dbg) fw.dbg[31] += 1; }
+    if (b == 0 && tid < k_obs) {           // lazy-clone bookkeeping of the EKF launch that just ran (see fs_lmstate_after_step_kernel)
+        const int l = po.o[tid].lm_id;
+        const int st = d.lmstate[l];
+        if (!(st & 2)) d.lmstate[l] = ((st & 1) ^ 1) | 2;
+    }
     double v[FX_ITEMS];
 #pragma unroll
     for (int k = 0; k < FX_ITEMS; ++k) { size_t i = first + k; v[k] = i < n ? d.w_raw[i] : 0.0; }
     grid.sync();                                               // flags[0] reset is visible before anyone raises it
+    FX_STAMP(0);
     // ---------------- S = sum w_raw; w = w_raw / S (fs1.rs:196-203) ----------------
     fx_tile_sum(v, fw.slot[0], sh, fw.flags);
+    FX_STAMP(1);
     grid.sync();
+    FX_STAMP(2);
     fx_classify(v, fw.slot[0], sh, rel);
+    FX_STAMP(3);
     grid.sync();
-    fx_chain(fw.slot[0], nt, XsValArray{d.w_raw}, n, sh, fw.flags);
+    FX_STAMP(4);
+    fx_chain(fw.slot[0], nt, XsValArray{d.w_raw}, n, sh, fw.flags, fw.dbg ? fw.dbg + 16 : nullptr);
+    FX_STAMP(5);
     const double S = sh.total;
     double q[FX_ITEMS];
 #pragma unroll
@@ -290,24 +357,47 @@ __global__ void __launch_bounds__(XS_NT, 2) fs_post_kernel(FsDev d, FxWork fw, d
         if (i < n) d.w[i] = v[k];
         q[k] = v[k] * v[k];
     }
-    // ---------------- Q = sum w^2 and S2 = sum w, sharing their barriers ----------------
-    fx_tile_sum(q, fw.slot[1], sh, fw.flags);
-    fx_tile_sum(v, fw.slot[2], sh, fw.flags);
+    // ---------------- gate: neff = 1 / sum w^2 < NTH (fs1.rs:186-193, 262-263) ----------------
+    // Only the DECISION feeds back into the state, so Q is first summed in tree order (one barrier).  The sequential sum
+    // the reference computes differs from it by at most (n+64)*2^-52 relatively; only when neff lands that close to NTH is
+    // the exact sequential sum evaluated (same decision as the reference in every case).
+    fx_tile_sum(q, fw.slot[1], sh, fw.flags);                  // per-tile partial sums of w^2
+    fx_tile_sum(v, fw.slot[2], sh, fw.flags);                  // per-tile sums of w (needed only if the gate opens)
+    FX_STAMP(6);
     grid.sync();
-    fx_classify(q, fw.slot[1], sh, rel);
-    fx_classify(v, fw.slot[2], sh, rel);
-    grid.sync();
-    fx_chain(fw.slot[1], nt, FsValWSq{d.w}, n, sh, fw.flags);
-    const double Q = sh.total;
-    fx_chain(fw.slot[2], nt, XsValArray{d.w}, n, sh, fw.flags);
-    const double S2 = sh.total;
-    const double neff = Q > 0.0 ? 1.0 / Q : 0.0;               // compute_neff fs1.rs:186-193
+    FX_STAMP(7);
+    double qpart = 0.0;
+    for (unsigned t = tid; t < nt; t += XS_NT) qpart += fw.slot[1].tsum[t];
+    double qa = block_sum<XS_NT>(qpart, sh.sm_d);
+    __syncthreads();
+    if (tid == 0) sh.total = qa;
+    __syncthreads();
+    double Q = sh.total;                                       // bit-identical in every CTA (same order everywhere)
+    double neff = Q > 0.0 ? 1.0 / Q : 0.0;
+    const double slack = 8.0 * (double)(d.n_global + 64) * 2.220446049250313e-16;
+    const bool border = !(fabs(neff - nth) > slack * fmax(fabs(nth), fabs(neff))) || (fw.flags[0] != 0);
+    FX_STAMP(8);
+    if (border) {                                              // rare; uniform over the grid
+        fx_classify(q, fw.slot[1], sh, rel);
+        grid.sync();
+        fx_chain(fw.slot[1], nt, FsValWSq{d.w}, n, sh, fw.flags);
+        Q = sh.total;
+        neff = Q > 0.0 ? 1.0 / Q : 0.0;                        // compute_neff fs1.rs:186-193
+    }
+    FX_STAMP(9);
     const int gate = neff < nth ? 1 : 0;                       // fs1.rs:263
     if (b == 0 && tid == 0) {
-        d.scal[0] = S; d.scal[1] = Q; d.scal[2] = S2; d.scal[3] = neff;
+        d.scal[0] = S; d.scal[1] = Q; d.scal[3] = neff;
         *d.gate = gate;
     }
-    if (!gate) return;                                         // the whole grid takes the same branch (Q is bit-identical everywhere)
+    if (!gate) return;                                         // the whole grid takes the same branch
+    // ---------------- resample: S2 = sum w (fs1.rs:207) ----------------
+    fx_classify(v, fw.slot[2], sh, rel);
+    grid.sync();
+    fx_chain(fw.slot[2], nt, XsValArray{d.w}, n, sh, fw.flags);
+    const double S2 = sh.total;
+    if (b == 0 && tid == 0) d.scal[2] = S2;
+    FX_STAMP(10);
     // ---------------- resample (fs1.rs:206-231) ----------------
     const double inv = 1.0 / (double)d.n_global;
     if (tid == 0) {
@@ -325,15 +415,20 @@ __global__ void __launch_bounds__(XS_NT, 2) fs_post_kernel(FsDev d, FxWork fw, d
     }
     fx_tile_sum(v, fw.slot[3], sh, fw.flags);
     fx_tile_sum(cv, fw.slot[4], sh, fw.flags);
+    FX_STAMP(11);
     grid.sync();
+    FX_STAMP(12);
     FxTile tc = fx_classify(v, fw.slot[3], sh, rel);
     FxTile tr = fx_classify(cv, fw.slot[4], sh, rel);
+    FX_STAMP(13);
     grid.sync();
+    FX_STAMP(14);
     double c[FX_ITEMS], r[FX_ITEMS];
     fx_chain(fw.slot[3], nt, FxValW2{d.w, S2}, n, sh, fw.flags);
     fx_emit(v, tc, sh, FxValW2{d.w, S2}, n, rel, c, fw.flags, d.cum);
     fx_chain(fw.slot[4], nt, FxValComb{r0, inv}, n, sh, fw.flags);
     fx_emit(cv, tr, sh, FxValComb{r0, inv}, n, rel, r, fw.flags, d.rcomb);
+    FX_STAMP(15);
 #pragma unroll
     for (int k = 0; k < FX_ITEMS; ++k) { size_t i = first + k; if (i < n) { d.cum[i] = c[k]; d.rcomb[i] = r[k]; } }
     // the index walk (fs1.rs:224-226) and the pose clone (fs1.rs:227-229) need every slice of cum: they run in the

@@ -84,13 +84,14 @@ __global__ void __launch_bounds__(PF_NT) pf_predict_weight_kernel(PfDev d, const
     if (DO_WEIGHT) {
         const double coeff = 1.0 / sqrt(2.0 * PFC_PI * (sigma * sigma));   // gauss_likelihood pf.rs:476-479
         const double denom = 2.0 * (sigma * sigma);
+        const pfc_rcp_t rdenom = pfc_rcp_make(denom);               // one reciprocal for all k_obs IEEE quotients
         double w = 1.0;                                             // pf.rs:317: the previous weight is discarded
         for (int j = 0; j < k_obs; ++j) {
             double dx = p.x - s_obs_pf[3 * j + 1];
             double dy = p.y - s_obs_pf[3 * j + 2];
             double d_pred = sqrt(dx * dx + dy * dy);
             double diff = s_obs_pf[3 * j] - d_pred;
-            w = w * (coeff * pfc_exp(-(diff * diff) / denom));
+            w = w * (coeff * pfc_exp(pfc_div_by(-(diff * diff), rdenom)));
         }
         d.w_raw[i] = w;
     }

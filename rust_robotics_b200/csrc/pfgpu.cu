@@ -534,6 +534,7 @@ struct pfgpu_fs {
     bool fused_post = false;
     unsigned fx_nt = 0;
     bool step_v2 = true;           // observation-parallel step kernel (PFGPU_STEP_V2=0 selects the one-thread-per-particle form)
+    int ekf_variant = 3;           // register budget of fs_ekf_kernel: 0 = 64 regs, 1 = 72 regs (2 CTAs/SM), 2 = up to 128 regs (1 CTA/SM)
     FsShard sh;                    // multi-GPU state (world == 1: unused)
 };
 
@@ -567,6 +568,7 @@ static int fs_create_impl(const pfgpu_fs_config* cfg, size_t n, size_t n_global,
     FS_TRY(cudaMalloc(&d.idx, n * sizeof(uint32_t)));
     FS_TRY(cudaMalloc(&d.scal, 16 * sizeof(double))); FS_TRY(cudaMemset(d.scal, 0, 16 * sizeof(double)));
     FS_TRY(cudaMalloc(&d.gate, sizeof(int))); FS_TRY(cudaMemset(d.gate, 0, sizeof(int)));
+    d.anc16 = (n <= 65536 && world == 1) ? 1 : 0;
     for (int b = 0; b < 2; ++b) FS_TRY(cudaMalloc(&d.anc[b], (m ? m : 1) * n * sizeof(uint32_t)));
     FS_TRY(cudaMalloc(&d.anc_cur, sizeof(int))); FS_TRY(cudaMemset(d.anc_cur, 0, sizeof(int)));
     FS_TRY(cudaMalloc(&d.lmstate, (m ? m : 1) * sizeof(int)));
@@ -582,6 +584,7 @@ static int fs_create_impl(const pfgpu_fs_config* cfg, size_t n, size_t n_global,
     rc = xs_work_alloc(h->xs, n);
     if (rc) return fail(rc);
     { const char* e2 = getenv("PFGPU_STEP_V2"); h->step_v2 = !(e2 && e2[0] == '0'); }
+    { const char* e3 = getenv("PFGPU_EKF_VARIANT"); if (e3 && e3[0] >= '0' && e3[0] <= '4') h->ekf_variant = e3[0] - '0'; }
     {   // fused post-step kernel: usable when one co-resident wave covers all tiles
         unsigned nt = cdiv_u(n, FX_TILE);
         int nb = 0;
@@ -602,6 +605,11 @@ static int fs_create_impl(const pfgpu_fs_config* cfg, size_t n, size_t n_global,
                 }
                 okalloc = okalloc && cudaMalloc(&h->fx.flags, 8 * sizeof(int)) == cudaSuccess &&
                           cudaMemset(h->fx.flags, 0, 8 * sizeof(int)) == cudaSuccess;
+                h->fx.dbg = nullptr;
+                if (getenv("PFGPU_POST_TRACE")) {
+                    okalloc = okalloc && cudaMalloc(&h->fx.dbg, 32 * sizeof(unsigned long long)) == cudaSuccess &&
+                              cudaMemset(h->fx.dbg, 0, 32 * sizeof(unsigned long long)) == cudaSuccess;
+                }
                 if (!okalloc) return fail(PFGPU_ERR_CUDA);
                 h->fused_post = true; h->fx_nt = nt;
             }
@@ -652,7 +660,7 @@ extern "C" void pfgpu_fs_destroy(pfgpu_fs* h) {
     cudaFree(d.gate); cudaFree(d.obs); cudaFree(d.best_w); cudaFree(d.best_i); cudaFree(d.counters);
     cudaFree(d.anc[0]); cudaFree(d.anc[1]); cudaFree(d.anc_cur); cudaFree(d.lmstate);
     for (int sl = 0; sl < FX_SLOTS; ++sl) { cudaFree(h->fx.slot[sl].tsum); cudaFree(h->fx.slot[sl].ttail); cudaFree(h->fx.slot[sl].tnd); cudaFree(h->fx.slot[sl].ent); }
-    cudaFree(h->fx.flags);
+    cudaFree(h->fx.flags); cudaFree(h->fx.dbg);
     {
         FsShard& sh = h->sh;
         cudaFree(sh.t_loc); cudaFree(sh.t_all); cudaFree(sh.approx_off); cudaFree(sh.sum_loc); cudaFree(sh.sum_all); cudaFree(sh.s_start);
@@ -867,6 +875,8 @@ extern "C" int pfgpu_fs_step(pfgpu_fs* h, const double u[2], const pfgpu_fs_obs*
         }
     }
     cuts.push_back(k);
+    FsObsParam last_po; int last_k = 0;
+    memset(&last_po, 0, sizeof(last_po));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->timer.on) { PF_CUDA(cudaEventCreate(&e0)); PF_CUDA(cudaEventCreate(&e1)); PF_CUDA(cudaEventRecord(e0, h->ctx.stream)); }
     for (size_t seg = 0; seg + 1 < cuts.size(); ++seg) {
@@ -883,7 +893,16 @@ extern "C" int pfgpu_fs_step(pfgpu_fs* h, const double u[2], const pfgpu_fs_obs*
                               sqrt(h->cfg.q11), h->seed, h->n_step);
                 if (kk) {
                     size_t smem = kk * 32 * sizeof(double) + kk * sizeof(unsigned) + 8;
-                    PF_LAUNCH(h->ctx, fs_ekf_kernel<true>, cdiv_u(d.n, 32), (unsigned)(32 * kk), smem, d, po, h->cfg.r00, h->cfg.r11, (int)kk);
+                    const int var = kk <= 14 ? h->ekf_variant : 0;
+                    if (var == 1)      PF_LAUNCH(h->ctx, (fs_ekf_kernel<true, 448, 2>), cdiv_u(d.n, 32), (unsigned)(32 * kk), smem, d, po, h->cfg.r00, h->cfg.r11, (int)kk);
+                    else if (var == 2) PF_LAUNCH(h->ctx, (fs_ekf_kernel<true, 448, 1>), cdiv_u(d.n, 32), (unsigned)(32 * kk), smem, d, po, h->cfg.r00, h->cfg.r11, (int)kk);
+                    else if (var == 3) PF_LAUNCH(h->ctx, (fs_ekf_kernel<true, 448, 3>), cdiv_u(d.n, 32), (unsigned)(32 * kk), smem, d, po, h->cfg.r00, h->cfg.r11, (int)kk);
+                    else if (var == 4) PF_LAUNCH(h->ctx, (fs_ekf_kernel<true, 448, 4>), cdiv_u(d.n, 32), (unsigned)(32 * kk), smem, d, po, h->cfg.r00, h->cfg.r11, (int)kk);
+                    else               PF_LAUNCH(h->ctx, (fs_ekf_kernel<true, 1024, 1>), cdiv_u(d.n, 32), (unsigned)(32 * kk), smem, d, po, h->cfg.r00, h->cfg.r11, (int)kk);
+                }
+                if (h->fused_post && seg + 2 == cuts.size() && kk <= 256) {   // last piece: the fused post kernel does the bookkeeping
+                    last_po = po; last_k = (int)kk;
+                    continue;
                 }
             } else
             PF_LAUNCH(h->ctx, fs_step_kernel<true>, cdiv_u(d.n, FS_NT), FS_NT, (kk ? kk : 1) * sizeof(FsObsDev), d, po, u[0], u[1], h->cfg.dt,
@@ -914,10 +933,24 @@ extern "C" int pfgpu_fs_step(pfgpu_fs* h, const double u[2], const pfgpu_fs_obs*
     if (h->fused_post) {
         // normalise, N_eff gate and (when it opens) the whole index computation + pose clone: one cooperative launch
         double nth = h->cfg.nth; uint64_t seed = h->seed; unsigned nt = h->fx_nt; double rel = xs_margin(d.n_global);
-        void* args[] = { (void*)&d, (void*)&h->fx, (void*)&nth, (void*)&seed, (void*)&nt, (void*)&rel };
+        void* args[] = { (void*)&d, (void*)&h->fx, (void*)&nth, (void*)&seed, (void*)&nt, (void*)&rel, (void*)&last_po, (void*)&last_k };
         PF_CUDA(cudaLaunchCooperativeKernel((void*)fs_post_kernel, dim3(nt), dim3(XS_NT), args, 0, h->ctx.stream));
         h->ctx.launches++;
         PF_LAUNCH(h->ctx, fs_search_pose_kernel, cdiv_u(d.n, 256), 256, 0, d);
+        if (d.m) {
+            dim3 grid(cdiv_u(d.n, 256), cdiv_u(d.m, FS_COMPOSE_ROWS));
+            if (d.anc16) PF_LAUNCH(h->ctx, fs_compose_anc_kernel<unsigned short>, grid, 256, 0, d);
+            else         PF_LAUNCH(h->ctx, fs_compose_anc_kernel<uint32_t>, grid, 256, 0, d);
+        }
+        PF_LAUNCH(h->ctx, fs_flip_kernel, 1, 256, 0, d);
+        h->steps++;
+        if (did) {
+            int* hp = reinterpret_cast<int*>(h->h_pin + 32);
+            PF_CUDA(cudaMemcpyAsync(hp, d.gate, sizeof(int), cudaMemcpyDeviceToHost, h->ctx.stream));
+            PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+            *did = *hp;
+        }
+        return 0;
     } else {
     // normalize_weights fs1.rs:259
     int rc = xs_total(h->ctx, h->xs, XsValArray{d.w_raw}, d.n, d.n_global, 0.0, d.scal + 0);
@@ -942,7 +975,8 @@ extern "C" int pfgpu_fs_step(pfgpu_fs* h, const double u[2], const pfgpu_fs_obs*
     }
     if (d.m) {
         dim3 grid(cdiv_u(d.n, 256), cdiv_u(d.m, FS_COMPOSE_ROWS));
-        PF_LAUNCH(h->ctx, fs_compose_anc_kernel, grid, 256, 0, d);      // lazy clone: ancestry columns instead of the map
+        if (d.anc16) PF_LAUNCH(h->ctx, fs_compose_anc_kernel<unsigned short>, grid, 256, 0, d);      // lazy clone: ancestry columns instead of the map
+        else         PF_LAUNCH(h->ctx, fs_compose_anc_kernel<uint32_t>, grid, 256, 0, d);
     }
     PF_LAUNCH(h->ctx, fs_flip_kernel, 1, 256, 0, d);
     h->steps++;
@@ -1037,6 +1071,15 @@ extern "C" int pfgpu_fs_stats(pfgpu_fs* h, pfgpu_stats* s) {
     if (rcx) return rcx;
     return read_fx_flags(h->fx, h->fused_post, s);
 }
+// debug: accumulated phase times of the fused post kernel (PFGPU_POST_TRACE=1); out32[31] = launches
+extern "C" int pfgpu_fs_post_trace(pfgpu_fs* h, unsigned long long* out32) {
+    if (!h || !out32) return PFGPU_ERR_INVALID;
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+    for (int k = 0; k < 32; ++k) out32[k] = 0;
+    if (h->fused_post && h->fx.dbg) PF_CUDA(cudaMemcpy(out32, h->fx.dbg, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return 0;
+}
 extern "C" int pfgpu_fs_time_main_kernel(pfgpu_fs* h, int on) {
     if (!h) return PFGPU_ERR_INVALID;
     PF_CUDA(cudaSetDevice(h->ctx.device));
@@ -1059,6 +1102,37 @@ extern "C" int pfgpu_nccl_unique_id(void* out128) {
     PF_NCCL(ncclGetUniqueId(&id));
     static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
     memcpy(out128, &id, sizeof(id));
+    return 0;
+}
+
+// ====================================================================================================
+// test hook: the device's reciprocal-based division (PFC_DIV) against the IEEE `/` on n random + adversarial pairs
+__global__ void pf_test_div_kernel(unsigned long long n, uint64_t seed, unsigned long long* mismatches) {
+    unsigned long long bad = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        pfc_u32x4 r = pfc_rng_block(seed, 7, 0, i), r2 = pfc_rng_block(seed, 7, 1, i);
+        uint64_t x = pfc_blk_u64(r, 0), z = pfc_blk_u64(r, 1), m = pfc_blk_u64(r2, 0);
+        int ea = (int)(m % 801) - 400, eb = (int)((m >> 10) % 801) - 400;
+        int kind = (int)((m >> 20) & 7);
+        if (kind == 0) z |= 0x000FFFFFFFFFF000ull; else if (kind == 1) z &= 0xFFF0000000000FFFull;
+        else if (kind == 2) x |= 0x000FFFFFFFFFFF00ull; else if (kind == 3) { x &= 0xFFF00000000000FFull; z &= 0xFFF00000000000FFull; }
+        double a = pfc_u2d((x & 0x800FFFFFFFFFFFFFull) | ((uint64_t)(ea + 1023) << 52));
+        double b = pfc_u2d((z & 0x800FFFFFFFFFFFFFull) | ((uint64_t)(eb + 1023) << 52));
+        if (kind == 7) a = (m & (1ull << 40)) ? 0.0 : -0.0;
+        double q = PFC_DIV(a, b), t = a / b;
+        if (pfc_d2u(q) != pfc_d2u(t)) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+extern "C" int pfgpu_test_div(unsigned long long n, uint64_t seed, unsigned long long* mismatches, int device) {
+    PF_CUDA(cudaSetDevice(device));
+    unsigned long long* d = nullptr;
+    PF_CUDA(cudaMalloc(&d, sizeof(*d)));
+    PF_CUDA(cudaMemset(d, 0, sizeof(*d)));
+    pf_test_div_kernel<<<148 * 8, 256>>>(n, seed, d);
+    PF_CUDA(cudaDeviceSynchronize());
+    PF_CUDA(cudaMemcpy(mismatches, d, sizeof(*d), cudaMemcpyDeviceToHost));
+    cudaFree(d);
     return 0;
 }
 

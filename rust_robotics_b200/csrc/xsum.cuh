@@ -26,7 +26,7 @@
 #define XS_TILE   (XS_NT * XS_ITEMS)
 #define XS_MAXD   32
 #define XS_CHAIN_NT 256
-#define XS_CHUNK  1024
+#define XS_CHUNK  768
 
 struct __align__(8) XsEntry { long long inc; int lvl; int pad; double v; };
 struct XsSeg { xs_t t; int flag; };
@@ -254,6 +254,7 @@ __global__ void __launch_bounds__(XS_CHAIN_NT) xs_chain(F f, size_t n, unsigned 
     __shared__ int carry_nd;
     __shared__ XsEntry sm_ent[XS_CHUNK];
     __shared__ double sm_after[XS_CHUNK];
+    __shared__ double sm_before[XS_CHUNK];
     __shared__ double s_run;
     __shared__ int ok_s;
     XS_GATE(w);
@@ -281,33 +282,33 @@ __global__ void __launch_bounds__(XS_CHAIN_NT) xs_chain(F f, size_t n, unsigned 
     // phase 2: apply the dirty entries in order (chunks staged through shared memory)
     if (!w.flags[0]) {
         for (int cbase = 0; cbase < D; cbase += XS_CHUNK) {
-            for (unsigned b = tid; b < nt; b += XS_CHAIN_NT) {
+            // one (tile, entry) pair per thread and iteration (parallel fetch of a tile's entries)
+            for (size_t idx = tid; idx < (size_t)nt * XS_MAXD; idx += XS_CHAIN_NT) {
+                const unsigned b = (unsigned)(idx / XS_MAXD);
+                const int e = (int)(idx % XS_MAXD);
                 int nd = w.tnd[b];
-                if (nd == 0) continue;
                 if (nd < 0) nd = 1;
-                int o0 = w.tdoff[b];
-                if (o0 >= cbase + XS_CHUNK || o0 + nd <= cbase) continue;
-                xs_t tinb = w.tin[b];
-                for (int e = 0; e < nd; ++e) {
-                    int o = o0 + e - cbase;
-                    if (o < 0 || o >= XS_CHUNK) continue;
-                    XsEntry en = w.ent[(size_t)b * XS_MAXD + e];
-                    if (e == 0) {
-                        xs_t r; r.inc = en.inc; r.lvl = en.lvl;
-                        r = xs_compose(tinb, r);
-                        en.inc = r.inc; en.lvl = r.lvl;
-                    }
-                    if (en.pad == 1) en.v = (double)b;      // overflow marker carries its tile index
-                    sm_ent[o] = en;
+                if (e >= nd) continue;
+                const int o = w.tdoff[b] + e - cbase;
+                if (o < 0 || o >= XS_CHUNK) continue;
+                XsEntry en = w.ent[(size_t)b * XS_MAXD + e];
+                if (e == 0) {
+                    xs_t r; r.inc = en.inc; r.lvl = en.lvl;
+                    r = xs_compose(w.tin[b], r);
+                    en.inc = r.inc; en.lvl = r.lvl;
                 }
+                if (en.pad == 1) en.v = (double)b;
+                sm_ent[o] = en;
             }
             __syncthreads();
+            const int cnt = D - cbase < XS_CHUNK ? D - cbase : XS_CHUNK;
+            // minimal serial part: per entry one integer add on the bit pattern and one FP add; certificates are checked
+            // afterwards in parallel
             if (tid == 0) {
-                double s = s_run; int ok = 1;
-                int cnt = D - cbase < XS_CHUNK ? D - cbase : XS_CHUNK;
+                double s = s_run;
                 for (int o = 0; o < cnt; ++o) {
-                    xs_t r; r.inc = sm_ent[o].inc; r.lvl = sm_ent[o].lvl;
-                    s = xs_apply(r, s, &ok);
+                    sm_before[o] = s;
+                    s = pfc_u2d(pfc_d2u(s) + (unsigned long long)sm_ent[o].inc);
                     if (sm_ent[o].pad == 1) {               // overflow tile: walk it with genuine FP adds
                         unsigned b = (unsigned)sm_ent[o].v;
                         w.sbase[b] = s;
@@ -320,11 +321,15 @@ __global__ void __launch_bounds__(XS_CHAIN_NT) xs_chain(F f, size_t n, unsigned 
                     sm_after[o] = s;
                 }
                 s_run = s;
-                if (!ok) ok_s = 0;
             }
             __syncthreads();
-            int cnt = D - cbase < XS_CHUNK ? D - cbase : XS_CHUNK;
-            for (int o = tid; o < cnt; o += XS_CHAIN_NT) w.s_after[cbase + o] = sm_after[o];
+            for (int o = tid; o < cnt; o += XS_CHAIN_NT) {
+                xs_t r; r.inc = sm_ent[o].inc; r.lvl = sm_ent[o].lvl;
+                int ok = 1;
+                (void)xs_apply(r, sm_before[o], &ok);
+                if (!ok) ok_s = 0;
+                w.s_after[cbase + o] = sm_after[o];
+            }
             __syncthreads();
         }
         if (tid == 0) {

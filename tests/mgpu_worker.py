@@ -31,7 +31,7 @@ def main():
         did = g.fastslam_update(sc.control, sc.obs[t])
         odid = bool(o.step(sc.control, sc.obs[t]))
         assert did == odid, f"rank {rank} step {t}: gate {did} vs oracle {odid}"
-        assert g.last_neff() == o.last_neff(), f"rank {rank} step {t}: neff"
+        assert abs(g.last_neff() - o.last_neff()) <= 1e-9 * abs(o.last_neff()), f"rank {rank} step {t}: neff"
         if did:
             resamples += 1
             assert np.array_equal(g.last_indices(), o.last_indices()[lo:hi]), f"rank {rank} step {t}: indices"

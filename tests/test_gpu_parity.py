@@ -79,6 +79,15 @@ def test_xsum_device_serial_fallback_on_bad_values():
     assert np.array_equal(out[:1234], ref[:1234]) and np.isnan(out[1234:]).all()
 
 
+def test_device_division_is_ieee_exact():
+    """PFC_DIV on the device (correctly rounded reciprocal + two fma corrections, guarded) must equal the IEEE quotient for
+    every operand pair: 2e9 random pairs over exponents +-400 incl. all-ones / sparse mantissas and signed zeros."""
+    L = rr.load_library()
+    bad = C.c_ulonglong(12345)
+    assert L.pfgpu_test_div(2_000_000_000, 99, C.byref(bad), 0) == 0, L.pfgpu_last_error()
+    assert bad.value == 0
+
+
 # ------------------------------------------------------------------------------------------------
 # ParticleFilterLocalizer / MonteCarloLocalizer
 # ------------------------------------------------------------------------------------------------
@@ -230,7 +239,8 @@ def test_fastslam_trajectory_bit_exact(oracle, n, side, steps):
         did = g.fastslam_update(sc.control, sc.obs[t])
         odid = o.step(sc.control, sc.obs[t])
         assert did == bool(odid), f"step {t}: gate (neff gpu {g.last_neff()} oracle {o.last_neff()})"
-        assert g.last_neff() == o.last_neff()
+        # neff itself is reported from the tree-order sum unless it is within rounding of NTH (then the exact one decides)
+        assert g.last_neff() == pytest.approx(o.last_neff(), rel=1e-9)
         if did:
             resamples += 1
             idx = g.last_indices()

@@ -310,6 +310,83 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# secondary workloads (BASELINE configs 2 and 5): MonteCarloLocalizer / ParticleFilterLocalizer, single GPU
+# ------------------------------------------------------------------------------------------------
+def run_pf(args):
+    import numpy as np
+    import rust_robotics_b200 as rr
+    from rust_robotics_b200 import scenarios
+    K, W = args.steps, args.warmup
+    n = args.particles
+    mcl = args.workload == "mcl"
+    sc = scenarios.PfScenario("c2" if mcl else "c1", steps=W + 2 * K + 2)
+    if mcl:   # C2: min == max == n, 360 range beams, noises of mcl.rs:490-498
+        g = rr.MonteCarloLocalizer.try_with_initial_state(sc.init, rr.MonteCarloLocalizationConfig(n, n, 0.05, 2.326, 0.25, 0.05, 0.02, 0.1), seed=42)
+    else:     # C5: the C1 model (5 landmarks), resample_threshold from --threshold
+        g = rr.ParticleFilterLocalizer.try_with_initial_state(sc.init, rr.ParticleFilterConfig(n, args.threshold, 0.25), seed=42)
+    obs = [np.ascontiguousarray(o) for o in sc.obs]
+    ctl = [np.asarray(c, dtype=np.float64) for c in sc.controls]
+    t = 0
+    for _ in range(W):
+        g.try_step(ctl[t], obs[t], want_estimate=False); t += 1
+    g.sync()
+    sampler = ClockSampler(0)
+    st0 = g.stats()
+    g.time_main_kernel(True)
+    for k in range(K):
+        g.flush_l2()
+        g.mark(2 * k)
+        g.try_step(ctl[t], obs[t], want_estimate=False); t += 1
+        g.mark(2 * k + 1)
+    g.sync()
+    tt = sum(g.elapsed_ms(2 * k, 2 * k + 1) for k in range(K)) * 1e-3
+    st1 = g.stats()
+    g.time_main_kernel(False)
+    t0 = time.perf_counter()
+    for k in range(K):
+        est = g.try_step(ctl[t], obs[t]); t += 1           # host buffers in, estimate read back every step
+    g.sync()
+    te = time.perf_counter() - t0
+    clocks = sampler.stop()
+    kobs = obs[0].shape[0]
+    kms = st1.main_kernel_ms_sum / max(st1.main_kernel_count, 1)
+    peak, peak_src = load_peaks()
+    alg = n * 72.0                                           # pose record R32 + W32, raw weight W8
+    line = {"metric": "particle-steps/sec", "value": n * K / tt, "unit": "particle-steps/s", "n_gpus": 1, "steps": K, "warmup": W,
+            "ms_per_step": tt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": ("MonteCarloLocalizer try_step (mcl.rs:291-300), BASELINE config 2" if mcl else
+                                    "ParticleFilterLocalizer try_step (pf.rs:488-497), BASELINE config 5 point"),
+                       "particles": n, "observations_per_step": kobs, "resample_threshold": None if mcl else args.threshold,
+                       "resamples_in_timed_steps": int(st1.resamples - st0.resamples), "l2": "flushed before every timed step"},
+            "e2e": {"value": n * K / te, "unit": "particle-steps/s", "h2d_bytes_per_step": 16 + 24 * kobs, "d2h_bytes_per_step": 32},
+            "gpu_launches": int(st1.kernel_launches - st0.kernel_launches),
+            "roofline": {"bound": "hbm", "kernel": "pf_predict_weight_kernel (predict + range likelihood, pf.rs:279-329)",
+                         "achieved": alg / (kms * 1e-3) / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                         "frac": alg / (kms * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": kms,
+                         "note": "FP64-bound when observations_per_step is large (config 2: 360 sqrt+exp+div per particle)"},
+            "clocks": clocks, "serial_fallbacks": int(st1.serial_fallbacks)}
+    if not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import _oracle
+        L = _oracle.load(libm=True)
+        nc = min(n, 1 << 16)
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        threads = min(threads, 64)
+        o = _oracle.OraclePF(L, nc, threshold=args.threshold, range_noise=0.25, velocity_noise=0.05 if mcl else 2.0,
+                             yaw_rate_noise=0.02 if mcl else np.deg2rad(40.0), mode=1 if mcl else 0, max_particles=nc)
+        L.orc_pf_set_fast_search(o.h, 1); L.orc_pf_set_threads(o.h, threads)
+        o.init_state(sc.init)
+        t0 = time.perf_counter(); ks = 0
+        while ks < K and time.perf_counter() - t0 < 12.0:
+            o.step(ctl[ks], obs[ks]); ks += 1
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": nc * ks / dt, "unit": "particle-steps/s", "cores": threads, "kind": "port",
+                                "sample": f"oracle port of {'mcl.rs' if mcl else 'pf.rs'} (C, glibc libm, OpenMP x{threads} over particles, lower_bound "
+                                          f"index search = reference-equivalent), {nc} particles, {ks} steps, {dt:.1f} s"}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -317,10 +394,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs)")
+    ap.add_argument("--workload", default="fastslam", choices=["fastslam", "mcl", "pf"],
+                    help="fastslam = BASELINE config 3 (default, the headline); mcl = config 2; pf = one point of the config-5 sweep")
+    ap.add_argument("--particles", type=int, default=1 << 20, help="mcl / pf workloads only")
+    ap.add_argument("--threshold", type=float, default=1.0, help="pf workload: resample_threshold (1.0 = resample every step)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.workload != "fastslam":
+        if rank == 0:
+            run_pf(args)
+        return
     if args.impl == "reference":
         run_reference(args, rank)
     else:

@@ -226,7 +226,7 @@ class _PfBase:
         return bool(did.value)
 
     def try_step(self, control, observations, want_estimate=True):
-        u = _f64(control)
+        u = control if isinstance(control, np.ndarray) and control.dtype == np.float64 else _f64(control)
         o = _f64(observations).reshape(-1, 3)
         est = np.empty(4)
         _check(self.L, self.L.pfgpu_pf_step(self.h, _dp(u), _dp(o), o.shape[0], _dp(est) if want_estimate else None))

@@ -122,6 +122,8 @@ struct pfgpu_pf {
     KernelTimer timer;
     Marks marks;
     double* h_pin = nullptr;   // pinned scratch (>= 64 doubles)
+    FsShard sh;                // multi-GPU state (world == 1: unused)
+    int cur_host = 0;          // sharded mode: host mirror of *d.cur (the host knows every gate there)
 };
 
 extern "C" void pfgpu_pf_default_config(pfgpu_pf_config* c, int mode) {
@@ -196,6 +198,8 @@ __global__ void pf_pack_kernel(PfDev d, double* aos5) {
 static int pf_refresh_cache(pfgpu_pf* h) {      // refresh_cache pf.rs:499-503
     PF_LAUNCH(h->ctx, pf_moments_kernel, h->mom_blocks, PF_NT, 0, h->d, h->mom_blocks);
     PF_LAUNCH(h->ctx, pf_moments_reduce_kernel, 1, PF_NT, 0, h->d.partial, h->mom_blocks, h->mom15);
+    if (h->world > 1)   // shard moments about the common centre (the previous, replicated estimate) add up
+        PF_NCCL(ncclAllReduce(h->mom15, h->mom15, PF_MOM, ncclDouble, ncclSum, h->sh.comm, h->ctx.stream));
     PF_LAUNCH(h->ctx, pf_moments_final_kernel, 1, 32, 0, h->d, h->mom15);
     return 0;
 }
@@ -227,21 +231,37 @@ static int pf_alloc(pfgpu_pf* h) {
     return xs_work_alloc(h->xs, n);
 }
 
-extern "C" int pfgpu_pf_create(const pfgpu_pf_config* cfg, uint64_t seed, int device, pfgpu_pf** out) {
+static int pf_create_impl(const pfgpu_pf_config* cfg, uint64_t seed, int device, const void* uid, int rank, int world, pfgpu_pf** out) {
     if (!out) return PFGPU_ERR_INVALID;
     *out = nullptr;
     int rc = pfgpu_pf_config_validate(cfg);
     if (rc) return rc;
     if (cfg->mode == 1 && cfg->max_particles != cfg->n_particles) return PFGPU_ERR_UNSUPPORTED;   // KLD-adaptive N: SURVEY.md §8(f) row 3
     if (cfg->n_particles > 0xFFFFFFFFull) return PFGPU_ERR_UNSUPPORTED;
+    if (world > 1 && (cfg->n_particles % (uint64_t)world) != 0) return PFGPU_ERR_INVALID;
     pfgpu_pf* h = new (std::nothrow) pfgpu_pf();
     if (!h) return PFGPU_ERR_CUDA;
     rc = ctx_open(h->ctx, device);
     if (rc) { delete h; return rc; }
-    h->cfg = *cfg; h->seed = seed;
-    h->d.n = h->d.n_global = cfg->n_particles; h->d.offset = 0;
+    h->cfg = *cfg; h->seed = seed; h->world = world; h->rank = rank;
+    h->d.n_global = cfg->n_particles; h->d.n = cfg->n_particles / (uint64_t)world; h->d.offset = (size_t)rank * h->d.n;
     rc = pf_alloc(h);
     if (rc) { pfgpu_pf_destroy(h); return rc; }
+    if (world > 1) {
+        FsShard& sh = h->sh;
+        sh.rank = rank; sh.world = world;
+        ncclUniqueId id;
+        memcpy(&id, uid, sizeof(id));
+        ncclResult_t nr = ncclCommInitRank(&sh.comm, world, id, rank);
+        if (nr != ncclSuccess) { snprintf(g_pfgpu_err, sizeof(g_pfgpu_err), "ncclCommInitRank: %s", ncclGetErrorString(nr)); pfgpu_pf_destroy(h); return PFGPU_ERR_NCCL; }
+        const size_t ng = h->d.n_global;
+        bool ok = cudaMalloc(&sh.t_loc, sizeof(double)) == cudaSuccess && cudaMalloc(&sh.t_all, world * sizeof(double)) == cudaSuccess &&
+                  cudaMalloc(&sh.approx_off, sizeof(double)) == cudaSuccess && cudaMalloc(&sh.sum_loc, sizeof(ShardSummary)) == cudaSuccess &&
+                  cudaMalloc(&sh.sum_all, world * sizeof(ShardSummary)) == cudaSuccess && cudaMalloc(&sh.s_start, sizeof(double)) == cudaSuccess &&
+                  cudaMalloc(&sh.err, sizeof(int)) == cudaSuccess && cudaMemset(sh.err, 0, sizeof(int)) == cudaSuccess &&
+                  cudaMalloc(&sh.cum_all, ng * sizeof(double)) == cudaSuccess && cudaMalloc(&sh.pose_all, 4 * ng * sizeof(double)) == cudaSuccess;
+        if (!ok) { pfgpu_pf_destroy(h); return PFGPU_ERR_CUDA; }
+    }
     PF_LAUNCH(h->ctx, pf_init_zero_kernel, cdiv_u(h->d.n, PF_NT), PF_NT, 0, h->d);
     rc = pf_refresh_cache(h);
     if (rc) { pfgpu_pf_destroy(h); return rc; }
@@ -249,9 +269,13 @@ extern "C" int pfgpu_pf_create(const pfgpu_pf_config* cfg, uint64_t seed, int de
     *out = h;
     return PFGPU_OK;
 }
-extern "C" int pfgpu_pf_create_sharded(const pfgpu_pf_config*, uint64_t, int, const void*, int, int, pfgpu_pf** out) {
+extern "C" int pfgpu_pf_create(const pfgpu_pf_config* cfg, uint64_t seed, int device, pfgpu_pf** out) {
+    return pf_create_impl(cfg, seed, device, nullptr, 0, 1, out);
+}
+extern "C" int pfgpu_pf_create_sharded(const pfgpu_pf_config* cfg, uint64_t seed, int device, const void* uid, int rank, int world, pfgpu_pf** out) {
     if (out) *out = nullptr;
-    return PFGPU_ERR_UNSUPPORTED;
+    if (!uid || world < 1 || world > SH_MAX_WORLD || rank < 0 || rank >= world) return PFGPU_ERR_INVALID;
+    return pf_create_impl(cfg, seed, device, uid, rank, world, out);
 }
 extern "C" void pfgpu_pf_destroy(pfgpu_pf* h) {
     if (!h) return;
@@ -261,6 +285,12 @@ extern "C" void pfgpu_pf_destroy(pfgpu_pf* h) {
     cudaFree(d.pose[0]); cudaFree(d.pose[1]); cudaFree(d.cur); cudaFree(d.w_raw); cudaFree(d.w); cudaFree(d.cum);
     cudaFree(d.idx); cudaFree(d.scal); cudaFree(d.gate); cudaFree(d.partial); cudaFree(d.obs); cudaFree(h->mom15); cudaFree(d.counters);
     if (h->h_pin) cudaFreeHost(h->h_pin);
+    {
+        FsShard& sh = h->sh;
+        cudaFree(sh.t_loc); cudaFree(sh.t_all); cudaFree(sh.approx_off); cudaFree(sh.sum_loc); cudaFree(sh.sum_all); cudaFree(sh.s_start);
+        cudaFree(sh.err); cudaFree(sh.cum_all); cudaFree(sh.pose_all);
+        if (sh.comm) ncclCommDestroy(sh.comm);
+    }
     marks_free(h->marks);
     xs_work_free(h->xs);
     for (auto& p : h->timer.pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
@@ -347,14 +377,67 @@ static int pf_launch_main(pfgpu_pf* h, const double u[2], const double* obs3, si
     return 0;
 }
 // normalize_weights: exact sequential sum of the raw weights, then the division pass
+// global index search + pose gather of the sharded mode (pose_all = ncclAllGather of the 32-byte records, rank order)
+__global__ void __launch_bounds__(PF_NT) pf_search_sharded_kernel(PfDev d, const double* cum_all, uint64_t seed, int mode) {
+    if (!*d.gate) return;
+    const size_t t = (size_t)blockIdx.x * PF_NT + threadIdx.x;
+    if (t >= d.n) return;
+    double r = pfc_u01_53(pfc_blk_u64(pfc_rng_block(seed, PFC_STREAM_PF_RESAMPLE, d.counters[0], d.offset + t), 0));
+    size_t lo = 0, hi = d.n_global;
+    while (lo < hi) {
+        size_t mid = lo + ((hi - lo) >> 1);
+        if (cum_all[mid] < r) lo = mid + 1; else hi = mid;
+    }
+    d.idx[t] = (uint32_t)(lo < d.n_global ? lo : (mode == 1 ? d.n_global - 1 : 0));
+}
+__global__ void __launch_bounds__(PF_NT) pf_gather_sharded_kernel(PfDev d, const Pose4* pose_all) {
+    if (!*d.gate) return;
+    const size_t t = (size_t)blockIdx.x * PF_NT + threadIdx.x;
+    if (t >= d.n) return;
+    Pose4 p;
+    pose_load(pose_all, d.idx[t], p);
+    pose_store(pf_pose(d, *d.cur ^ 1), t, p);
+    d.w[t] = 1.0 / (double)d.n_global;
+}
+template <class F>
+static int pf_total(pfgpu_pf* h, F f, double* out) {
+    if (h->world > 1) return xs_total_sharded(h->ctx, h->xs, h->sh, f, h->d.n, h->d.n_global, out);
+    return xs_total(h->ctx, h->xs, f, h->d.n, h->d.n_global, 0.0, out);
+}
+static int pf_resample_sharded(pfgpu_pf* h) {
+    PfDev& d = h->d; FsShard& sh = h->sh; Ctx& ctx = h->ctx;
+    int rc = xs_total_sharded(ctx, h->xs, sh, PfValWSq{d.w}, d.n, d.n_global, d.scal + 1);          // calc_n_eff pf.rs:416-423
+    if (rc) return rc;
+    PF_LAUNCH(ctx, pf_gate_kernel, 1, 1, 0, d, h->cfg.resample_threshold, h->cfg.mode);
+    int gate = 1;
+    int* hp = reinterpret_cast<int*>(h->h_pin + 32);
+    // the collectives below are host-enqueued: every rank must know the gate (MCL: always open, mcl.rs:298)
+    PF_CUDA(cudaMemcpyAsync(hp, d.gate, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+    PF_CUDA(cudaMemcpyAsync(hp + 1, sh.err, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+    PF_CUDA(cudaStreamSynchronize(ctx.stream));
+    if (hp[1]) { snprintf(g_pfgpu_err, sizeof(g_pfgpu_err), "sharded exact sum: a shard was not summarisable (degenerate weights)"); return PFGPU_ERR_UNSUPPORTED; }
+    gate = *hp;
+    if (!gate) return 0;
+    rc = xs_scan_sharded(ctx, h->xs, sh, XsValArray{d.w}, XsSinkStore{d.cum}, d.n, d.n_global, d.scal + 2);   // pf.rs:448-453
+    if (rc) return rc;
+    if (h->cfg.mode == 1 && sh.rank == sh.world - 1) PF_LAUNCH(ctx, pf_force_last_kernel, 1, 1, 0, d);        // mcl.rs:334-336
+    PF_NCCL(ncclAllGather(d.cum, sh.cum_all, d.n, ncclDouble, sh.comm, ctx.stream));
+    PF_LAUNCH(ctx, pf_search_sharded_kernel, cdiv_u(d.n, PF_NT), PF_NT, 0, d, sh.cum_all, h->seed, h->cfg.mode);
+    PF_NCCL(ncclAllGather(d.pose[h->cur_host], sh.pose_all, 4 * d.n, ncclDouble, sh.comm, ctx.stream));
+    PF_LAUNCH(ctx, pf_gather_sharded_kernel, cdiv_u(d.n, PF_NT), PF_NT, 0, d, reinterpret_cast<const Pose4*>(sh.pose_all));
+    PF_LAUNCH(ctx, pf_flip_kernel, 1, 1, 0, d);
+    h->cur_host ^= 1;
+    return 0;
+}
 static int pf_normalize(pfgpu_pf* h) {
-    int rc = xs_total(h->ctx, h->xs, XsValArray{h->d.w_raw}, h->d.n, h->d.n_global, 0.0, h->d.scal + 0);
+    int rc = pf_total(h, XsValArray{h->d.w_raw}, h->d.scal + 0);
     if (rc) return rc;
     PF_LAUNCH(h->ctx, pf_normalize_kernel, cdiv_u(h->d.n, PF_NT), PF_NT, 0, h->d);
     return 0;
 }
 static int pf_resample_impl(pfgpu_pf* h) {
     PfDev& d = h->d;
+    if (h->world > 1) return pf_resample_sharded(h);
     int rc = xs_total(h->ctx, h->xs, PfValWSq{d.w}, d.n, d.n_global, 0.0, d.scal + 1);        // calc_n_eff pf.rs:416-423
     if (rc) return rc;
     PF_LAUNCH(h->ctx, pf_gate_kernel, 1, 1, 0, d, h->cfg.resample_threshold, h->cfg.mode);
@@ -444,7 +527,7 @@ extern "C" int pfgpu_pf_estimate(pfgpu_pf* h, double est[4], double cov_cm[16]) 
 extern "C" int pfgpu_pf_neff(pfgpu_pf* h, double* neff) {
     if (!h || !neff) return PFGPU_ERR_INVALID;
     PF_CUDA(cudaSetDevice(h->ctx.device));
-    int rc = xs_total(h->ctx, h->xs, PfValWSq{h->d.w}, h->d.n, h->d.n_global, 0.0, h->d.scal + 1);
+    int rc = pf_total(h, PfValWSq{h->d.w}, h->d.scal + 1);
     if (rc) return rc;
     PF_CUDA(cudaMemcpyAsync(h->h_pin, h->d.scal + 1, sizeof(double), cudaMemcpyDeviceToHost, h->ctx.stream));
     PF_CUDA(cudaStreamSynchronize(h->ctx.stream));

@@ -14,11 +14,48 @@ from rust_robotics_b200 import dist as rdist, scenarios  # noqa: E402
 import _oracle  # noqa: E402
 
 
+def run_pf(kind, rank, world, local, n_global, steps, uid):
+    """sharded ParticleFilterLocalizer / MonteCarloLocalizer vs the full-size oracle"""
+    mcl = kind == "mcl"
+    sc = scenarios.PfScenario("c2" if mcl else "c1", steps=steps)
+    L = _oracle.load(libm=False)
+    if mcl:
+        g = rr.MonteCarloLocalizer(rr.MonteCarloLocalizationConfig(n_global, n_global, 0.05, 2.326, 0.25, 0.05, 0.02, 0.1), seed=5, device=local,
+                                   shard=(uid, rank, world))
+        o = _oracle.OraclePF(L, n_global, range_noise=0.25, velocity_noise=0.05, yaw_rate_noise=0.02, seed=5, mode=1, max_particles=n_global)
+    else:
+        g = rr.ParticleFilterLocalizer(rr.ParticleFilterConfig(n_global, 0.6, 0.25), seed=5, device=local, shard=(uid, rank, world))
+        o = _oracle.OraclePF(L, n_global, threshold=0.6, range_noise=0.25, seed=5)
+    L.orc_pf_set_fast_search(o.h, 1)
+    rc = g.L.pfgpu_pf_init_state(g.h, rr.api._dp(np.asarray(sc.init, dtype=np.float64)))
+    assert rc == 0
+    o.init_state(sc.init)
+    lo, hi = rdist.shard_bounds(n_global, rank, world)
+    resamples = 0
+    for t in range(steps):
+        obs = sc.obs[t][:: max(1, sc.obs[t].shape[0] // 24)] if mcl else sc.obs[t]
+        ge = g.try_step(sc.controls[t], obs)
+        oe, did = o.step(sc.controls[t], obs)
+        assert np.allclose(ge, oe, rtol=1e-6, atol=1e-9), f"rank {rank} step {t}: estimate {ge} vs {oe}"
+        if did:
+            resamples += 1
+            assert np.array_equal(g.last_indices(), o.last_indices()[lo:hi]), f"rank {rank} step {t}: indices"
+    assert np.array_equal(g.get_particles(), o.particles()[lo:hi]), f"rank {rank}: particles differ"
+    assert resamples > 0
+    dist.barrier()
+    if rank == 0:
+        print(f"MGPU_OK kind={kind} world={world} n={n_global} resamples={resamples}")
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    n_global, side, steps = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
     dist.init_process_group("gloo", init_method="env://")
     uid = rdist.broadcast_unique_id(dist, rdist.nccl_unique_id, rank)
+    if sys.argv[1] in ("pf", "mcl"):
+        run_pf(sys.argv[1], rank, world, local, int(sys.argv[2]), int(sys.argv[3]), uid)
+        dist.destroy_process_group()
+        return
+    n_global, side, steps = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
     sc = scenarios.FastSlamScenario(side, (10.0 * side / 2 - 5.0, 10.0 * side / 2 - 5.0, 0.0), (1.0, 0.025), steps)
     g = rr.FastSlam1(n_global, sc.m, rr.FsConfig(nth=n_global / 1.5), seed=9, device=local, shard=(uid, rank, world))
     L = _oracle.load(libm=False)

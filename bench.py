@@ -235,15 +235,24 @@ def run_ours(args, rank, world, local_rank):
     g.time_main_kernel(True)
     barrier()
     first = step
+    flush_mode = os.environ.get("BENCH_FLUSH_MODE", "flush")
     for t in range(K):
-        g.flush_l2()
-        if dist is not None:
-            barrier()            # ranks enter the timed step together: a peer still flushing would otherwise be billed to the step
+        if flush_mode != "none":
+            g.flush_l2()
+        if flush_mode == "flush_sync":
+            g.sync()
+        if dist is not None and os.environ.get("BENCH_STEP_BARRIER", "0") == "1":
+            barrier()            # optional: ranks enter the timed step together (costs a host round trip per step)
         g.mark(2 * t)
         g.fastslam_update(sc.control, sc.obs[step], want_flag=False, obs_array=arrs[step]); step += 1
         g.mark(2 * t + 1)
     barrier()
     step_ms = [g.elapsed_ms(2 * t, 2 * t + 1) for t in range(K)]
+    if os.environ.get("BENCH_VERBOSE") and rank == 0:
+        ss = sorted(step_ms)
+        sys.stderr.write("step ms: min %.3f  p50 %.3f  p90 %.3f  p99 %.3f  max %.3f  sum %.1f; worst steps %s\n" % (
+            ss[0], ss[len(ss) // 2], ss[int(len(ss) * 0.9)], ss[int(len(ss) * 0.99)], ss[-1], sum(ss),
+            sorted(range(K), key=lambda i: -step_ms[i])[:8]))
     st1 = g.stats()
     g.time_main_kernel(False)
     t_flushed = maxr(sum(step_ms) * 1e-3)
@@ -293,7 +302,9 @@ def run_ours(args, rank, world, local_rank):
         line = {"metric": "particle-steps/sec", "value": n_global * K / t_flushed, "unit": "particle-steps/s",
                 "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_flushed / K * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": dict(workload_config(sc, world), resamples_in_timed_steps=int(resamples)),
+                "config": dict(workload_config(sc, world), resamples_in_timed_steps=int(resamples),
+                               **({"imported_particles_rank0": int(st1.imported_particles - st0.imported_particles),
+                                   "guest_compactions_rank0": int(st1.compactions - st0.compactions)} if world > 1 else {})),
                 "value_steady_state_no_flush": n_global * K / t_noflush,
                 "e2e": {"value": n_global * K / t_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d / K,
                         "d2h_bytes_per_step": d2h / K},

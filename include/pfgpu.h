@@ -146,6 +146,8 @@ typedef struct {
     uint64_t xsum_dirty_last;    /* dirty elements in the most recent exact scan */
     double   main_kernel_ms_sum; /* sum of CUDA-event times of the dominant kernel when timing is on */
     uint64_t main_kernel_count;
+    uint64_t compactions;        /* sharded FastSLAM: guest-column compactions so far */
+    uint64_t imported_particles; /* sharded FastSLAM: particles whose map came from another rank so far */
 } pfgpu_stats;
 int  pfgpu_pf_stats(pfgpu_pf*, pfgpu_stats*);
 int  pfgpu_fs_stats(pfgpu_fs*, pfgpu_stats*);

@@ -47,7 +47,8 @@ class _FsObs(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("steps", C.c_uint64), ("resamples", C.c_uint64),
                 ("serial_fallbacks", C.c_uint64), ("xsum_dirty_last", C.c_uint64),
-                ("main_kernel_ms_sum", C.c_double), ("main_kernel_count", C.c_uint64)]
+                ("main_kernel_ms_sum", C.c_double), ("main_kernel_count", C.c_uint64), ("compactions", C.c_uint64),
+                ("imported_particles", C.c_uint64)]
 
 
 EXPORTS = [

@@ -47,6 +47,8 @@ struct FsDev {
     int* lmstate = nullptr;                  // device [m]: bit0 = buffer holding landmark l, bit1 = ancestry is the identity
     int eager = 0;                           // 1 (sharded mode): maps are cloned eagerly; every landmark lives in buffer *cur
     int anc16 = 0;                           // 1: ancestry columns hold u16 (n <= 65 536)
+    size_t ld = 0;                           // column stride of the landmark arrays: n, plus the GUEST columns of sharded mode
+                                             // (maps imported from other ranks live in columns [n, ld) until the next compaction)
 };
 
 // Observation lists of up to FS_PARAM_OBS entries travel inside the kernel's launch parameters (no H2D copy).
@@ -180,15 +182,15 @@ __global__ void __launch_bounds__(FS_NT) fs_step_kernel(FsDev d, const __grid_co
         double* __restrict__ dst = fs_lm(d, ident ? (st & 1) : ((st & 1) ^ 1));
         const size_t col = ident ? i : fs_anc_load(d, anc_c, l * n + i);       // lazy clone: read the ancestor's copy
         FsLm L;
-        L.x = src[lm_index(n, l, 0, col)]; L.y = src[lm_index(n, l, 1, col)];
-        L.c00 = src[lm_index(n, l, 2, col)]; L.c01 = src[lm_index(n, l, 3, col)];
-        L.c10 = src[lm_index(n, l, 4, col)]; L.c11 = src[lm_index(n, l, 5, col)];
+        L.x = src[lm_index(d.ld, l, 0, col)]; L.y = src[lm_index(d.ld, l, 1, col)];
+        L.c00 = src[lm_index(d.ld, l, 2, col)]; L.c01 = src[lm_index(d.ld, l, 3, col)];
+        L.c10 = src[lm_index(d.ld, l, 4, col)]; L.c11 = src[lm_index(d.ld, l, 5, col)];
         bool wrote_cov;
         double lik = fs_update_landmark(L, px, py, pyaw, zd, za, r00, r11, &wrote_cov);
-        dst[lm_index(n, l, 0, i)] = L.x; dst[lm_index(n, l, 1, i)] = L.y;
+        dst[lm_index(d.ld, l, 0, i)] = L.x; dst[lm_index(d.ld, l, 1, i)] = L.y;
         if (wrote_cov || !ident) {                             // a materialising write must carry the covariance too
-            dst[lm_index(n, l, 2, i)] = L.c00; dst[lm_index(n, l, 3, i)] = L.c01;
-            dst[lm_index(n, l, 4, i)] = L.c10; dst[lm_index(n, l, 5, i)] = L.c11;
+            dst[lm_index(d.ld, l, 2, i)] = L.c00; dst[lm_index(d.ld, l, 3, i)] = L.c01;
+            dst[lm_index(d.ld, l, 4, i)] = L.c10; dst[lm_index(d.ld, l, 5, i)] = L.c11;
         }
         if (wrote_cov) w = w * lik;                            // fs1.rs:181 (only when det_s > 0: lik == 1.0 otherwise)
     }
@@ -241,19 +243,20 @@ __global__ void __launch_bounds__(MAXT, MINB) fs_ekf_kernel(FsDev d, const __gri
     const size_t l = (size_t)ob.lm_id;
     const int st = d.lmstate[l];
     const bool ident = (st & 2) != 0;
-    const double* __restrict__ src = fs_lm(d, st & 1) + l * 6 * n;
-    double* __restrict__ dst = fs_lm(d, ident ? (st & 1) : ((st & 1) ^ 1)) + l * 6 * n + i;
+    const size_t ld = d.ld;
+    const double* __restrict__ src = fs_lm(d, st & 1) + l * 6 * ld;
+    double* __restrict__ dst = fs_lm(d, ident ? (st & 1) : ((st & 1) ^ 1)) + l * 6 * ld + i;
     bool wrote_cov = false;
     double lik = 1.0;
     if (valid) {
         const size_t col = ident ? i : fs_anc_load(d, *d.anc_cur, l * n + i);     // lazy clone: the ancestor's copy
         const double* __restrict__ sp = src + col;
         FsLm L;
-        L.x = sp[0]; L.y = sp[n]; L.c00 = sp[2 * n]; L.c01 = sp[3 * n]; L.c10 = sp[4 * n]; L.c11 = sp[5 * n];
+        L.x = sp[0]; L.y = sp[ld]; L.c00 = sp[2 * ld]; L.c01 = sp[3 * ld]; L.c10 = sp[4 * ld]; L.c11 = sp[5 * ld];
         const double px = fs_px(d, cur)[i], py = fs_py(d, cur)[i], pyaw = fs_pyaw(d, cur)[i];
         lik = fs_update_landmark(L, px, py, pyaw, ob.d, ob.angle, r00, r11, &wrote_cov);
-        dst[0] = L.x; dst[n] = L.y;
-        if (wrote_cov || !ident) { dst[2 * n] = L.c00; dst[3 * n] = L.c01; dst[4 * n] = L.c10; dst[5 * n] = L.c11; }
+        dst[0] = L.x; dst[ld] = L.y;
+        if (wrote_cov || !ident) { dst[2 * ld] = L.c00; dst[3 * ld] = L.c01; dst[4 * ld] = L.c10; dst[5 * ld] = L.c11; }
     }
     s_lik[wj * 32 + lane] = lik;
     const unsigned mask = __ballot_sync(0xffffffffu, wrote_cov);
@@ -456,7 +459,7 @@ __global__ void __launch_bounds__(256) fs_unpack_lm_kernel(FsDev d, const double
     if (e >= tot) return;
     size_t ip = e / (d.m * 6), rem = e % (d.m * 6);
     size_t l = rem / 6; int f = (int)(rem % 6);
-    fs_lm(d, d.eager ? *d.cur : 0)[lm_index(d.n, l, f, i0 + ip)] = aos[e];
+    fs_lm(d, d.eager ? *d.cur : 0)[lm_index(d.ld, l, f, i0 + ip)] = aos[e];
 }
 __global__ void __launch_bounds__(256) fs_pack_lm_kernel(FsDev d, double* aos, size_t i0, size_t cnt) {
     const size_t e = (size_t)blockIdx.x * 256 + threadIdx.x;
@@ -466,7 +469,7 @@ __global__ void __launch_bounds__(256) fs_pack_lm_kernel(FsDev d, double* aos, s
     size_t l = rem / 6; int f = (int)(rem % 6);
     const int st = d.lmstate[l];
     const size_t col = (st & 2) ? (i0 + ip) : fs_anc_load(d, *d.anc_cur, l * d.n + i0 + ip);   // materialise through the ancestry
-    aos[e] = fs_lm(d, st & 1)[lm_index(d.n, l, f, col)];
+    aos[e] = fs_lm(d, st & 1)[lm_index(d.ld, l, f, col)];
 }
 __global__ void fs_lmstate_reset_kernel(FsDev d) {     // every landmark identity-mapped in buffer 0 (eager mode: *cur) after init/upload/seed
     const int buf = d.eager ? *d.cur : 0;
@@ -479,9 +482,9 @@ __global__ void __launch_bounds__(256) fs_init_kernel(FsDev d, double init_weigh
     d.w[i] = init_weight; d.w_raw[i] = init_weight;
     d.px[0][i] = 0.0; d.py[0][i] = 0.0; d.pyaw[0][i] = 0.0;
     for (size_t l = 0; l < d.m; ++l) {
-        d.lm[0][lm_index(d.n, l, 0, i)] = 0.0; d.lm[0][lm_index(d.n, l, 1, i)] = 0.0;
-        d.lm[0][lm_index(d.n, l, 2, i)] = 1000.0; d.lm[0][lm_index(d.n, l, 3, i)] = 0.0;
-        d.lm[0][lm_index(d.n, l, 4, i)] = 0.0; d.lm[0][lm_index(d.n, l, 5, i)] = 1000.0;
+        d.lm[0][lm_index(d.ld, l, 0, i)] = 0.0; d.lm[0][lm_index(d.ld, l, 1, i)] = 0.0;
+        d.lm[0][lm_index(d.ld, l, 2, i)] = 1000.0; d.lm[0][lm_index(d.ld, l, 3, i)] = 0.0;
+        d.lm[0][lm_index(d.ld, l, 4, i)] = 0.0; d.lm[0][lm_index(d.ld, l, 5, i)] = 1000.0;
     }
 }
 
@@ -500,8 +503,8 @@ __global__ void __launch_bounds__(256) fs_seed_lm_kernel(FsDev d, const double* 
     double* lm = fs_lm(d, d.eager ? *d.cur : 0);
     double z0, z1;
     pfc_normal_pair(pfc_rng_block(seed, PFC_STREAM_INIT_A, 0, (d.offset + i) * d.m + l), &z0, &z1);
-    lm[lm_index(d.n, l, 0, i)] = lm_xy[2 * l] + sigma * z0;
-    lm[lm_index(d.n, l, 1, i)] = lm_xy[2 * l + 1] + sigma * z1;
-    lm[lm_index(d.n, l, 2, i)] = cov0; lm[lm_index(d.n, l, 3, i)] = 0.0;
-    lm[lm_index(d.n, l, 4, i)] = 0.0; lm[lm_index(d.n, l, 5, i)] = cov0;
+    lm[lm_index(d.ld, l, 0, i)] = lm_xy[2 * l] + sigma * z0;
+    lm[lm_index(d.ld, l, 1, i)] = lm_xy[2 * l + 1] + sigma * z1;
+    lm[lm_index(d.ld, l, 2, i)] = cov0; lm[lm_index(d.ld, l, 3, i)] = 0.0;
+    lm[lm_index(d.ld, l, 4, i)] = 0.0; lm[lm_index(d.ld, l, 5, i)] = cov0;
 }

@@ -637,8 +637,10 @@ static int fs_create_impl(const pfgpu_fs_config* cfg, size_t n, size_t n_global,
     if (rc) { delete h; return rc; }
     h->cfg = *cfg; h->seed = seed; h->world = world; h->rank = rank;
     FsDev& d = h->d;
-    d.n = n; d.n_global = n_global; d.offset = offset; d.m = m; d.eager = world > 1 ? 1 : 0;
-    h->lm_bytes = (m ? m : 1) * 6 * n * sizeof(double);
+    d.n = n; d.n_global = n_global; d.offset = offset; d.m = m; d.eager = 0;
+    h->sh.n_guest = world > 1 ? std::max<size_t>(2048, n / 8) : 0;
+    d.ld = n + h->sh.n_guest;
+    h->lm_bytes = (m ? m : 1) * 6 * d.ld * sizeof(double);
     auto fail = [&](int code) { pfgpu_fs_destroy(h); return code; };
 #define FS_TRY(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { snprintf(g_pfgpu_err, sizeof(g_pfgpu_err), "%s -> %s", #x, cudaGetErrorString(e__)); return fail(PFGPU_ERR_CUDA); } } while (0)
     for (int b = 0; b < 2; ++b) {
@@ -713,6 +715,26 @@ static int fs_create_impl(const pfgpu_fs_config* cfg, size_t n, size_t n_global,
         SH_TRY(cudaMalloc(&sh.cum_all, n_global * sizeof(double))); SH_TRY(cudaMalloc(&sh.idx_all, n_global * sizeof(uint32_t)));
         SH_TRY(cudaMalloc(&sh.pose_all, 3 * n_global * sizeof(double))); SH_TRY(cudaMallocHost(&sh.h_idx, n_global * sizeof(uint32_t)));
         SH_TRY(cudaMalloc(&sh.best_loc, 8 * sizeof(double))); SH_TRY(cudaMalloc(&sh.best_all, 8 * world * sizeof(double)));
+        {   // NCCL sets up peer connections lazily, on the first send/recv or collective of each kind (>100 ms once): do it here,
+            // not inside somebody's timed step
+            PF_NCCL(ncclAllGather(sh.t_loc, sh.t_all, 1, ncclDouble, sh.comm, h->ctx.stream));
+            PF_NCCL(ncclAllGather(sh.sum_loc, sh.sum_all, sizeof(ShardSummary), ncclChar, sh.comm, h->ctx.stream));
+            PF_NCCL(ncclAllGather(d.idx, sh.idx_all, n, ncclUint32, sh.comm, h->ctx.stream));
+            PF_NCCL(ncclAllGather(d.cum, sh.cum_all, n, ncclDouble, sh.comm, h->ctx.stream));
+            PF_NCCL(ncclGroupStart());
+            for (int g = 0; g < world; ++g) {
+                if (g == rank) continue;
+                PF_NCCL(ncclSend(sh.best_loc, 8, ncclDouble, g, sh.comm, h->ctx.stream));
+                PF_NCCL(ncclRecv(sh.best_all + 8 * g, 8, ncclDouble, g, sh.comm, h->ctx.stream));
+            }
+            PF_NCCL(ncclGroupEnd());
+            SH_TRY(cudaStreamSynchronize(h->ctx.stream));
+        }
+        {   // exchange buffers sized for the worst admissible resample up front: no cudaMalloc on the step path
+            size_t cap = std::max<size_t>(3 * n, sh.n_guest * 6 * (m ? m : 1)) + 1024;
+            SH_TRY(cudaMalloc(&sh.sendbuf, cap * sizeof(double))); sh.send_cap = cap;
+            SH_TRY(cudaMalloc(&sh.recvbuf, cap * sizeof(double))); sh.recv_cap = cap;
+        }
 #undef SH_TRY
     }
     fs_init_kernel<<<cdiv_u(n, 256), 256, 0, h->ctx.stream>>>(d, cfg->init_weight);
@@ -860,14 +882,41 @@ static int fs_post_sharded(pfgpu_fs* h) {
     int rc = xs_total_sharded(ctx, h->xs, sh, XsValArray{d.w_raw}, nl, ng, d.scal + 0);              // fs1.rs:259
     if (rc) return rc;
     PF_LAUNCH(ctx, fs_normalize_kernel, cdiv_u(nl, 256), 256, 0, d);
-    rc = xs_total_sharded(ctx, h->xs, sh, FsValWSq{d.w}, nl, ng, d.scal + 1);                        // fs1.rs:262
-    if (rc) return rc;
-    PF_LAUNCH(ctx, fs_gate_kernel, 1, 1, 0, d, h->cfg.nth);
+    // gate (fs1.rs:262-263): tree-order sum of w^2 first (one small allgather); the exact sequential sum only when neff is
+    // within rounding of NTH — same decision as the reference in every case (see fs_post.cuh)
     int* hp = reinterpret_cast<int*>(h->h_pin + 32);
-    PF_CUDA(cudaMemcpyAsync(hp, d.gate, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
-    PF_CUDA(cudaMemcpyAsync(hp + 1, sh.err, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
-    PF_CUDA(cudaStreamSynchronize(ctx.stream));
+    double* hq = h->h_pin + 40;
+    {
+        unsigned nt = cdiv_u(nl, XS_TILE);
+        PF_CUDA(cudaMemsetAsync(h->xs.flags, 0, 4 * sizeof(int), ctx.stream));
+        PF_LAUNCH(ctx, xs_tile_sums<FsValWSq>, nt, XS_NT, 0, FsValWSq{d.w}, nl, h->xs);
+        PF_LAUNCH(ctx, sh_local_total_kernel, 1, 256, 0, h->xs.tsum, nt, sh.t_loc);
+        PF_NCCL(ncclAllGather(sh.t_loc, sh.t_all, 1, ncclDouble, sh.comm, ctx.stream));
+        PF_CUDA(cudaMemcpyAsync(hq, sh.t_all, sh.world * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+        PF_CUDA(cudaMemcpyAsync(hp + 1, sh.err, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+        PF_CUDA(cudaMemcpyAsync(hp + 2, h->xs.flags + 3, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+        PF_CUDA(cudaStreamSynchronize(ctx.stream));
+    }
     if (hp[1]) { snprintf(g_pfgpu_err, sizeof(g_pfgpu_err), "sharded exact sum: a shard was not summarisable (degenerate weights)"); return PFGPU_ERR_UNSUPPORTED; }
+    double Qa = 0.0;
+    for (int g = 0; g < sh.world; ++g) Qa += hq[g];                       // same order on every rank: identical value
+    double neff = Qa > 0.0 ? 1.0 / Qa : 0.0;
+    const double slack = 8.0 * (double)(ng + 64) * 2.220446049250313e-16;
+    const bool border = !(std::fabs(neff - h->cfg.nth) > slack * std::fmax(std::fabs(h->cfg.nth), std::fabs(neff))) || hp[2] != 0;
+    if (border) {
+        rc = xs_total_sharded(ctx, h->xs, sh, FsValWSq{d.w}, nl, ng, d.scal + 1);                    // fs1.rs:262, exact
+        if (rc) return rc;
+        PF_LAUNCH(ctx, fs_gate_kernel, 1, 1, 0, d, h->cfg.nth);
+        PF_CUDA(cudaMemcpyAsync(hp, d.gate, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+        PF_CUDA(cudaStreamSynchronize(ctx.stream));
+    } else {
+        *hp = neff < h->cfg.nth ? 1 : 0;
+        double* hs = h->h_pin + 60;
+        hs[0] = Qa; hs[1] = neff;
+        PF_CUDA(cudaMemcpyAsync(d.scal + 1, hs, sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+        PF_CUDA(cudaMemcpyAsync(d.scal + 3, hs + 1, sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+        PF_CUDA(cudaMemcpyAsync(d.gate, hp, sizeof(int), cudaMemcpyHostToDevice, ctx.stream));
+    }
     if (!*hp) return 0;
     // ---------------- resample fs1.rs:206-234 ----------------
     rc = xs_total_sharded(ctx, h->xs, sh, XsValArray{d.w}, nl, ng, d.scal + 2);                      // fs1.rs:207
@@ -899,22 +948,30 @@ static int fs_post_sharded(pfgpu_fs* h) {
         if ((size_t)(src + 1) * nl > 0xFFFFFFFFull) b1 = nl;
         *lo = (size_t)dst * nl + b0; *hi = (size_t)dst * nl + b1;
     };
-    size_t send_tot = 0, recv_tot = 0;
+    size_t send_tot = 0, recv_tot = 0, recv_cnt = 0;
     size_t s_lo[SH_MAX_WORLD], s_hi[SH_MAX_WORLD], r_lo[SH_MAX_WORLD], r_hi[SH_MAX_WORLD];
     for (int g = 0; g < G; ++g) {
         s_lo[g] = s_hi[g] = r_lo[g] = r_hi[g] = 0;
         if (g == me) continue;
         run_of(g, me, &s_lo[g], &s_hi[g]);           // what I send to g
         run_of(me, g, &r_lo[g], &r_hi[g]);           // what I receive from g
-        send_tot += (s_hi[g] - s_lo[g]) * rows; recv_tot += (r_hi[g] - r_lo[g]) * rows;
+        send_tot += (s_hi[g] - s_lo[g]) * rows; recv_tot += (r_hi[g] - r_lo[g]) * rows; recv_cnt += r_hi[g] - r_lo[g];
+    }
+    if (recv_cnt > sh.n_guest) { snprintf(g_pfgpu_err, sizeof(g_pfgpu_err), "resample imports %zu particles, guest capacity %zu", recv_cnt, sh.n_guest); return PFGPU_ERR_UNSUPPORTED; }
+    if (rows && sh.guest_used + recv_cnt > sh.n_guest) {   // guests exhausted: compact (everything identity-mapped, all guests free)
+        dim3 cg(cdiv_u(nl, 256), cdiv_u(d.m, 4));
+        PF_LAUNCH(ctx, sh_compact_kernel, cg, 256, 0, d);
+        PF_LAUNCH(ctx, sh_compact_finish_kernel, 1, 256, 0, d);
+        sh.guest_used = 0; sh.compactions++;
     }
     rc = sh_grow(&sh.sendbuf, &sh.send_cap, send_tot > 3 * nl ? send_tot : 3 * nl);
     if (!rc) rc = sh_grow(&sh.recvbuf, &sh.recv_cap, recv_tot + 1);
     if (rc) return rc;
     ShRecvTable tab;
-    size_t soff[SH_MAX_WORLD], so = 0, ro = 0;
+    size_t soff[SH_MAX_WORLD], so = 0, ro = 0, gc = nl + sh.guest_used;
     for (int g = 0; g < G; ++g) {
-        tab.t0[g] = r_lo[g]; tab.base[g] = ro; ro += (r_hi[g] - r_lo[g]) * rows;
+        tab.t0[g] = r_lo[g]; tab.base[g] = ro; tab.cnt[g] = r_hi[g] - r_lo[g]; tab.gcol[g] = gc;
+        ro += (r_hi[g] - r_lo[g]) * rows; gc += r_hi[g] - r_lo[g];
         soff[g] = so; so += (s_hi[g] - s_lo[g]) * rows;
         size_t cnt = s_hi[g] - s_lo[g];
         if (cnt && rows) PF_LAUNCH(ctx, sh_pack_map_kernel, cdiv_u(cnt * rows, 256), 256, 0, d, sh.idx_all, s_lo[g], cnt, me, sh.sendbuf + soff[g]);
@@ -928,8 +985,13 @@ static int fs_post_sharded(pfgpu_fs* h) {
             if (rcn) PF_NCCL(ncclRecv(sh.recvbuf + tab.base[g], rcn, ncclDouble, g, sh.comm, ctx.stream));
         }
         PF_NCCL(ncclGroupEnd());
-        dim3 grid(cdiv_u(nl, 256), cdiv_u(rows, 16));
-        PF_LAUNCH(ctx, sh_clone_map_kernel, grid, 256, 0, d, sh.recvbuf, tab, me);
+        for (int g = 0; g < G; ++g) {
+            size_t cnt = r_hi[g] - r_lo[g];
+            if (g != me && cnt) PF_LAUNCH(ctx, sh_unpack_guest_kernel, cdiv_u(cnt * rows, 256), 256, 0, d, sh.recvbuf, tab, g);
+        }
+        sh.guest_used += recv_cnt; sh.imported += recv_cnt;
+        dim3 grid(cdiv_u(nl, 256), cdiv_u(d.m, FS_COMPOSE_ROWS));
+        PF_LAUNCH(ctx, sh_compose_anc_kernel, grid, 256, 0, d, tab, me);
     }
     PF_LAUNCH(ctx, sh_flip_kernel, 1, 256, 0, d);
     return 0;
@@ -1150,6 +1212,7 @@ extern "C" int pfgpu_fs_stats(pfgpu_fs* h, pfgpu_stats* s) {
     PF_CUDA(cudaMemcpy(&cnt, h->d.counters, sizeof(unsigned int), cudaMemcpyDeviceToHost));
     s->kernel_launches = h->ctx.launches; s->steps = h->steps; s->resamples = cnt;
     s->main_kernel_ms_sum = h->timer.ms_sum; s->main_kernel_count = h->timer.count;
+    s->compactions = h->sh.compactions; s->imported_particles = h->sh.imported;
     int rcx = read_xs_flags(h->ctx, h->xs, s);
     if (rcx) return rcx;
     return read_fx_flags(h->fx, h->fused_post, s);

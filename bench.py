@@ -304,7 +304,10 @@ def run_ours(args, rank, world, local_rank):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": dict(workload_config(sc, world), resamples_in_timed_steps=int(resamples),
                                **({"imported_particles_rank0": int(st1.imported_particles - st0.imported_particles),
-                                   "guest_compactions_rank0": int(st1.compactions - st0.compactions)} if world > 1 else {})),
+                                   "guest_compactions_rank0": int(st1.compactions - st0.compactions),
+                                   "exchange": {1: "NCCL collectives + host-planned send/recv", 2: "peer memory (NVLink stores/atomics/loads "
+                                                "inside the kernels; no NCCL call, no host sync per step)"}.get(g.shard_mode(), "?")}
+                                  if world > 1 else {})),
                 "value_steady_state_no_flush": n_global * K / t_noflush,
                 "e2e": {"value": n_global * K / t_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d / K,
                         "d2h_bytes_per_step": d2h / K},

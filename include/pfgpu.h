@@ -153,6 +153,9 @@ int  pfgpu_pf_stats(pfgpu_pf*, pfgpu_stats*);
 int  pfgpu_fs_stats(pfgpu_fs*, pfgpu_stats*);
 /* debug (PFGPU_POST_TRACE=1): accumulated per-phase times [ns] of the fused post-step kernel; out32[31] = launches */
 int  pfgpu_fs_post_trace(pfgpu_fs*, unsigned long long* out32);
+/* how the coupled part of the step runs: 0 = one GPU, 1 = sharded over NCCL collectives, 2 = sharded over peer memory
+   (NVLink loads/stores/atomics inside the kernels; no NCCL call and no host sync per step) */
+int  pfgpu_fs_shard_mode(pfgpu_fs*, int* mode);
 int  pfgpu_pf_time_main_kernel(pfgpu_pf*, int on);
 int  pfgpu_fs_time_main_kernel(pfgpu_fs*, int on);
 /* CUDA events on the handle's own stream (bench.py times steps with these): mark(slot 0..16383) records an

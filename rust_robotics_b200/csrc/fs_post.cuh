@@ -35,18 +35,19 @@ struct FxWork {
                               // [3] cumulative overflow tiles
 };
 
-struct FxShared {
+template <int MAXT>
+struct FxSharedT {
     double sm_d[XS_NT / 32];
     int sm_i[XS_NT / 32];
     XsSeg sm_s[XS_NT / 32];
     XsSeg carry_seg;
     int carry_nd;
     int ndl;                           // number of tiles holding dirty values
-    unsigned short dl_tile[FX_MAX_TILES];   // ... their ids, in order
-    int dl_off[FX_MAX_TILES];          // ... and the ordinal of their first dirty value
-    xs_t tin[FX_MAX_TILES];
-    int tdoff[FX_MAX_TILES];
-    int tnd[FX_MAX_TILES];
+    unsigned short dl_tile[MAXT];      // ... their ids, in order
+    int dl_off[MAXT];                  // ... and the ordinal of their first dirty value
+    xs_t tin[MAXT];
+    int tdoff[MAXT];
+    int tnd[MAXT];
     XsEntry ent[FX_CHUNK];
     double before[FX_CHUNK];           // exact running sum in front of / right after each staged dirty value
     double after[FX_CHUNK];
@@ -57,6 +58,18 @@ struct FxShared {
     int serial;
     double r0;
 };
+typedef FxSharedT<FX_MAX_TILES> FxShared;
+
+// Where a tile's aggregates are published.  One GPU: plain stores into the local slot arrays, tile id = blockIdx.x.
+// (fs_mg.cuh has the multi-GPU publisher: the same stores repeated into every peer's window over NVLink.)
+struct FxPubLocal {
+    __device__ __forceinline__ unsigned me() const { return blockIdx.x; }
+    __device__ __forceinline__ void tsum(const FxSlot& s, int, unsigned b, double v) const { s.tsum[b] = v; }
+    __device__ __forceinline__ void tail(const FxSlot& s, int, unsigned b, xs_t t, int nd) const { s.ttail[b] = t; s.tnd[b] = nd; }
+    __device__ __forceinline__ void ent(const FxSlot& s, int, size_t k, const XsEntry& e) const { s.ent[k] = e; }
+    __device__ __forceinline__ void bad(int* flags) const { flags[0] = 1; }
+    __device__ __forceinline__ int is_bad(const int* flags) const { return flags[0]; }
+};
 
 struct FxTile {            // what a thread keeps between classify and emit
     double toff, excl;
@@ -66,18 +79,20 @@ struct FxTile {            // what a thread keeps between classify and emit
 };
 
 // ---- phase 1: approximate tile sum -> global -------------------------------------------------------
-__device__ __forceinline__ void fx_tile_sum(const double (&v)[FX_ITEMS], const FxSlot& s, FxShared& sh, int* flags) {
+template <class P, class SH>
+__device__ __forceinline__ void fx_tile_sum(const double (&v)[FX_ITEMS], const FxSlot& s, int si, SH& sh, int* flags, const P& pub) {
     double t = 0.0; bool bad = false;
 #pragma unroll
     for (int k = 0; k < FX_ITEMS; ++k) { t += v[k]; if (!(v[k] >= 0.0) || !(v[k] <= 1.7976931348623157e308)) bad = true; }
-    if (bad) flags[0] = 1;
+    if (bad) pub.bad(flags);
     double tot = block_sum<XS_NT>(t, sh.sm_d);
-    if (threadIdx.x == 0) s.tsum[blockIdx.x] = tot;
+    if (threadIdx.x == 0) pub.tsum(s, si, pub.me(), tot);
 }
 
 // ---- phase 2 (after a grid barrier): classify the tile, publish its aggregate and dirty entries ----------------
-__device__ __forceinline__ FxTile fx_classify(const double (&v)[FX_ITEMS], const FxSlot& s, FxShared& sh, double rel) {
-    const unsigned b = blockIdx.x;
+template <class P, class SH>
+__device__ __forceinline__ FxTile fx_classify(const double (&v)[FX_ITEMS], const FxSlot& s, int si, SH& sh, double rel, const P& pub) {
+    const unsigned b = pub.me();
     FxTile c;
     double part = 0.0;
     for (unsigned t = threadIdx.x; t < b; t += XS_NT) part += s.tsum[t];
@@ -111,7 +126,7 @@ __device__ __forceinline__ FxTile fx_classify(const double (&v)[FX_ITEMS], const
             if (xs_classify(v[k], a_prev, a_cur, rel, &t)) run = xs_compose(run, t);
             else {
                 XsEntry e; e.inc = run.inc; e.lvl = run.lvl; e.pad = 0; e.v = v[k];
-                s.ent[(size_t)b * XS_MAXD + slot] = e;
+                pub.ent(s, si, (size_t)b * XS_MAXD + slot, e);
                 slot++;
                 run = xs_identity();
             }
@@ -121,12 +136,10 @@ __device__ __forceinline__ FxTile fx_classify(const double (&v)[FX_ITEMS], const
     if (threadIdx.x == 0) {
         if (overflow) {
             XsEntry e; e.inc = 0; e.lvl = XS_EMPTY; e.pad = 1; e.v = 0.0;
-            s.ent[(size_t)b * XS_MAXD] = e;
-            s.ttail[b] = xs_identity();
-            s.tnd[b] = -1;
+            pub.ent(s, si, (size_t)b * XS_MAXD, e);
+            pub.tail(s, si, b, xs_identity(), -1);
         } else {
-            s.ttail[b] = stot.t;
-            s.tnd[b] = ndtot;
+            pub.tail(s, si, b, stot.t, ndtot);
         }
     }
     return c;
@@ -135,17 +148,17 @@ __device__ __forceinline__ FxTile fx_classify(const double (&v)[FX_ITEMS], const
 // ---- phase 3 (after a grid barrier): every CTA evaluates the whole chain; results land in shared memory ---------
 // sh.total = exact total; sh.tin[blockIdx.x], sh.tdoff[blockIdx.x], sh.after_win[] serve fx_emit for this tile.
 #define FXC_STAMP(k) do { if (dbg && me == 0 && tid == 0) { unsigned long long t__; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t__)); dbg[k] += t__ - tp; tp = t__; } } while (0)
-template <class F>
-__device__ __noinline__ void fx_chain(const FxSlot& s, unsigned nt, F f, size_t n, FxShared& sh, int* flags, unsigned long long* dbg = nullptr) {
+template <class F, class P, class SH>
+__device__ __noinline__ void fx_chain(const FxSlot& s, unsigned nt, F f, size_t n, SH& sh, int* flags, const P& pub, unsigned long long* dbg = nullptr) {
     const int tid = threadIdx.x;
-    const unsigned me = blockIdx.x;
+    const unsigned me = pub.me();
     unsigned long long tp = 0;
     if (dbg) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tp));
     __syncthreads();
     // ---- tile-level segmented scan: all threads fetch the aggregates (coalesced), ONE warp scans them from shared memory
     // (nt <= FX_MAX_TILES = 16 tiles per lane), no block-wide scan primitives on this path
     for (unsigned b = tid; b < nt; b += XS_NT) { sh.tnd[b] = s.tnd[b]; sh.tin[b] = s.ttail[b]; }
-    if (tid == 0) { sh.s_run = 0.0; sh.ok = 1; sh.serial = flags[0]; }
+    if (tid == 0) { sh.s_run = 0.0; sh.ok = 1; sh.serial = pub.is_bad(flags); }
     __syncthreads();
     if (tid < 32) {
         const unsigned per = (nt + 31) / 32;
@@ -271,10 +284,11 @@ __device__ __noinline__ void fx_chain(const FxSlot& s, unsigned nt, F f, size_t 
 }
 
 // ---- phase 4: exact inclusive prefix of this thread's 8 values ------------------------------------------------------
-template <class F>
-__device__ __forceinline__ void fx_emit(const double (&v)[FX_ITEMS], const FxTile& c, FxShared& sh, F f, size_t n, double rel,
-                                        double (&out)[FX_ITEMS], int* flags, double* gscratch /* [n], this tile's slice is ours */) {
-    const unsigned me = blockIdx.x;
+template <class F, class P, class SH>
+__device__ __forceinline__ void fx_emit(const double (&v)[FX_ITEMS], const FxTile& c, SH& sh, F f, size_t n, double rel,
+                                        double (&out)[FX_ITEMS], int* flags, double* gscratch /* [n], this tile's slice is ours */,
+                                        const P& pub) {
+    const unsigned me = pub.me();
     const size_t first = (size_t)me * FX_TILE + (size_t)threadIdx.x * FX_ITEMS;
     if (sh.serial || sh.tnd[me] < 0) {          // serial walk / overflow tile: thread 0 walks the tile from its exact base
         if (threadIdx.x == 0) {
@@ -321,6 +335,7 @@ __global__ void __launch_bounds__(XS_NT, 2) fs_post_kernel(FsDev d, FxWork fw, d
                                                            const __grid_constant__ FsObsParam po, int k_obs) {
     cg::grid_group grid = cg::this_grid();
     __shared__ FxShared sh;
+    const FxPubLocal pub;
     const unsigned b = blockIdx.x;
     const int tid = threadIdx.x;
     const size_t first = (size_t)b * FX_TILE + (size_t)tid * FX_ITEMS;
@@ -338,15 +353,15 @@ __global__ void __launch_bounds__(XS_NT, 2) fs_post_kernel(FsDev d, FxWork fw, d
     grid.sync();                                               // flags[0] reset is visible before anyone raises it
     FX_STAMP(0);
     // ---------------- S = sum w_raw; w = w_raw / S (fs1.rs:196-203) ----------------
-    fx_tile_sum(v, fw.slot[0], sh, fw.flags);
+    fx_tile_sum(v, fw.slot[0], 0, sh, fw.flags, pub);
     FX_STAMP(1);
     grid.sync();
     FX_STAMP(2);
-    fx_classify(v, fw.slot[0], sh, rel);
+    fx_classify(v, fw.slot[0], 0, sh, rel, pub);
     FX_STAMP(3);
     grid.sync();
     FX_STAMP(4);
-    fx_chain(fw.slot[0], nt, XsValArray{d.w_raw}, n, sh, fw.flags, fw.dbg ? fw.dbg + 16 : nullptr);
+    fx_chain(fw.slot[0], nt, XsValArray{d.w_raw}, n, sh, fw.flags, pub, fw.dbg ? fw.dbg + 16 : nullptr);
     FX_STAMP(5);
     const double S = sh.total;
     double q[FX_ITEMS];
@@ -361,8 +376,8 @@ __global__ void __launch_bounds__(XS_NT, 2) fs_post_kernel(FsDev d, FxWork fw, d
     // Only the DECISION feeds back into the state, so Q is first summed in tree order (one barrier).  The sequential sum
     // the reference computes differs from it by at most (n+64)*2^-52 relatively; only when neff lands that close to NTH is
     // the exact sequential sum evaluated (same decision as the reference in every case).
-    fx_tile_sum(q, fw.slot[1], sh, fw.flags);                  // per-tile partial sums of w^2
-    fx_tile_sum(v, fw.slot[2], sh, fw.flags);                  // per-tile sums of w (needed only if the gate opens)
+    fx_tile_sum(q, fw.slot[1], 1, sh, fw.flags, pub);                  // per-tile partial sums of w^2
+    fx_tile_sum(v, fw.slot[2], 2, sh, fw.flags, pub);                  // per-tile sums of w (needed only if the gate opens)
     FX_STAMP(6);
     grid.sync();
     FX_STAMP(7);
@@ -378,9 +393,9 @@ __global__ void __launch_bounds__(XS_NT, 2) fs_post_kernel(FsDev d, FxWork fw, d
     const bool border = !(fabs(neff - nth) > slack * fmax(fabs(nth), fabs(neff))) || (fw.flags[0] != 0);
     FX_STAMP(8);
     if (border) {                                              // rare; uniform over the grid
-        fx_classify(q, fw.slot[1], sh, rel);
+        fx_classify(q, fw.slot[1], 1, sh, rel, pub);
         grid.sync();
-        fx_chain(fw.slot[1], nt, FsValWSq{d.w}, n, sh, fw.flags);
+        fx_chain(fw.slot[1], nt, FsValWSq{d.w}, n, sh, fw.flags, pub);
         Q = sh.total;
         neff = Q > 0.0 ? 1.0 / Q : 0.0;                        // compute_neff fs1.rs:186-193
     }
@@ -392,9 +407,9 @@ __global__ void __launch_bounds__(XS_NT, 2) fs_post_kernel(FsDev d, FxWork fw, d
     }
     if (!gate) return;                                         // the whole grid takes the same branch
     // ---------------- resample: S2 = sum w (fs1.rs:207) ----------------
-    fx_classify(v, fw.slot[2], sh, rel);
+    fx_classify(v, fw.slot[2], 2, sh, rel, pub);
     grid.sync();
-    fx_chain(fw.slot[2], nt, XsValArray{d.w}, n, sh, fw.flags);
+    fx_chain(fw.slot[2], nt, XsValArray{d.w}, n, sh, fw.flags, pub);
     const double S2 = sh.total;
     if (b == 0 && tid == 0) d.scal[2] = S2;
     FX_STAMP(10);
@@ -413,21 +428,21 @@ __global__ void __launch_bounds__(XS_NT, 2) fs_post_kernel(FsDev d, FxWork fw, d
         if (S2 > 0.0) v[k] = v[k] / S2;                        // normalize_weights inside resample() fs1.rs:207
         cv[k] = i < n ? (i == 0 ? r0 : inv) : 0.0;
     }
-    fx_tile_sum(v, fw.slot[3], sh, fw.flags);
-    fx_tile_sum(cv, fw.slot[4], sh, fw.flags);
+    fx_tile_sum(v, fw.slot[3], 3, sh, fw.flags, pub);
+    fx_tile_sum(cv, fw.slot[4], 4, sh, fw.flags, pub);
     FX_STAMP(11);
     grid.sync();
     FX_STAMP(12);
-    FxTile tc = fx_classify(v, fw.slot[3], sh, rel);
-    FxTile tr = fx_classify(cv, fw.slot[4], sh, rel);
+    FxTile tc = fx_classify(v, fw.slot[3], 3, sh, rel, pub);
+    FxTile tr = fx_classify(cv, fw.slot[4], 4, sh, rel, pub);
     FX_STAMP(13);
     grid.sync();
     FX_STAMP(14);
     double c[FX_ITEMS], r[FX_ITEMS];
-    fx_chain(fw.slot[3], nt, FxValW2{d.w, S2}, n, sh, fw.flags);
-    fx_emit(v, tc, sh, FxValW2{d.w, S2}, n, rel, c, fw.flags, d.cum);
-    fx_chain(fw.slot[4], nt, FxValComb{r0, inv}, n, sh, fw.flags);
-    fx_emit(cv, tr, sh, FxValComb{r0, inv}, n, rel, r, fw.flags, d.rcomb);
+    fx_chain(fw.slot[3], nt, FxValW2{d.w, S2}, n, sh, fw.flags, pub);
+    fx_emit(v, tc, sh, FxValW2{d.w, S2}, n, rel, c, fw.flags, d.cum, pub);
+    fx_chain(fw.slot[4], nt, FxValComb{r0, inv}, n, sh, fw.flags, pub);
+    fx_emit(cv, tr, sh, FxValComb{r0, inv}, n, rel, r, fw.flags, d.rcomb, pub);
     FX_STAMP(15);
 #pragma unroll
     for (int k = 0; k < FX_ITEMS; ++k) { size_t i = first + k; if (i < n) { d.cum[i] = c[k]; d.rcomb[i] = r[k]; } }

@@ -6,6 +6,7 @@
 #include "fs_kernels.cuh"
 #include "fs_post.cuh"
 #include "fs_sharded.cuh"
+#include "fs_mg.cuh"
 #include <cstdlib>
 #include <new>
 #include <vector>
@@ -619,7 +620,14 @@ struct pfgpu_fs {
     bool step_v2 = true;           // observation-parallel step kernel (PFGPU_STEP_V2=0 selects the one-thread-per-particle form)
     int ekf_variant = 3;           // register budget of fs_ekf_kernel: 0 = 64 regs, 1 = 72 regs (2 CTAs/SM), 2 = up to 128 regs (1 CTA/SM)
     FsShard sh;                    // multi-GPU state (world == 1: unused)
+    // peer-memory form of the sharded step (fs_mg.cuh): one arena per rank, mapped by every peer
+    char* arena = nullptr; size_t arena_bytes = 0;
+    void* peer_ptr[SH_MAX_WORLD] = {};
+    char** d_peer = nullptr;
+    MgDev mg = {};
+    bool mg_on = false;
 };
+static int fs_mg_error(int code);
 
 extern "C" void pfgpu_fs_default_config(pfgpu_fs_config* c) {            // fs1.rs:13-23
     c->dt = 0.1; c->max_range = 20.0; c->nth = 100.0 / 1.5; c->q00 = 0.3; c->q11 = 0.0305; c->r00 = 0.5; c->r11 = 0.0305;
@@ -639,24 +647,65 @@ static int fs_create_impl(const pfgpu_fs_config* cfg, size_t n, size_t n_global,
     FsDev& d = h->d;
     d.n = n; d.n_global = n_global; d.offset = offset; d.m = m; d.eager = 0;
     h->sh.n_guest = world > 1 ? std::max<size_t>(2048, n / 8) : 0;
+    if (world > 1) { const char* eg = getenv("PFGPU_GUEST_COLS"); if (eg && atoll(eg) > 0) h->sh.n_guest = (size_t)atoll(eg); }
     d.ld = n + h->sh.n_guest;
     h->lm_bytes = (m ? m : 1) * 6 * d.ld * sizeof(double);
     auto fail = [&](int code) { pfgpu_fs_destroy(h); return code; };
 #define FS_TRY(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { snprintf(g_pfgpu_err, sizeof(g_pfgpu_err), "%s -> %s", #x, cudaGetErrorString(e__)); return fail(PFGPU_ERR_CUDA); } } while (0)
+    // Sharded mode keeps everything a peer may touch in ONE allocation with the same layout on every rank, so that a
+    // single IPC mapping per peer gives access to all of it (fs_mg.cuh).
+    bool want_mg = false;
+    {
+        const char* env = getenv("PFGPU_SHARD_P2P");
+        want_mg = world > 1 && !(env && env[0] == '0') && n % FX_TILE == 0 && (size_t)world * (n / FX_TILE) <= MG_MAX_TILES;
+    }
+    if (want_mg) {
+        MgDev& mg = h->mg;
+        const size_t mm = m ? m : 1;
+        const unsigned ntl = (unsigned)(n / FX_TILE), NT = ntl * (unsigned)world;
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+        mg.G = world; mg.rank = rank; mg.ntl = ntl; mg.NT = NT;
+        mg.o_ctr = take(512); mg.o_bad = mg.o_ctr + 384;
+        for (int sl = 0; sl < FX_SLOTS; ++sl) {
+            mg.o_tsum[sl] = take(NT * sizeof(double)); mg.o_ttail[sl] = take(NT * sizeof(xs_t));
+            mg.o_tnd[sl] = take(NT * sizeof(int)); mg.o_ent[sl] = take((size_t)NT * XS_MAXD * sizeof(XsEntry));
+        }
+        mg.o_cum_all = take(n_global * sizeof(double));
+        mg.o_w_raw = take(n * sizeof(double)); mg.o_w = take(n * sizeof(double));
+        for (int b = 0; b < 2; ++b) { mg.o_px[b] = take(n * sizeof(double)); mg.o_py[b] = take(n * sizeof(double)); mg.o_pyaw[b] = take(n * sizeof(double)); }
+        mg.o_lmstate = take(mm * sizeof(int));
+        for (int b = 0; b < 2; ++b) mg.o_anc[b] = take(mm * n * sizeof(uint32_t));
+        for (int b = 0; b < 2; ++b) mg.o_lm[b] = take(h->lm_bytes);
+        h->arena_bytes = off;
+        FS_TRY(cudaMalloc(&h->arena, off));
+        FS_TRY(cudaMemset(h->arena, 0, mg.o_cum_all));
+        char* A = h->arena;
+        for (int b = 0; b < 2; ++b) {
+            d.px[b] = (double*)(A + mg.o_px[b]); d.py[b] = (double*)(A + mg.o_py[b]); d.pyaw[b] = (double*)(A + mg.o_pyaw[b]);
+            d.lm[b] = (double*)(A + mg.o_lm[b]); d.anc[b] = (uint32_t*)(A + mg.o_anc[b]);
+        }
+        d.w = (double*)(A + mg.o_w); d.w_raw = (double*)(A + mg.o_w_raw); d.lmstate = (int*)(A + mg.o_lmstate);
+        for (int sl = 0; sl < FX_SLOTS; ++sl) {
+            h->fx.slot[sl].tsum = (double*)(A + mg.o_tsum[sl]); h->fx.slot[sl].ttail = (xs_t*)(A + mg.o_ttail[sl]);
+            h->fx.slot[sl].tnd = (int*)(A + mg.o_tnd[sl]); h->fx.slot[sl].ent = (XsEntry*)(A + mg.o_ent[sl]);
+        }
+    } else {
     for (int b = 0; b < 2; ++b) {
         FS_TRY(cudaMalloc(&d.px[b], n * sizeof(double))); FS_TRY(cudaMalloc(&d.py[b], n * sizeof(double)));
         FS_TRY(cudaMalloc(&d.pyaw[b], n * sizeof(double))); FS_TRY(cudaMalloc(&d.lm[b], h->lm_bytes));
     }
-    FS_TRY(cudaMalloc(&d.cur, sizeof(int))); FS_TRY(cudaMemset(d.cur, 0, sizeof(int)));
     FS_TRY(cudaMalloc(&d.w, n * sizeof(double))); FS_TRY(cudaMalloc(&d.w_raw, n * sizeof(double)));
+    }
+    FS_TRY(cudaMalloc(&d.cur, sizeof(int))); FS_TRY(cudaMemset(d.cur, 0, sizeof(int)));
     FS_TRY(cudaMalloc(&d.cum, n * sizeof(double))); FS_TRY(cudaMalloc(&d.rcomb, n * sizeof(double)));
     FS_TRY(cudaMalloc(&d.idx, n * sizeof(uint32_t)));
     FS_TRY(cudaMalloc(&d.scal, 16 * sizeof(double))); FS_TRY(cudaMemset(d.scal, 0, 16 * sizeof(double)));
     FS_TRY(cudaMalloc(&d.gate, sizeof(int))); FS_TRY(cudaMemset(d.gate, 0, sizeof(int)));
     d.anc16 = (n <= 65536 && world == 1) ? 1 : 0;
-    for (int b = 0; b < 2; ++b) FS_TRY(cudaMalloc(&d.anc[b], (m ? m : 1) * n * sizeof(uint32_t)));
+    if (!h->arena) for (int b = 0; b < 2; ++b) FS_TRY(cudaMalloc(&d.anc[b], (m ? m : 1) * n * sizeof(uint32_t)));
     FS_TRY(cudaMalloc(&d.anc_cur, sizeof(int))); FS_TRY(cudaMemset(d.anc_cur, 0, sizeof(int)));
-    FS_TRY(cudaMalloc(&d.lmstate, (m ? m : 1) * sizeof(int)));
+    if (!h->arena) FS_TRY(cudaMalloc(&d.lmstate, (m ? m : 1) * sizeof(int)));
     FS_TRY(cudaMalloc(&d.counters, 4 * sizeof(unsigned int))); FS_TRY(cudaMemset(d.counters, 0, 4 * sizeof(unsigned int)));
     h->obs_cap = FS_MAX_OBS;
     FS_TRY(cudaMalloc(&d.obs, h->obs_cap * sizeof(FsObsDev)));
@@ -730,6 +779,59 @@ static int fs_create_impl(const pfgpu_fs_config* cfg, size_t n, size_t n_global,
             PF_NCCL(ncclGroupEnd());
             SH_TRY(cudaStreamSynchronize(h->ctx.stream));
         }
+        if (h->arena) {
+            // map every peer's arena; all ranks must agree on the outcome, so the verdict is gathered too
+            int ok = 1;
+            cudaIpcMemHandle_t mine, all[SH_MAX_WORLD];
+            char* d_hand = nullptr;
+            SH_TRY(cudaMalloc(&d_hand, (size_t)(world + 1) * sizeof(cudaIpcMemHandle_t)));
+            if (cudaIpcGetMemHandle(&mine, h->arena) != cudaSuccess) { ok = 0; memset(&mine, 0, sizeof(mine)); cudaGetLastError(); }
+            SH_TRY(cudaMemcpy(d_hand + (size_t)world * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice));
+            PF_NCCL(ncclAllGather(d_hand + (size_t)world * sizeof(mine), d_hand, sizeof(mine), ncclChar, sh.comm, h->ctx.stream));
+            SH_TRY(cudaStreamSynchronize(h->ctx.stream));
+            SH_TRY(cudaMemcpy(all, d_hand, (size_t)world * sizeof(mine), cudaMemcpyDeviceToHost));
+            for (int g = 0; g < world && ok; ++g) {
+                if (g == rank) { h->peer_ptr[g] = h->arena; continue; }
+                if (cudaIpcOpenMemHandle(&h->peer_ptr[g], all[g], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    ok = 0; h->peer_ptr[g] = nullptr; cudaGetLastError();
+                }
+            }
+            int nb = 0, coop = 0;
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+            if (cudaFuncSetAttribute(fs_post_mg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MgShared)) != cudaSuccess ||
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fs_post_mg_kernel, XS_NT, sizeof(MgShared)) != cudaSuccess ||
+                (size_t)nb * (size_t)h->ctx.num_sms < h->mg.ntl || !coop) { ok = 0; cudaGetLastError(); }
+            int* d_ok = reinterpret_cast<int*>(d_hand);
+            SH_TRY(cudaMemcpy(d_ok + world, &ok, sizeof(int), cudaMemcpyHostToDevice));
+            PF_NCCL(ncclAllGather(d_ok + world, d_ok, 1, ncclInt, sh.comm, h->ctx.stream));
+            SH_TRY(cudaStreamSynchronize(h->ctx.stream));
+            int oks[SH_MAX_WORLD];
+            SH_TRY(cudaMemcpy(oks, d_ok, (size_t)world * sizeof(int), cudaMemcpyDeviceToHost));
+            cudaFree(d_hand);
+            for (int g = 0; g < world; ++g) ok = ok && oks[g];
+            if (ok) {
+                MgDev& mg = h->mg;
+                SH_TRY(cudaMalloc(&h->d_peer, world * sizeof(char*)));
+                SH_TRY(cudaMemcpy(h->d_peer, h->peer_ptr, world * sizeof(char*), cudaMemcpyHostToDevice));
+                mg.peer = h->d_peer;
+                SH_TRY(cudaMalloc(&mg.tgt, 4 * sizeof(unsigned))); SH_TRY(cudaMemset(mg.tgt, 0, 4 * sizeof(unsigned)));
+                SH_TRY(cudaMalloc(&mg.err, sizeof(int))); SH_TRY(cudaMemset(mg.err, 0, sizeof(int)));
+                SH_TRY(cudaMalloc(&mg.gcol, n * sizeof(unsigned)));
+                SH_TRY(cudaMalloc(&mg.plan, 8 * sizeof(unsigned long long))); SH_TRY(cudaMemset(mg.plan, 0, 8 * sizeof(unsigned long long)));
+                mg.n_guest = sh.n_guest;
+                SH_TRY(cudaMalloc(&h->fx.flags, 8 * sizeof(int))); SH_TRY(cudaMemset(h->fx.flags, 0, 8 * sizeof(int)));
+                h->fx.dbg = nullptr;
+                if (getenv("PFGPU_POST_TRACE")) {
+                    SH_TRY(cudaMalloc(&h->fx.dbg, 32 * sizeof(unsigned long long)));
+                    SH_TRY(cudaMemset(h->fx.dbg, 0, 32 * sizeof(unsigned long long)));
+                }
+                h->mg_on = true;
+                // nobody may start pushing into an arena before its owner has zeroed it (cudaMemset above, synchronous) and
+                // everybody has mapped it: one more collective as the fence
+                PF_NCCL(ncclAllGather(sh.t_loc, sh.t_all, 1, ncclDouble, sh.comm, h->ctx.stream));
+                SH_TRY(cudaStreamSynchronize(h->ctx.stream));
+            }
+        }
         {   // exchange buffers sized for the worst admissible resample up front: no cudaMalloc on the step path
             size_t cap = std::max<size_t>(3 * n, sh.n_guest * 6 * (m ? m : 1)) + 1024;
             SH_TRY(cudaMalloc(&sh.sendbuf, cap * sizeof(double))); sh.send_cap = cap;
@@ -760,6 +862,14 @@ extern "C" void pfgpu_fs_destroy(pfgpu_fs* h) {
     cudaSetDevice(h->ctx.device);
     if (h->ctx.stream) cudaStreamSynchronize(h->ctx.stream);
     FsDev& d = h->d;
+    if (h->arena) {      // these live inside the arena
+        for (int b = 0; b < 2; ++b) { d.px[b] = d.py[b] = d.pyaw[b] = d.lm[b] = nullptr; d.anc[b] = nullptr; }
+        d.w = d.w_raw = nullptr; d.lmstate = nullptr;
+        for (int sl = 0; sl < FX_SLOTS; ++sl) { h->fx.slot[sl].tsum = nullptr; h->fx.slot[sl].ttail = nullptr; h->fx.slot[sl].tnd = nullptr; h->fx.slot[sl].ent = nullptr; }
+        for (int g = 0; g < h->world; ++g) if (g != h->rank && h->peer_ptr[g]) cudaIpcCloseMemHandle(h->peer_ptr[g]);
+        cudaFree(h->d_peer); cudaFree(h->mg.tgt); cudaFree(h->mg.err); cudaFree(h->mg.gcol); cudaFree(h->mg.plan);
+        cudaFree(h->arena);
+    }
     for (int b = 0; b < 2; ++b) { cudaFree(d.px[b]); cudaFree(d.py[b]); cudaFree(d.pyaw[b]); cudaFree(d.lm[b]); }
     cudaFree(d.cur); cudaFree(d.w); cudaFree(d.w_raw); cudaFree(d.cum); cudaFree(d.rcomb); cudaFree(d.idx); cudaFree(d.scal);
     cudaFree(d.gate); cudaFree(d.obs); cudaFree(d.best_w); cudaFree(d.best_i); cudaFree(d.counters);
@@ -786,6 +896,11 @@ extern "C" int pfgpu_fs_sync(pfgpu_fs* h) {
     if (!h) return PFGPU_ERR_INVALID;
     PF_CUDA(cudaSetDevice(h->ctx.device));
     PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+    if (h->mg_on) {        // errors of the device-side sharded step are sticky and surface at the next sync
+        int e = 0;
+        PF_CUDA(cudaMemcpy(&e, h->mg.err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (e) return fs_mg_error(e);
+    }
     return 0;
 }
 extern "C" int pfgpu_fs_count(pfgpu_fs* h, size_t* nl, size_t* ng, size_t* m) {
@@ -875,6 +990,11 @@ static int sh_grow(double** buf, size_t* cap, size_t need) {
     *cap = need + need / 4 + 1024;
     PF_CUDA(cudaMalloc(buf, *cap * sizeof(double)));
     return 0;
+}
+static int fs_mg_error(int code) {
+    if (code == 3) { snprintf(g_pfgpu_err, sizeof(g_pfgpu_err), "sharded resample: more imported particles than guest columns (shard weights too unbalanced)"); return PFGPU_ERR_UNSUPPORTED; }
+    snprintf(g_pfgpu_err, sizeof(g_pfgpu_err), "sharded step: a peer GPU never arrived at a barrier (code %d)", code);
+    return PFGPU_ERR_CUDA;
 }
 static int fs_post_sharded(pfgpu_fs* h) {
     FsDev& d = h->d; FsShard& sh = h->sh; Ctx& ctx = h->ctx;
@@ -1045,7 +1165,7 @@ extern "C" int pfgpu_fs_step(pfgpu_fs* h, const double u[2], const pfgpu_fs_obs*
                     else if (var == 4) PF_LAUNCH(h->ctx, (fs_ekf_kernel<true, 448, 4>), cdiv_u(d.n, 32), (unsigned)(32 * kk), smem, d, po, h->cfg.r00, h->cfg.r11, (int)kk);
                     else               PF_LAUNCH(h->ctx, (fs_ekf_kernel<true, 1024, 1>), cdiv_u(d.n, 32), (unsigned)(32 * kk), smem, d, po, h->cfg.r00, h->cfg.r11, (int)kk);
                 }
-                if (h->fused_post && seg + 2 == cuts.size() && kk <= 256) {   // last piece: the fused post kernel does the bookkeeping
+                if ((h->fused_post || h->mg_on) && seg + 2 == cuts.size() && kk <= 256) {   // last piece: the fused post kernel does the bookkeeping
                     last_po = po; last_k = (int)kk;
                     continue;
                 }
@@ -1065,6 +1185,36 @@ extern "C" int pfgpu_fs_step(pfgpu_fs* h, const double u[2], const pfgpu_fs_obs*
     }
     if (h->timer.on) { PF_CUDA(cudaEventRecord(e1, h->ctx.stream)); h->timer.pending.push_back({e0, e1}); }
     h->n_step++;
+    if (h->mg_on) {
+        // peer-memory form (fs_mg.cuh): everything stays on the device, no NCCL call and no host sync on this path
+        double nth = h->cfg.nth; uint64_t seed = h->seed; double rel = xs_margin(d.n_global);
+        void* args[] = { (void*)&d, (void*)&h->fx, (void*)&h->mg, (void*)&nth, (void*)&seed, (void*)&rel, (void*)&last_po, (void*)&last_k };
+        PF_CUDA(cudaLaunchCooperativeKernel((void*)fs_post_mg_kernel, dim3(h->mg.ntl), dim3(XS_NT), args, sizeof(MgShared), h->ctx.stream));
+        h->ctx.launches++;
+        PF_LAUNCH(h->ctx, fs_mg_search_pose_kernel, cdiv_u(d.n, 256), 256, 0, d, h->mg);
+        PF_LAUNCH(h->ctx, fs_mg_plan_kernel, 1, 1024, 0, d, h->mg);
+        PF_LAUNCH(h->ctx, fs_mg_import_kernel, (unsigned)h->ctx.num_sms * 4, 256, 0, d, h->mg);
+        if (d.m) {
+            dim3 grid(cdiv_u(d.n, 256), cdiv_u(d.m, FS_COMPOSE_ROWS));
+            PF_LAUNCH(h->ctx, fs_mg_compose_anc_kernel, grid, 256, 0, d, h->mg);
+        }
+        PF_LAUNCH(h->ctx, fs_mg_flip_kernel, 1, 256, 0, d, h->mg);
+        if (d.m) {
+            dim3 cgrid((unsigned)h->ctx.num_sms, 8);
+            PF_LAUNCH(h->ctx, fs_mg_compact_kernel, cgrid, 256, 0, d, h->mg);
+            PF_LAUNCH(h->ctx, fs_mg_compact_finish_kernel, 1, 256, 0, d, h->mg);
+        }
+        h->steps++;
+        if (did) {
+            int* hp = reinterpret_cast<int*>(h->h_pin + 32);
+            PF_CUDA(cudaMemcpyAsync(hp, d.gate, sizeof(int), cudaMemcpyDeviceToHost, h->ctx.stream));
+            PF_CUDA(cudaMemcpyAsync(hp + 1, h->mg.err, sizeof(int), cudaMemcpyDeviceToHost, h->ctx.stream));
+            PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+            *did = *hp;
+            if (hp[1]) return fs_mg_error(hp[1]);
+        }
+        return 0;
+    }
     if (h->world > 1) {
         int rcs = fs_post_sharded(h);
         if (rcs) return rcs;
@@ -1213,9 +1363,19 @@ extern "C" int pfgpu_fs_stats(pfgpu_fs* h, pfgpu_stats* s) {
     s->kernel_launches = h->ctx.launches; s->steps = h->steps; s->resamples = cnt;
     s->main_kernel_ms_sum = h->timer.ms_sum; s->main_kernel_count = h->timer.count;
     s->compactions = h->sh.compactions; s->imported_particles = h->sh.imported;
+    if (h->mg_on) {
+        unsigned long long pl[8];
+        PF_CUDA(cudaMemcpy(pl, h->mg.plan, sizeof(pl), cudaMemcpyDeviceToHost));
+        s->imported_particles = pl[4]; s->compactions = pl[5];
+    }
     int rcx = read_xs_flags(h->ctx, h->xs, s);
     if (rcx) return rcx;
-    return read_fx_flags(h->fx, h->fused_post, s);
+    return read_fx_flags(h->fx, h->fused_post || h->mg_on, s);
+}
+extern "C" int pfgpu_fs_shard_mode(pfgpu_fs* h, int* mode) {
+    if (!h || !mode) return PFGPU_ERR_INVALID;
+    *mode = h->world <= 1 ? 0 : (h->mg_on ? 2 : 1);
+    return 0;
 }
 // debug: accumulated phase times of the fused post kernel (PFGPU_POST_TRACE=1); out32[31] = launches
 extern "C" int pfgpu_fs_post_trace(pfgpu_fs* h, unsigned long long* out32) {
@@ -1223,7 +1383,7 @@ extern "C" int pfgpu_fs_post_trace(pfgpu_fs* h, unsigned long long* out32) {
     PF_CUDA(cudaSetDevice(h->ctx.device));
     PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
     for (int k = 0; k < 32; ++k) out32[k] = 0;
-    if (h->fused_post && h->fx.dbg) PF_CUDA(cudaMemcpy(out32, h->fx.dbg, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if ((h->fused_post || h->mg_on) && h->fx.dbg) PF_CUDA(cudaMemcpy(out32, h->fx.dbg, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return 0;
 }
 extern "C" int pfgpu_fs_time_main_kernel(pfgpu_fs* h, int on) {

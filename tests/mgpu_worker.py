@@ -81,7 +81,9 @@ def main():
     assert resamples > 0
     dist.barrier()
     if rank == 0:
-        print(f"MGPU_OK world={world} n={n_global} resamples={resamples}")
+        st = g.stats()
+        print(f"MGPU_OK world={world} n={n_global} resamples={resamples} mode={g.shard_mode()} imported={st.imported_particles} "
+              f"compactions={st.compactions} serial_fallbacks={st.serial_fallbacks}")
     dist.destroy_process_group()
 
 

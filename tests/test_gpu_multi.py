@@ -18,14 +18,23 @@ def n_gpus():
     return c.value
 
 
-@pytest.mark.parametrize("world,n,side,steps", [(2, 4096, 6, 16), (2, 1 << 16, 8, 6)])
-def test_sharded_fastslam_matches_oracle(world, n, side, steps):
+# mode 2: peer-memory step (fs_mg.cuh, the default when the shard size allows it); mode 1: NCCL collectives (fs_sharded.cuh)
+@pytest.mark.parametrize("world,n,side,steps,mode,guests", [(2, 4096, 6, 16, 2, 0), (2, 1 << 16, 8, 6, 2, 0), (2, 4096, 6, 16, 1, 0),
+                                                            (2, 4000, 6, 12, 1, 0), (2, 4096, 6, 40, 2, 192), (2, 4096, 6, 40, 1, 192)])
+def test_sharded_fastslam_matches_oracle(world, n, side, steps, mode, guests):
     if n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
+    env = dict(os.environ)
+    env["PFGPU_SHARD_P2P"] = "1" if mode == 2 else "0"
+    if guests:
+        env["PFGPU_GUEST_COLS"] = str(guests)       # few guest columns: the compaction path has to run
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", "29541", os.path.join(ROOT, "tests", "mgpu_worker.py"), str(n), str(side), str(steps)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+    assert f"mode={mode}" in r.stdout, r.stdout[-2000:]
+    if guests:
+        assert "compactions=0 " not in r.stdout, r.stdout[-2000:]
 
 
 @pytest.mark.parametrize("kind,n,steps", [("pf", 1 << 14, 40), ("mcl", 1 << 15, 8)])

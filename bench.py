@@ -291,6 +291,14 @@ def run_ours(args, rank, world, local_rank):
         nl = max(out[31], 1)
         names = ["init+sync", "S tilesum", "sync", "S classify", "sync", "S chain", "norm+Q/S2 tilesums", "sync", "Q approx", "Q exact (border)",
                  "S2 classify+sync+chain", "cum/comb tilesum", "sync", "cum/comb classify", "sync", "chains+emit"]
+        if world > 1 and g.shard_mode() == 2:
+            nr = max(int(g.stats().resamples), 1)
+            sys.stderr.write("fs_post_mg_kernel (us per launch, CTA 0): load+S tilesum+barrier=%.2f classify+barrier=%.2f chain S+Q/S2 tilesums+barrier=%.2f | "
+                             "per RESAMPLE: S2 classify..cum/comb classify (3 barriers)=%.2f chains+emit+CDF push=%.2f\n" %
+                             (out[0] / nl / 1e3, out[1] / nl / 1e3, out[2] / nl / 1e3, out[3] / nr / 1e3, out[4] / nr / 1e3))
+            sys.stderr.write("resample-step stages (us per resample, kernel start to next kernel start): post=%.1f search+pose=%.1f plan=%.1f "
+                             "(unused)=%.1f import+compose=%.1f flip(wait)=%.1f   [%d resamples traced]\n" %
+                             tuple([out[8 + k] / nr / 1e3 for k in range(6)] + [nr]))
         sys.stderr.write("fs_post_kernel phase times (us per launch, CTA 0): " +
                          ", ".join(f"{nm}={out[k] / nl / 1e3:.2f}" for k, nm in enumerate(names)) + f"  launches={out[31]}\n")
         sys.stderr.write("  S chain detail (us): segscan=%.2f staging=%.2f walk=%.2f verify+final=%.2f  mean dirty=%.1f\n" %

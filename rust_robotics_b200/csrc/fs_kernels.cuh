@@ -383,6 +383,37 @@ __global__ void __launch_bounds__(256) fs_compose_anc_kernel(FsDev d) {
 }
 // Everything a resample does once the exact CDF and comb are known, one pass per particle slot t (gated):
 //   index walk (fs1.rs:224-226) as a lower bound, pose clone + weight (fs1.rs:227-229), and the lazy map clone: compose
+// Same composition, 4 consecutive slots per thread: one 8 / 16-byte store per landmark row instead of four 2 / 4-byte ones
+// (the kernel is bound by load/store instruction issue, not by bytes; the four gathers of a row mostly share a sector because
+// systematic ancestries ascend by about one per slot).  Needs n % 4 == 0.
+template <class AncT> struct AncVec4;
+template <> struct AncVec4<unsigned short> { typedef ushort4 type; };
+template <> struct AncVec4<uint32_t> { typedef uint4 type; };
+template <class AncT>
+__global__ void __launch_bounds__(256) fs_compose_anc_vec_kernel(FsDev d) {
+    if (!*d.gate) return;
+    typedef typename AncVec4<AncT>::type V;
+    const size_t q = (size_t)blockIdx.x * 256 + threadIdx.x;           // quad of slots
+    const size_t t = q * 4;
+    if (t >= d.n) return;
+    const int ac = *d.anc_cur;
+    const AncT* __restrict__ src = reinterpret_cast<const AncT*>(fs_anc(d, ac));
+    AncT* __restrict__ dst = reinterpret_cast<AncT*>(fs_anc(d, ac ^ 1));
+    const uint4 jj = *reinterpret_cast<const uint4*>(d.idx + t);
+    const size_t l0 = (size_t)blockIdx.y * FS_COMPOSE_ROWS;
+#pragma unroll
+    for (int rr = 0; rr < FS_COMPOSE_ROWS; ++rr) {
+        const size_t l = l0 + rr;
+        if (l >= d.m) break;
+        V o;
+        if (d.lmstate[l] & 2) { o.x = (AncT)jj.x; o.y = (AncT)jj.y; o.z = (AncT)jj.z; o.w = (AncT)jj.w; }
+        else {
+            const AncT* __restrict__ row = src + l * d.n;
+            o.x = row[jj.x]; o.y = row[jj.y]; o.z = row[jj.z]; o.w = row[jj.w];
+        }
+        *reinterpret_cast<V*>(dst + l * d.n + t) = o;
+    }
+}
 //   each landmark's ancestry column with this resample's ancestry (see fs_compose_anc_kernel).  A CTA = 256 slots, all m
 //   landmarks (coalesced 2 or 4 B per particle and landmark in each direction).
 template <class AncT>

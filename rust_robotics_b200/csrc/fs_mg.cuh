@@ -32,8 +32,9 @@ struct MgDev {
     unsigned* tgt;              // local [4]: arrivals already consumed on the three counters; [3] = launch epoch
     int* err;                   // local, sticky: 2 = a peer never arrived (timeout), 3 = guest columns exhausted
     unsigned* gcol;             // local [n]: guest column of each importing slot
-    unsigned long long* plan;   // local [8]: 0 head-run length, 1 tail-run start, 2 imports of this resample, 3 guests in use,
-                                //            4 imported (total), 5 compactions, 6 import CTAs finished
+    unsigned long long* plan;   // local [32]: 0 head-run length, 1 tail-run start, 2 imports of this resample, 3 guests in use,
+                                //            4 imported (total), 5 compactions, 6 import CTAs finished; trace (PFGPU_POST_TRACE):
+                                //            13 on/off, 14 last stamp, 16+k accumulated ns up to stage k of a resample step
     size_t n_guest;
 };
 
@@ -51,6 +52,14 @@ __device__ __forceinline__ bool mg_wait(const unsigned* ctr, unsigned target, in
         if (++spins > (1ull << 24)) { *err = 2; return false; }
         __nanosleep(100);
     }
+}
+// trace: time since the previous stamp, accumulated per stage (one thread of the first CTA of each kernel calls it)
+__device__ __forceinline__ void mg_stamp(const MgDev& mg, int k) {
+    if (!mg.plan[13]) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    if (k > 0) mg.plan[16 + k] += t - mg.plan[14];
+    mg.plan[14] = t;
 }
 // one arrival per CTA on every rank's counter `which`
 __device__ __forceinline__ void mg_arrive(const MgDev& mg, int which) {
@@ -118,6 +127,7 @@ __global__ void __launch_bounds__(XS_NT, 2) fs_post_mg_kernel(FsDev d, FxWork fw
 #define MG_FINISH() do { if (bl == 0 && tid == 0) { mg.tgt[0] = target; mg.tgt[3] = epoch + 1u; } } while (0)
 #define MG_BARRIER() do { if (!mg_barrier(mg, target, &s_ok)) { MG_FINISH(); return; } } while (0)
     if (bl == 0 && tid == 0 && fw.dbg) fw.dbg[31] += 1;
+    if (bl == 0 && tid == 0) mg_stamp(mg, 0);
     if (bl == 0 && tid < k_obs) {           // lazy-clone bookkeeping of the EKF launch that just ran
         const int l = po.o[tid].lm_id;
         const int st = d.lmstate[l];
@@ -222,6 +232,7 @@ __global__ void __launch_bounds__(XS_NT, 2) fs_post_mg_kernel(FsDev d, FxWork fw
 __global__ void __launch_bounds__(256) fs_mg_search_pose_kernel(FsDev d, const __grid_constant__ MgDev mg) {
     if (!*d.gate) return;
     __shared__ int s_ok;
+    if (blockIdx.x == 0 && threadIdx.x == 0) mg_stamp(mg, 1);
     if (threadIdx.x == 0)
         s_ok = mg_wait(mg_at<unsigned>(mg, mg.rank, mg.o_ctr) + 32, mg.tgt[1] + (unsigned)mg.G * mg.ntl, mg.err) ? 1 : 0;
     __syncthreads();
@@ -248,22 +259,34 @@ __global__ void __launch_bounds__(256) fs_mg_search_pose_kernel(FsDev d, const _
 // Which of my slots have an ancestor on another rank, and which guest column each of them gets.  The ancestry is
 // monotone, so these slots are a head run [0, nh) (ancestors below my block) and a tail run [t1, n) (above); slots that
 // share an ancestor share a guest column (the first of them copies).
+// number of leading slots whose ancestor index is below `bound` (idx ascends): all 1024 threads, two rounds
+__device__ __forceinline__ unsigned mg_count_below(const uint32_t* __restrict__ idx, size_t n, unsigned long long bound, unsigned* s_acc) {
+    const size_t chunk = (n + 1023) / 1024;
+    const size_t t0 = (size_t)threadIdx.x * chunk;
+    const int c1 = __syncthreads_count(t0 < n && (unsigned long long)idx[t0] < bound);   // chunk starts below: boundary is in chunk c1-1
+    if (c1 == 0) return 0;
+    const size_t base = (size_t)(c1 - 1) * chunk;
+    if (threadIdx.x == 0) *s_acc = 0;
+    __syncthreads();
+    unsigned cnt = 0;
+    for (size_t o = threadIdx.x; o < chunk; o += 1024) { const size_t u = base + o; cnt += (u < n && (unsigned long long)idx[u] < bound) ? 1u : 0u; }
+    if (cnt) atomicAdd(s_acc, cnt);
+    __syncthreads();
+    const unsigned r = (unsigned)base + *s_acc;
+    __syncthreads();
+    return r;
+}
 __global__ void __launch_bounds__(1024) fs_mg_plan_kernel(FsDev d, const __grid_constant__ MgDev mg) {
     if (!*d.gate) return;
-    __shared__ unsigned s_nh, s_t1, s_carry;
+    __shared__ unsigned s_nh, s_t1, s_carry, s_acc;
     __shared__ int sm_i[32];
     const int tid = threadIdx.x;
     const size_t n = d.n;
-    if (tid == 0) {
-        const uint32_t lo_g = (uint32_t)d.offset;
-        const unsigned long long hi_g = (unsigned long long)d.offset + n;
-        size_t a = 0, bnd = n;
-        while (a < bnd) { size_t mid = a + ((bnd - a) >> 1); if (d.idx[mid] < lo_g) a = mid + 1; else bnd = mid; }
-        s_nh = (unsigned)a;
-        a = 0; bnd = n;
-        while (a < bnd) { size_t mid = a + ((bnd - a) >> 1); if ((unsigned long long)d.idx[mid] < hi_g) a = mid + 1; else bnd = mid; }
-        s_t1 = (unsigned)a;
-        s_carry = 0;
+    if (tid == 0) mg_stamp(mg, 2);
+    {
+        const unsigned nh = mg_count_below(d.idx, n, (unsigned long long)d.offset, &s_acc);
+        const unsigned t1 = mg_count_below(d.idx, n, (unsigned long long)d.offset + n, &s_acc);
+        if (tid == 0) { s_nh = nh; s_t1 = t1; s_carry = 0; }
     }
     __syncthreads();
     const unsigned base = (unsigned)mg.plan[3];
@@ -288,59 +311,69 @@ __global__ void __launch_bounds__(1024) fs_mg_plan_kernel(FsDev d, const __grid_
     }
 }
 
-// pull the maps of remote ancestors through their owner's lazy-clone ancestry into my guest columns
-__global__ void __launch_bounds__(256) fs_mg_import_kernel(FsDev d, const __grid_constant__ MgDev mg) {
+// One launch does both halves of the map clone (fs1.rs:227-229):
+//   CTAs with blockIdx.y <  MG_IMPORT_Y: PULL the maps of remote ancestors through their owner's lazy-clone ancestry into my
+//                                        guest columns (NVLink reads; latency-bound, so they start first and overlap the rest)
+//   CTAs with blockIdx.y >= MG_IMPORT_Y: lazy clone — anc'[l][t] = guest column for imported slots, composed local ancestry
+//                                        otherwise; 4 slots per thread, one 16-byte store per landmark row
+#define MG_IMPORT_Y 4
+__global__ void __launch_bounds__(256) fs_mg_import_compose_kernel(FsDev d, const __grid_constant__ MgDev mg) {
     if (!*d.gate) return;
-    if (!*(volatile int*)mg.err) {
-        const size_t n = d.n, nl = d.n, rows = 6 * d.m;
-        const size_t nh = (size_t)mg.plan[0], t1 = (size_t)mg.plan[1];
-        const size_t cnt = nh + (n - t1), total = cnt * rows;
-        const int ac = *d.anc_cur;                             // the same on every rank
-        for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
-            const size_t row = e / cnt, q = e - row * cnt;
-            const size_t t = q < nh ? q : t1 + (q - nh);
-            if (!(t == 0 || t == t1 || d.idx[t] != d.idx[t - 1])) continue;     // a neighbour copies this ancestor
-            const size_t l = row / 6; const int f = (int)(row - l * 6);
-            const size_t j = d.idx[t], g = j / nl, jl = j - g * nl;
-            const int rst = mg_at<int>(mg, (int)g, mg.o_lmstate)[l];
-            const size_t col = (rst & 2) ? jl : (size_t)mg_at<uint32_t>(mg, (int)g, ac ? mg.o_anc[1] : mg.o_anc[0])[l * nl + jl];
-            const double val = mg_at<double>(mg, (int)g, (rst & 1) ? mg.o_lm[1] : mg.o_lm[0])[lm_index(d.ld, l, f, col)];
-            const int st = d.lmstate[l];
-            fs_lm(d, st & 1)[lm_index(d.ld, l, f, (size_t)mg.gcol[t])] = val;
+    const size_t n = d.n, nl = d.n;
+    if (blockIdx.y < MG_IMPORT_Y) {
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) mg_stamp(mg, 3);
+        const size_t vb = (size_t)blockIdx.y * gridDim.x + blockIdx.x, nvb = (size_t)MG_IMPORT_Y * gridDim.x;
+        if (!*(volatile int*)mg.err) {
+            const size_t rows = 6 * d.m;
+            const size_t nh = (size_t)mg.plan[0], t1 = (size_t)mg.plan[1];
+            const size_t cnt = nh + (n - t1), total = cnt * rows;
+            const int ac = *d.anc_cur;                             // the same on every rank
+            for (size_t e = vb * 256 + threadIdx.x; e < total; e += nvb * 256) {
+                const size_t row = e / cnt, q = e - row * cnt;
+                const size_t t = q < nh ? q : t1 + (q - nh);
+                if (!(t == 0 || t == t1 || d.idx[t] != d.idx[t - 1])) continue;     // a neighbour copies this ancestor
+                const size_t l = row / 6; const int f = (int)(row - l * 6);
+                const size_t j = d.idx[t], g = j / nl, jl = j - g * nl;
+                const int rst = mg_at<int>(mg, (int)g, mg.o_lmstate)[l];
+                const size_t col = (rst & 2) ? jl : (size_t)mg_at<uint32_t>(mg, (int)g, ac ? mg.o_anc[1] : mg.o_anc[0])[l * nl + jl];
+                const double val = mg_at<double>(mg, (int)g, (rst & 1) ? mg.o_lm[1] : mg.o_lm[0])[lm_index(d.ld, l, f, col)];
+                const int st = d.lmstate[l];
+                fs_lm(d, st & 1)[lm_index(d.ld, l, f, (size_t)mg.gcol[t])] = val;
+            }
         }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            const unsigned long long prev = atomicAdd(&mg.plan[6], 1ull);
+            if (prev + 1 == nvb)                                   // my last remote read has returned: tell every rank
+                for (int g = 0; g < mg.G; ++g) atomicAdd_system(mg_at<unsigned>(mg, g, mg.o_ctr) + 64, 1u);
+        }
+        return;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        const unsigned long long prev = atomicAdd(&mg.plan[6], 1ull);
-        if (prev + 1 == gridDim.x)                             // my last remote read has returned: tell every rank
-            for (int g = 0; g < mg.G; ++g) atomicAdd_system(mg_at<unsigned>(mg, g, mg.o_ctr) + 64, 1u);
-    }
-}
-
-// lazy clone: anc'[l][t] = the guest column for imported slots, the composed local ancestry otherwise
-__global__ void __launch_bounds__(256) fs_mg_compose_anc_kernel(FsDev d, const __grid_constant__ MgDev mg) {
-    if (!*d.gate) return;
-    const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (t >= d.n) return;
+    const size_t t = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (t >= n) return;
     const int ac = *d.anc_cur;
     const uint32_t* __restrict__ src = fs_anc(d, ac);
     uint32_t* __restrict__ dst = fs_anc(d, ac ^ 1);
-    const size_t nl = d.n;
-    const size_t j = d.idx[t];
-    const size_t g = j / nl;
-    const size_t l0 = (size_t)blockIdx.y * FS_COMPOSE_ROWS;
-    if ((int)g == mg.rank) {
-        const uint32_t jl = (uint32_t)(j - g * nl);
+    const uint4 jj = *reinterpret_cast<const uint4*>(d.idx + t);
+    const size_t lo = d.offset, hi = d.offset + nl;
+    const bool r0 = jj.x < lo || jj.x >= hi, r1 = jj.y < lo || jj.y >= hi, r2 = jj.z < lo || jj.z >= hi, r3 = jj.w < lo || jj.w >= hi;
+    uint4 gc = make_uint4(0, 0, 0, 0);
+    if (r0 | r1 | r2 | r3) gc = *reinterpret_cast<const uint4*>(mg.gcol + t);
+    const uint32_t a0 = jj.x - (uint32_t)lo, a1 = jj.y - (uint32_t)lo, a2 = jj.z - (uint32_t)lo, a3 = jj.w - (uint32_t)lo;
+    const size_t l0 = (size_t)(blockIdx.y - MG_IMPORT_Y) * FS_COMPOSE_ROWS;
 #pragma unroll
-        for (int rr = 0; rr < FS_COMPOSE_ROWS; ++rr) {
-            size_t l = l0 + rr;
-            if (l < d.m) dst[l * nl + t] = (d.lmstate[l] & 2) ? jl : src[l * nl + jl];
-        }
-    } else {
-        const uint32_t gc = mg.gcol[t];
-#pragma unroll
-        for (int rr = 0; rr < FS_COMPOSE_ROWS; ++rr) { size_t l = l0 + rr; if (l < d.m) dst[l * nl + t] = gc; }
+    for (int rr = 0; rr < FS_COMPOSE_ROWS; ++rr) {
+        const size_t l = l0 + rr;
+        if (l >= d.m) break;
+        const bool ident = (d.lmstate[l] & 2) != 0;
+        const uint32_t* __restrict__ row = src + l * nl;
+        uint4 o;
+        o.x = r0 ? gc.x : (ident ? a0 : row[a0]);
+        o.y = r1 ? gc.y : (ident ? a1 : row[a1]);
+        o.z = r2 ? gc.z : (ident ? a2 : row[a2]);
+        o.w = r3 ? gc.w : (ident ? a3 : row[a3]);
+        *reinterpret_cast<uint4*>(dst + l * nl + t) = o;
     }
 }
 
@@ -348,12 +381,14 @@ __global__ void __launch_bounds__(256) fs_mg_compose_anc_kernel(FsDev d, const _
 __global__ void fs_mg_flip_kernel(FsDev d, const __grid_constant__ MgDev mg) {
     if (!*d.gate) return;
     __shared__ int s_ok;
+    if (threadIdx.x == 0) mg_stamp(mg, 5);
     if (threadIdx.x == 0) s_ok = mg_wait(mg_at<unsigned>(mg, mg.rank, mg.o_ctr) + 64, mg.tgt[2] + (unsigned)mg.G, mg.err) ? 1 : 0;
     __syncthreads();
     for (size_t l = threadIdx.x; l < d.m; l += blockDim.x) d.lmstate[l] &= 1;
     if (threadIdx.x == 0) {
         *d.cur ^= 1; *d.anc_cur ^= 1; d.counters[0] += 1;
         mg.tgt[1] += (unsigned)mg.G * mg.ntl; mg.tgt[2] += (unsigned)mg.G;
+        mg_stamp(mg, 6);
     }
 }
 

@@ -618,6 +618,7 @@ struct pfgpu_fs {
     bool fused_post = false;
     unsigned fx_nt = 0;
     bool step_v2 = true;           // observation-parallel step kernel (PFGPU_STEP_V2=0 selects the one-thread-per-particle form)
+    bool compose_vec = true;       // 4 slots per thread in the ancestry composition (PFGPU_COMPOSE_VEC=0: one)
     int ekf_variant = 3;           // register budget of fs_ekf_kernel: 0 = 64 regs, 1 = 72 regs (2 CTAs/SM), 2 = up to 128 regs (1 CTA/SM)
     FsShard sh;                    // multi-GPU state (world == 1: unused)
     // peer-memory form of the sharded step (fs_mg.cuh): one arena per rank, mapped by every peer
@@ -718,6 +719,7 @@ static int fs_create_impl(const pfgpu_fs_config* cfg, size_t n, size_t n_global,
     rc = xs_work_alloc(h->xs, n);
     if (rc) return fail(rc);
     { const char* e2 = getenv("PFGPU_STEP_V2"); h->step_v2 = !(e2 && e2[0] == '0'); }
+    { const char* e4 = getenv("PFGPU_COMPOSE_VEC"); h->compose_vec = !(e4 && e4[0] == '0'); }
     { const char* e3 = getenv("PFGPU_EKF_VARIANT"); if (e3 && e3[0] >= '0' && e3[0] <= '4') h->ekf_variant = e3[0] - '0'; }
     {   // fused post-step kernel: usable when one co-resident wave covers all tiles
         unsigned nt = cdiv_u(n, FX_TILE);
@@ -817,13 +819,15 @@ static int fs_create_impl(const pfgpu_fs_config* cfg, size_t n, size_t n_global,
                 SH_TRY(cudaMalloc(&mg.tgt, 4 * sizeof(unsigned))); SH_TRY(cudaMemset(mg.tgt, 0, 4 * sizeof(unsigned)));
                 SH_TRY(cudaMalloc(&mg.err, sizeof(int))); SH_TRY(cudaMemset(mg.err, 0, sizeof(int)));
                 SH_TRY(cudaMalloc(&mg.gcol, n * sizeof(unsigned)));
-                SH_TRY(cudaMalloc(&mg.plan, 8 * sizeof(unsigned long long))); SH_TRY(cudaMemset(mg.plan, 0, 8 * sizeof(unsigned long long)));
+                SH_TRY(cudaMalloc(&mg.plan, 32 * sizeof(unsigned long long))); SH_TRY(cudaMemset(mg.plan, 0, 32 * sizeof(unsigned long long)));
                 mg.n_guest = sh.n_guest;
                 SH_TRY(cudaMalloc(&h->fx.flags, 8 * sizeof(int))); SH_TRY(cudaMemset(h->fx.flags, 0, 8 * sizeof(int)));
                 h->fx.dbg = nullptr;
                 if (getenv("PFGPU_POST_TRACE")) {
                     SH_TRY(cudaMalloc(&h->fx.dbg, 32 * sizeof(unsigned long long)));
                     SH_TRY(cudaMemset(h->fx.dbg, 0, 32 * sizeof(unsigned long long)));
+                    unsigned long long one = 1;
+                    SH_TRY(cudaMemcpy(mg.plan + 13, &one, sizeof(one), cudaMemcpyHostToDevice));
                 }
                 h->mg_on = true;
                 // nobody may start pushing into an arena before its owner has zeroed it (cudaMemset above, synchronous) and
@@ -1193,10 +1197,9 @@ extern "C" int pfgpu_fs_step(pfgpu_fs* h, const double u[2], const pfgpu_fs_obs*
         h->ctx.launches++;
         PF_LAUNCH(h->ctx, fs_mg_search_pose_kernel, cdiv_u(d.n, 256), 256, 0, d, h->mg);
         PF_LAUNCH(h->ctx, fs_mg_plan_kernel, 1, 1024, 0, d, h->mg);
-        PF_LAUNCH(h->ctx, fs_mg_import_kernel, (unsigned)h->ctx.num_sms * 4, 256, 0, d, h->mg);
-        if (d.m) {
-            dim3 grid(cdiv_u(d.n, 256), cdiv_u(d.m, FS_COMPOSE_ROWS));
-            PF_LAUNCH(h->ctx, fs_mg_compose_anc_kernel, grid, 256, 0, d, h->mg);
+        {
+            dim3 grid(cdiv_u(d.n / 4, 256), MG_IMPORT_Y + cdiv_u(d.m, FS_COMPOSE_ROWS));
+            PF_LAUNCH(h->ctx, fs_mg_import_compose_kernel, grid, 256, 0, d, h->mg);
         }
         PF_LAUNCH(h->ctx, fs_mg_flip_kernel, 1, 256, 0, d, h->mg);
         if (d.m) {
@@ -1233,9 +1236,15 @@ extern "C" int pfgpu_fs_step(pfgpu_fs* h, const double u[2], const pfgpu_fs_obs*
         h->ctx.launches++;
         PF_LAUNCH(h->ctx, fs_search_pose_kernel, cdiv_u(d.n, 256), 256, 0, d);
         if (d.m) {
-            dim3 grid(cdiv_u(d.n, 256), cdiv_u(d.m, FS_COMPOSE_ROWS));
-            if (d.anc16) PF_LAUNCH(h->ctx, fs_compose_anc_kernel<unsigned short>, grid, 256, 0, d);
-            else         PF_LAUNCH(h->ctx, fs_compose_anc_kernel<uint32_t>, grid, 256, 0, d);
+            if (d.n % 4 == 0 && h->compose_vec) {
+                dim3 grid(cdiv_u(d.n / 4, 256), cdiv_u(d.m, FS_COMPOSE_ROWS));
+                if (d.anc16) PF_LAUNCH(h->ctx, fs_compose_anc_vec_kernel<unsigned short>, grid, 256, 0, d);
+                else         PF_LAUNCH(h->ctx, fs_compose_anc_vec_kernel<uint32_t>, grid, 256, 0, d);
+            } else {
+                dim3 grid(cdiv_u(d.n, 256), cdiv_u(d.m, FS_COMPOSE_ROWS));
+                if (d.anc16) PF_LAUNCH(h->ctx, fs_compose_anc_kernel<unsigned short>, grid, 256, 0, d);
+                else         PF_LAUNCH(h->ctx, fs_compose_anc_kernel<uint32_t>, grid, 256, 0, d);
+            }
         }
         PF_LAUNCH(h->ctx, fs_flip_kernel, 1, 256, 0, d);
         h->steps++;
@@ -1384,6 +1393,7 @@ extern "C" int pfgpu_fs_post_trace(pfgpu_fs* h, unsigned long long* out32) {
     PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
     for (int k = 0; k < 32; ++k) out32[k] = 0;
     if ((h->fused_post || h->mg_on) && h->fx.dbg) PF_CUDA(cudaMemcpy(out32, h->fx.dbg, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (h->mg_on && h->fx.dbg) PF_CUDA(cudaMemcpy(out32 + 8, h->mg.plan + 17, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));   // [8..13]: stages of a resample step
     return 0;
 }
 extern "C" int pfgpu_fs_time_main_kernel(pfgpu_fs* h, int on) {

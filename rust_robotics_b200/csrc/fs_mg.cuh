@@ -156,6 +156,11 @@ __global__ void __launch_bounds__(XS_NT, 2) fs_post_mg_kernel(FsDev d, FxWork fw
     // ---------------- gate: neff = 1 / sum w^2 < NTH (fs1.rs:186-193, 262-263) ----------------
     fx_tile_sum(q, fw.slot[1], 1, sh, fw.flags, pub);
     fx_tile_sum(v, fw.slot[2], 2, sh, fw.flags, pub);
+    // A cross-GPU barrier costs more than a classification, so S2 = sum w (needed only if the gate opens) is classified
+    // speculatively and published under the same barrier; its approximate tile prefix comes from the tile sums of w_raw / S.
+    double toff_w = fx_tile_offset(fw.slot[0], b, sh);
+    if (S > 0.0) toff_w = toff_w / S;
+    fx_classify_at(v, toff_w, fw.slot[2], 2, sh, rel, pub, fw.flags);
     MG_BARRIER();
     if (bl == 0 && tid == 0 && fw.dbg) { unsigned long long t = fx_now(); fw.dbg[2] += t - t_prev; t_prev = t; }
     double qpart = 0.0;
@@ -182,8 +187,6 @@ __global__ void __launch_bounds__(XS_NT, 2) fs_post_mg_kernel(FsDev d, FxWork fw
     }
     if (!gate) { MG_FINISH(); return; }
     // ---------------- resample: S2 = sum w (fs1.rs:207) ----------------
-    fx_classify(v, fw.slot[2], 2, sh, rel, pub);
-    MG_BARRIER();
     fx_chain(fw.slot[2], NT, MgValW{&mg, nl}, ng, sh, fw.flags, pub);
     const double S2 = sh.total;
     if (bl == 0 && tid == 0) d.scal[2] = S2;
@@ -201,11 +204,12 @@ __global__ void __launch_bounds__(XS_NT, 2) fs_post_mg_kernel(FsDev d, FxWork fw
         if (S2 > 0.0) v[k] = v[k] / S2;
         cv[k] = i < n ? ((d.offset + i) == 0 ? r0 : inv) : 0.0;
     }
-    fx_tile_sum(v, fw.slot[3], 3, sh, fw.flags, pub);
-    fx_tile_sum(cv, fw.slot[4], 4, sh, fw.flags, pub);
-    MG_BARRIER();
-    FxTile tc = fx_classify(v, fw.slot[3], 3, sh, rel, pub);
-    FxTile tr = fx_classify(cv, fw.slot[4], 4, sh, rel, pub);
+    // approximate tile prefixes without another publish + barrier (see fs_post_kernel)
+    double toff_c = fx_tile_offset(fw.slot[2], b, sh);
+    if (S2 > 0.0) toff_c = toff_c / S2;
+    const double toff_r = b == 0 ? 0.0 : r0 + ((double)((size_t)b * FX_TILE) - 1.0) * inv;
+    FxTile tc = fx_classify_at(v, toff_c, fw.slot[3], 3, sh, rel, pub, fw.flags);
+    FxTile tr = fx_classify_at(cv, toff_r, fw.slot[4], 4, sh, rel, pub, fw.flags);
     MG_BARRIER();
     if (bl == 0 && tid == 0 && fw.dbg) { unsigned long long t = fx_now(); fw.dbg[3] += t - t_prev; t_prev = t; }
     double c[FX_ITEMS], r[FX_ITEMS];

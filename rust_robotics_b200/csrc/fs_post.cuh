@@ -90,17 +90,39 @@ __device__ __forceinline__ void fx_tile_sum(const double (&v)[FX_ITEMS], const F
 }
 
 // ---- phase 2 (after a grid barrier): classify the tile, publish its aggregate and dirty entries ----------------
-template <class P, class SH>
-__device__ __forceinline__ FxTile fx_classify(const double (&v)[FX_ITEMS], const FxSlot& s, int si, SH& sh, double rel, const P& pub) {
-    const unsigned b = pub.me();
-    FxTile c;
+// approximate sum of the tiles in front of tile b, from the published tile sums of slot s (same order in every CTA)
+template <class SH>
+__device__ __forceinline__ double fx_tile_offset(const FxSlot& s, unsigned b, SH& sh) {
     double part = 0.0;
     for (unsigned t = threadIdx.x; t < b; t += XS_NT) part += s.tsum[t];
     double toff_b = block_sum<XS_NT>(part, sh.sm_d);
     __syncthreads();
     if (threadIdx.x == 0) sh.total = toff_b;
     __syncthreads();
-    c.toff = sh.total;
+    return sh.total;
+}
+template <class P, class SH>
+__device__ __forceinline__ FxTile fx_classify_impl(const double (&v)[FX_ITEMS], double toff, const FxSlot& s, int si, SH& sh, double rel, const P& pub);
+// `toff`: approximate prefix in front of this tile.  It only steers the classification (any value within the margin `rel`
+// of the exact prefix gives the same exact result), so callers may derive it from sums they already hold instead of
+// publishing tile sums of these very values first — e.g. sum(w_i / S) from sum(w_i) / S (one rounding per term apart).
+template <class P, class SH>
+__device__ __forceinline__ FxTile fx_classify_at(const double (&v)[FX_ITEMS], double toff, const FxSlot& s, int si, SH& sh, double rel, const P& pub, int* flags) {
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < FX_ITEMS; ++k) if (!(v[k] >= 0.0) || !(v[k] <= 1.7976931348623157e308)) bad = true;
+    if (bad) pub.bad(flags);
+    return fx_classify_impl(v, toff, s, si, sh, rel, pub);
+}
+template <class P, class SH>
+__device__ __forceinline__ FxTile fx_classify(const double (&v)[FX_ITEMS], const FxSlot& s, int si, SH& sh, double rel, const P& pub) {
+    return fx_classify_impl(v, fx_tile_offset(s, pub.me(), sh), s, si, sh, rel, pub);
+}
+template <class P, class SH>
+__device__ __forceinline__ FxTile fx_classify_impl(const double (&v)[FX_ITEMS], double toff, const FxSlot& s, int si, SH& sh, double rel, const P& pub) {
+    const unsigned b = pub.me();
+    FxTile c;
+    c.toff = toff;
     double tsum = 0.0;
 #pragma unroll
     for (int k = 0; k < FX_ITEMS; ++k) tsum += v[k];
@@ -428,13 +450,15 @@ __global__ void __launch_bounds__(XS_NT, 2) fs_post_kernel(FsDev d, FxWork fw, d
         if (S2 > 0.0) v[k] = v[k] / S2;                        // normalize_weights inside resample() fs1.rs:207
         cv[k] = i < n ? (i == 0 ? r0 : inv) : 0.0;
     }
-    fx_tile_sum(v, fw.slot[3], 3, sh, fw.flags, pub);
-    fx_tile_sum(cv, fw.slot[4], 4, sh, fw.flags, pub);
+    // approximate tile prefixes without another publish + barrier: the CDF's from the tile sums of w (slot 2) scaled by
+    // 1/S2, the comb's in closed form
     FX_STAMP(11);
-    grid.sync();
+    double toff_c = fx_tile_offset(fw.slot[2], b, sh);
+    if (S2 > 0.0) toff_c = toff_c / S2;
+    const double toff_r = b == 0 ? 0.0 : r0 + ((double)((size_t)b * FX_TILE) - 1.0) * inv;
     FX_STAMP(12);
-    FxTile tc = fx_classify(v, fw.slot[3], 3, sh, rel, pub);
-    FxTile tr = fx_classify(cv, fw.slot[4], 4, sh, rel, pub);
+    FxTile tc = fx_classify_at(v, toff_c, fw.slot[3], 3, sh, rel, pub, fw.flags);
+    FxTile tr = fx_classify_at(cv, toff_r, fw.slot[4], 4, sh, rel, pub, fw.flags);
     FX_STAMP(13);
     grid.sync();
     FX_STAMP(14);

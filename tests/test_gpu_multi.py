@@ -20,7 +20,8 @@ def n_gpus():
 
 # mode 2: peer-memory step (fs_mg.cuh, the default when the shard size allows it); mode 1: NCCL collectives (fs_sharded.cuh)
 @pytest.mark.parametrize("world,n,side,steps,mode,guests", [(2, 4096, 6, 16, 2, 0), (2, 1 << 16, 8, 6, 2, 0), (2, 4096, 6, 16, 1, 0),
-                                                            (2, 4000, 6, 12, 1, 0), (2, 4096, 6, 40, 2, 192), (2, 4096, 6, 40, 1, 192)])
+                                                            (2, 4000, 6, 12, 1, 0), (2, 4096, 6, 40, 2, 192), (2, 4096, 6, 40, 1, 192),
+                                                            (4, 8192, 6, 14, 2, 0), (8, 16384, 6, 14, 2, 0)])
 def test_sharded_fastslam_matches_oracle(world, n, side, steps, mode, guests):
     if n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")

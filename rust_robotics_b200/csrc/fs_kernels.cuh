@@ -414,6 +414,40 @@ __global__ void __launch_bounds__(256) fs_compose_anc_vec_kernel(FsDev d) {
         *reinterpret_cast<V*>(dst + l * d.n + t) = o;
     }
 }
+// the same with the ping-pong flip (fs_flip_kernel) done by the last CTA to finish: one launch fewer per step
+template <class AncT>
+__global__ void __launch_bounds__(256) fs_compose_flip_kernel(FsDev d) {
+    if (!*d.gate) return;
+    typedef typename AncVec4<AncT>::type V;
+    __shared__ int s_last;
+    const size_t t = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (t < d.n) {
+        const int ac = *d.anc_cur;
+        const AncT* __restrict__ src = reinterpret_cast<const AncT*>(fs_anc(d, ac));
+        AncT* __restrict__ dst = reinterpret_cast<AncT*>(fs_anc(d, ac ^ 1));
+        const uint4 jj = *reinterpret_cast<const uint4*>(d.idx + t);
+        const size_t l0 = (size_t)blockIdx.y * FS_COMPOSE_ROWS;
+#pragma unroll
+        for (int rr = 0; rr < FS_COMPOSE_ROWS; ++rr) {
+            const size_t l = l0 + rr;
+            if (l >= d.m) break;
+            V o;
+            if (d.lmstate[l] & 2) { o.x = (AncT)jj.x; o.y = (AncT)jj.y; o.z = (AncT)jj.z; o.w = (AncT)jj.w; }
+            else {
+                const AncT* __restrict__ row = src + l * d.n;
+                o.x = row[jj.x]; o.y = row[jj.y]; o.z = row[jj.z]; o.w = row[jj.w];
+            }
+            *reinterpret_cast<V*>(dst + l * d.n + t) = o;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&d.counters[2], 1u) + 1u == gridDim.x * gridDim.y) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;                                           // every other CTA has read lmstate / anc_cur by now
+    for (size_t l = threadIdx.x; l < d.m; l += blockDim.x) d.lmstate[l] &= 1;
+    if (threadIdx.x == 0) { *d.cur ^= 1; *d.anc_cur ^= 1; d.counters[0] += 1; d.counters[2] = 0; }
+}
 //   each landmark's ancestry column with this resample's ancestry (see fs_compose_anc_kernel).  A CTA = 256 slots, all m
 //   landmarks (coalesced 2 or 4 B per particle and landmark in each direction).
 template <class AncT>

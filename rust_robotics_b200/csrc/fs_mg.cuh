@@ -30,10 +30,11 @@ struct MgDev {
     size_t o_w_raw, o_w;
     size_t o_px[2], o_py[2], o_pyaw[2], o_lm[2], o_anc[2], o_lmstate;
     unsigned* tgt;              // local [4]: arrivals already consumed on the three counters; [3] = launch epoch
-    int* err;                   // local, sticky: 2 = a peer never arrived (timeout), 3 = guest columns exhausted
+    int* err;                   // local, sticky: 2 = a peer never arrived (timeout)
     unsigned* gcol;             // local [n]: guest column of each importing slot
     unsigned long long* plan;   // local [32]: 0 head-run length, 1 tail-run start, 2 imports of this resample, 3 guests in use,
-                                //            4 imported (total), 5 compactions, 6 import CTAs finished; trace (PFGPU_POST_TRACE):
+                                //            4 imported (total), 5 eager rebuilds, 6 / 8 finished CTAs of the clone / search launch,
+                                //            7 this resample rebuilds eagerly; trace (PFGPU_POST_TRACE):
                                 //            13 on/off, 14 last stamp, 16+k accumulated ns up to stage k of a resample step
     size_t n_guest;
 };
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(XS_NT, 2) fs_post_mg_kernel(FsDev d, FxWork fw
         *d.gate = gate;
     }
     if (!gate) { MG_FINISH(); return; }
+    if (bl == 0 && tid == 0) { mg.plan[6] = 0; mg.plan[8] = 0; }     // completion counters of the two launches that follow
     // ---------------- resample: S2 = sum w (fs1.rs:207) ----------------
     fx_chain(fw.slot[2], NT, MgValW{&mg, nl}, ng, sh, fw.flags, pub);
     const double S2 = sh.total;
@@ -232,106 +234,124 @@ __global__ void __launch_bounds__(XS_NT, 2) fs_post_mg_kernel(FsDev d, FxWork fw
 #undef MG_FINISH
 }
 
-// index walk fs1.rs:224-226 in the global CDF + pose clone fs1.rs:227-229 (the ancestor's pose is pulled from its owner)
-__global__ void __launch_bounds__(256) fs_mg_search_pose_kernel(FsDev d, const __grid_constant__ MgDev mg) {
-    if (!*d.gate) return;
-    __shared__ int s_ok;
-    if (blockIdx.x == 0 && threadIdx.x == 0) mg_stamp(mg, 1);
-    if (threadIdx.x == 0)
-        s_ok = mg_wait(mg_at<unsigned>(mg, mg.rank, mg.o_ctr) + 32, mg.tgt[1] + (unsigned)mg.G * mg.ntl, mg.err) ? 1 : 0;
-    __syncthreads();
-    if (!s_ok) return;
-    const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (t >= d.n) return;
-    const double* __restrict__ cum_all = mg_at<double>(mg, mg.rank, mg.o_cum_all);
-    const double r = d.rcomb[t];
-    size_t lo = 0, hi = d.n_global;
-    while (lo < hi) {
-        size_t mid = lo + ((hi - lo) >> 1);
-        if (cum_all[mid] < r) lo = mid + 1; else hi = mid;
-    }
-    const size_t j = lo < d.n_global ? lo : d.n_global - 1;
-    d.idx[t] = (uint32_t)j;
-    const int cur = *d.cur;                                    // the same on every rank: all ranks flip together
-    const size_t nl = d.n, g = j / nl, jl = j - g * nl;
-    fs_px(d, cur ^ 1)[t] = mg_at<double>(mg, (int)g, cur ? mg.o_px[1] : mg.o_px[0])[jl];
-    fs_py(d, cur ^ 1)[t] = mg_at<double>(mg, (int)g, cur ? mg.o_py[1] : mg.o_py[0])[jl];
-    fs_pyaw(d, cur ^ 1)[t] = mg_at<double>(mg, (int)g, cur ? mg.o_pyaw[1] : mg.o_pyaw[0])[jl];
-    d.w[t] = 1.0 / (double)d.n_global;
-}
-
-// Which of my slots have an ancestor on another rank, and which guest column each of them gets.  The ancestry is
-// monotone, so these slots are a head run [0, nh) (ancestors below my block) and a tail run [t1, n) (above); slots that
-// share an ancestor share a guest column (the first of them copies).
-// number of leading slots whose ancestor index is below `bound` (idx ascends): all 1024 threads, two rounds
-__device__ __forceinline__ unsigned mg_count_below(const uint32_t* __restrict__ idx, size_t n, unsigned long long bound, unsigned* s_acc) {
-    const size_t chunk = (n + 1023) / 1024;
+// ---- resample, part 2 -------------------------------------------------------------------------------------------------
+// number of leading slots whose ancestor index is below `bound` (idx ascends): all NT threads of the CTA, two rounds
+template <int NT>
+__device__ __forceinline__ unsigned mg_count_below(const uint32_t* idx, size_t n, unsigned long long bound, unsigned* s_acc) {
+    const size_t chunk = (n + NT - 1) / NT;
     const size_t t0 = (size_t)threadIdx.x * chunk;
-    const int c1 = __syncthreads_count(t0 < n && (unsigned long long)idx[t0] < bound);   // chunk starts below: boundary is in chunk c1-1
+    const int c1 = __syncthreads_count(t0 < n && (unsigned long long)__ldcg(idx + t0) < bound);   // chunk starts below: boundary is in chunk c1-1
     if (c1 == 0) return 0;
     const size_t base = (size_t)(c1 - 1) * chunk;
     if (threadIdx.x == 0) *s_acc = 0;
     __syncthreads();
     unsigned cnt = 0;
-    for (size_t o = threadIdx.x; o < chunk; o += 1024) { const size_t u = base + o; cnt += (u < n && (unsigned long long)idx[u] < bound) ? 1u : 0u; }
+    for (size_t o = threadIdx.x; o < chunk; o += NT) { const size_t u = base + o; cnt += (u < n && (unsigned long long)__ldcg(idx + u) < bound) ? 1u : 0u; }
     if (cnt) atomicAdd(s_acc, cnt);
     __syncthreads();
     const unsigned r = (unsigned)base + *s_acc;
     __syncthreads();
     return r;
 }
-__global__ void __launch_bounds__(1024) fs_mg_plan_kernel(FsDev d, const __grid_constant__ MgDev mg) {
-    if (!*d.gate) return;
-    __shared__ unsigned s_nh, s_t1, s_carry, s_acc;
-    __shared__ int sm_i[32];
+// Which of my slots have an ancestor on another rank, and which guest column each of them gets.  The ancestry is
+// monotone, so these slots are a head run [0, nh) (ancestors below my block) and a tail run [t1, n) (above); slots that
+// share an ancestor share a guest column (the first of them copies).  If the guests left do not suffice, this rank
+// rebuilds its shard EAGERLY in this resample instead (plan[7] = 1): every landmark of every slot is copied (pulled, if
+// remote) into its own column of the other buffer, which needs no guest column and frees all of them.
+template <int NT>
+__device__ __forceinline__ void mg_plan(const FsDev& d, const MgDev& mg, int* sm_i /* NT/32 */, unsigned* s_u /* 4 */) {
     const int tid = threadIdx.x;
     const size_t n = d.n;
-    if (tid == 0) mg_stamp(mg, 2);
-    {
-        const unsigned nh = mg_count_below(d.idx, n, (unsigned long long)d.offset, &s_acc);
-        const unsigned t1 = mg_count_below(d.idx, n, (unsigned long long)d.offset + n, &s_acc);
-        if (tid == 0) { s_nh = nh; s_t1 = t1; s_carry = 0; }
-    }
+    const unsigned nh = mg_count_below<NT>(d.idx, n, (unsigned long long)d.offset, &s_u[3]);
+    const unsigned t1 = mg_count_below<NT>(d.idx, n, (unsigned long long)d.offset + n, &s_u[3]);
+    if (tid == 0) { s_u[0] = nh; s_u[1] = t1; s_u[2] = 0; }
     __syncthreads();
     const unsigned base = (unsigned)mg.plan[3];
     for (int run = 0; run < 2; ++run) {
-        const size_t start = run == 0 ? 0 : s_t1, end = run == 0 ? s_nh : n;
-        for (size_t c = start; c < end; c += 1024) {
+        const size_t start = run == 0 ? 0 : s_u[1], end = run == 0 ? s_u[0] : n;
+        for (size_t c = start; c < end; c += NT) {
             const size_t t = c + tid;
-            const int flag = (t < end && (t == start || d.idx[t] != d.idx[t - 1])) ? 1 : 0;
+            const int flag = (t < end && (t == start || __ldcg(d.idx + t) != __ldcg(d.idx + t - 1))) ? 1 : 0;
             int tot;
-            const int ex = block_excl_scan_int<1024>(flag, &tot, sm_i);
-            if (t < end) mg.gcol[t] = (unsigned)n + base + s_carry + (unsigned)(ex + flag - 1);
+            const int ex = block_excl_scan_int<NT>(flag, &tot, sm_i);
+            if (t < end) mg.gcol[t] = (unsigned)n + base + s_u[2] + (unsigned)(ex + flag - 1);
             __syncthreads();
-            if (tid == 0) s_carry += (unsigned)tot;
+            if (tid == 0) s_u[2] += (unsigned)tot;
             __syncthreads();
         }
     }
     if (tid == 0) {
-        const unsigned need = s_carry;
-        mg.plan[0] = s_nh; mg.plan[1] = s_t1; mg.plan[2] = need; mg.plan[6] = 0;
-        if ((size_t)base + need > mg.n_guest) *mg.err = 3;
-        else { mg.plan[3] = base + need; mg.plan[4] += need; }
+        const unsigned need = s_u[2];
+        mg.plan[0] = s_u[0]; mg.plan[1] = s_u[1]; mg.plan[2] = need;
+        mg.plan[4] += need;
+        if ((size_t)base + need > mg.n_guest) { mg.plan[7] = 1; mg.plan[5] += 1; }
+        else { mg.plan[7] = 0; mg.plan[3] = base + need; }
     }
 }
 
-// One launch does both halves of the map clone (fs1.rs:227-229):
+// index walk fs1.rs:224-226 in the global CDF + pose clone fs1.rs:227-229 (the ancestor's pose is pulled from its owner);
+// the last CTA to finish plans the map import
+__global__ void __launch_bounds__(256) fs_mg_search_plan_kernel(FsDev d, const __grid_constant__ MgDev mg) {
+    if (!*d.gate) return;
+    __shared__ int s_ok, s_last;
+    __shared__ int sm_i[8];
+    __shared__ unsigned s_u[4];
+    if (blockIdx.x == 0 && threadIdx.x == 0) mg_stamp(mg, 1);
+    if (threadIdx.x == 0)
+        s_ok = mg_wait(mg_at<unsigned>(mg, mg.rank, mg.o_ctr) + 32, mg.tgt[1] + (unsigned)mg.G * mg.ntl, mg.err) ? 1 : 0;
+    __syncthreads();
+    const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (s_ok && t < d.n) {
+        const double* __restrict__ cum_all = mg_at<double>(mg, mg.rank, mg.o_cum_all);
+        const double r = d.rcomb[t];
+        size_t lo = 0, hi = d.n_global;
+        while (lo < hi) {
+            size_t mid = lo + ((hi - lo) >> 1);
+            if (cum_all[mid] < r) lo = mid + 1; else hi = mid;
+        }
+        const size_t j = lo < d.n_global ? lo : d.n_global - 1;
+        d.idx[t] = (uint32_t)j;
+        const int cur = *d.cur;                                // the same on every rank: all ranks flip together
+        const size_t nl = d.n, g = j / nl, jl = j - g * nl;
+        fs_px(d, cur ^ 1)[t] = mg_at<double>(mg, (int)g, cur ? mg.o_px[1] : mg.o_px[0])[jl];
+        fs_py(d, cur ^ 1)[t] = mg_at<double>(mg, (int)g, cur ? mg.o_py[1] : mg.o_py[0])[jl];
+        fs_pyaw(d, cur ^ 1)[t] = mg_at<double>(mg, (int)g, cur ? mg.o_pyaw[1] : mg.o_pyaw[0])[jl];
+        d.w[t] = 1.0 / (double)d.n_global;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&mg.plan[8], 1ull) + 1 == gridDim.x) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) mg_stamp(mg, 2);
+    if (*(volatile int*)mg.err) return;                        // a peer went missing: idx is not valid, nothing to plan
+    mg_plan<256>(d, mg, sm_i, s_u);
+}
+
+// One launch finishes the resample (fs1.rs:227-229 for the maps, then the ping-pong flip):
 //   CTAs with blockIdx.y <  MG_IMPORT_Y: PULL the maps of remote ancestors through their owner's lazy-clone ancestry into my
 //                                        guest columns (NVLink reads; latency-bound, so they start first and overlap the rest)
 //   CTAs with blockIdx.y >= MG_IMPORT_Y: lazy clone — anc'[l][t] = guest column for imported slots, composed local ancestry
 //                                        otherwise; 4 slots per thread, one 16-byte store per landmark row
+//                                        (eager rebuild, plan[7]: copy the landmarks themselves instead, see mg_plan)
+//   the last CTA to finish tells every rank that my reads of their state are over, waits for the same from all of them,
+//   and flips the ping-pong state (nobody may see the flip while still reading the old state).
 #define MG_IMPORT_Y 4
-__global__ void __launch_bounds__(256) fs_mg_import_compose_kernel(FsDev d, const __grid_constant__ MgDev mg) {
+__global__ void __launch_bounds__(256) fs_mg_clone_kernel(FsDev d, const __grid_constant__ MgDev mg) {
     if (!*d.gate) return;
+    __shared__ int s_last, s_ok;
     const size_t n = d.n, nl = d.n;
+    const int eager = (int)mg.plan[7];
+    const int ac = *d.anc_cur;                                     // the same on every rank
+    const bool dead = *(volatile int*)mg.err != 0;                 // a peer went missing: skip the data movement, keep the protocol
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) mg_stamp(mg, 3);
     if (blockIdx.y < MG_IMPORT_Y) {
-        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) mg_stamp(mg, 3);
-        const size_t vb = (size_t)blockIdx.y * gridDim.x + blockIdx.x, nvb = (size_t)MG_IMPORT_Y * gridDim.x;
-        if (!*(volatile int*)mg.err) {
+        if (!eager && !dead) {
+            const size_t vb = (size_t)blockIdx.y * gridDim.x + blockIdx.x, nvb = (size_t)MG_IMPORT_Y * gridDim.x;
             const size_t rows = 6 * d.m;
             const size_t nh = (size_t)mg.plan[0], t1 = (size_t)mg.plan[1];
             const size_t cnt = nh + (n - t1), total = cnt * rows;
-            const int ac = *d.anc_cur;                             // the same on every rank
             for (size_t e = vb * 256 + threadIdx.x; e < total; e += nvb * 256) {
                 const size_t row = e / cnt, q = e - row * cnt;
                 const size_t t = q < nh ? q : t1 + (q - nh);
@@ -345,76 +365,72 @@ __global__ void __launch_bounds__(256) fs_mg_import_compose_kernel(FsDev d, cons
                 fs_lm(d, st & 1)[lm_index(d.ld, l, f, (size_t)mg.gcol[t])] = val;
             }
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence_system();
-            const unsigned long long prev = atomicAdd(&mg.plan[6], 1ull);
-            if (prev + 1 == nvb)                                   // my last remote read has returned: tell every rank
-                for (int g = 0; g < mg.G; ++g) atomicAdd_system(mg_at<unsigned>(mg, g, mg.o_ctr) + 64, 1u);
-        }
-        return;
-    }
-    const size_t t = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
-    if (t >= n) return;
-    const int ac = *d.anc_cur;
-    const uint32_t* __restrict__ src = fs_anc(d, ac);
-    uint32_t* __restrict__ dst = fs_anc(d, ac ^ 1);
-    const uint4 jj = *reinterpret_cast<const uint4*>(d.idx + t);
-    const size_t lo = d.offset, hi = d.offset + nl;
-    const bool r0 = jj.x < lo || jj.x >= hi, r1 = jj.y < lo || jj.y >= hi, r2 = jj.z < lo || jj.z >= hi, r3 = jj.w < lo || jj.w >= hi;
-    uint4 gc = make_uint4(0, 0, 0, 0);
-    if (r0 | r1 | r2 | r3) gc = *reinterpret_cast<const uint4*>(mg.gcol + t);
-    const uint32_t a0 = jj.x - (uint32_t)lo, a1 = jj.y - (uint32_t)lo, a2 = jj.z - (uint32_t)lo, a3 = jj.w - (uint32_t)lo;
-    const size_t l0 = (size_t)(blockIdx.y - MG_IMPORT_Y) * FS_COMPOSE_ROWS;
+    } else {
+        const size_t t = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
+        const size_t l0 = (size_t)(blockIdx.y - MG_IMPORT_Y) * FS_COMPOSE_ROWS;
+        if (t < n && !eager && !dead) {
+            const uint32_t* __restrict__ src = fs_anc(d, ac);
+            uint32_t* __restrict__ dst = fs_anc(d, ac ^ 1);
+            const uint4 jj = *reinterpret_cast<const uint4*>(d.idx + t);
+            const size_t lo = d.offset, hi = d.offset + nl;
+            const bool r0 = jj.x < lo || jj.x >= hi, r1 = jj.y < lo || jj.y >= hi, r2 = jj.z < lo || jj.z >= hi, r3 = jj.w < lo || jj.w >= hi;
+            uint4 gc = make_uint4(0, 0, 0, 0);
+            if (r0 | r1 | r2 | r3) gc = *reinterpret_cast<const uint4*>(mg.gcol + t);
+            const uint32_t a0 = jj.x - (uint32_t)lo, a1 = jj.y - (uint32_t)lo, a2 = jj.z - (uint32_t)lo, a3 = jj.w - (uint32_t)lo;
 #pragma unroll
-    for (int rr = 0; rr < FS_COMPOSE_ROWS; ++rr) {
-        const size_t l = l0 + rr;
-        if (l >= d.m) break;
-        const bool ident = (d.lmstate[l] & 2) != 0;
-        const uint32_t* __restrict__ row = src + l * nl;
-        uint4 o;
-        o.x = r0 ? gc.x : (ident ? a0 : row[a0]);
-        o.y = r1 ? gc.y : (ident ? a1 : row[a1]);
-        o.z = r2 ? gc.z : (ident ? a2 : row[a2]);
-        o.w = r3 ? gc.w : (ident ? a3 : row[a3]);
-        *reinterpret_cast<uint4*>(dst + l * nl + t) = o;
+            for (int rr = 0; rr < FS_COMPOSE_ROWS; ++rr) {
+                const size_t l = l0 + rr;
+                if (l >= d.m) break;
+                const bool ident = (d.lmstate[l] & 2) != 0;
+                const uint32_t* __restrict__ row = src + l * nl;
+                uint4 o;
+                o.x = r0 ? gc.x : (ident ? a0 : row[a0]);
+                o.y = r1 ? gc.y : (ident ? a1 : row[a1]);
+                o.z = r2 ? gc.z : (ident ? a2 : row[a2]);
+                o.w = r3 ? gc.w : (ident ? a3 : row[a3]);
+                *reinterpret_cast<uint4*>(dst + l * nl + t) = o;
+            }
+        } else if (!dead) {
+            // eager rebuild: lm[other][l][.][t] = the ancestor's landmark, local or remote, through its owner's ancestry.
+            // This CTA owns slots [1024 bx, +1024) x landmarks [l0, l0 + ROWS): consecutive threads take consecutive slots
+            // (coalesced columns), iterations are independent (several gathers in flight per thread).
+            const size_t tb = (size_t)blockIdx.x * 1024;
+#pragma unroll 4
+            for (int it = 0; it < 4 * FS_COMPOSE_ROWS; ++it) {
+                const int p = it * 256 + threadIdx.x;
+                const size_t tk = tb + (size_t)(p & 1023), l = l0 + (size_t)(p >> 10);
+                if (tk >= n || l >= d.m) continue;
+                const size_t j = d.idx[tk], g = j / nl, jl = j - g * nl;
+                const int rst = mg_at<int>(mg, (int)g, mg.o_lmstate)[l];
+                const size_t col = (rst & 2) ? jl : (size_t)mg_at<uint32_t>(mg, (int)g, ac ? mg.o_anc[1] : mg.o_anc[0])[l * nl + jl];
+                const double* __restrict__ sl = mg_at<double>(mg, (int)g, (rst & 1) ? mg.o_lm[1] : mg.o_lm[0]);
+                double* __restrict__ o = fs_lm(d, (d.lmstate[l] & 1) ^ 1);
+#pragma unroll
+                for (int f = 0; f < 6; ++f) o[lm_index(d.ld, l, f, tk)] = sl[lm_index(d.ld, l, f, col)];
+            }
+        }
     }
-}
-
-// flip the ping-pong state once every rank has finished reading the old one
-__global__ void fs_mg_flip_kernel(FsDev d, const __grid_constant__ MgDev mg) {
-    if (!*d.gate) return;
-    __shared__ int s_ok;
-    if (threadIdx.x == 0) mg_stamp(mg, 5);
-    if (threadIdx.x == 0) s_ok = mg_wait(mg_at<unsigned>(mg, mg.rank, mg.o_ctr) + 64, mg.tgt[2] + (unsigned)mg.G, mg.err) ? 1 : 0;
+    // ---- completion: the last CTA signals, waits for all ranks, flips ----
+    __threadfence();
     __syncthreads();
-    for (size_t l = threadIdx.x; l < d.m; l += blockDim.x) d.lmstate[l] &= 1;
+    if (threadIdx.x == 0) s_last = (atomicAdd(&mg.plan[6], 1ull) + 1 == (unsigned long long)gridDim.x * gridDim.y) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) {
+        mg_stamp(mg, 5);
+        for (int g = 0; g < mg.G; ++g) atomicAdd_system(mg_at<unsigned>(mg, g, mg.o_ctr) + 64, 1u);   // my reads of your state are over
+        s_ok = mg_wait(mg_at<unsigned>(mg, mg.rank, mg.o_ctr) + 64, mg.tgt[2] + (unsigned)mg.G, mg.err) ? 1 : 0;
+    }
+    __syncthreads();
+    for (size_t l = threadIdx.x; l < d.m; l += blockDim.x) {
+        const int st = __ldcg(d.lmstate + l);
+        d.lmstate[l] = eager ? (((st & 1) ^ 1) | 2) : (st & 1);   // eager: every landmark now sits in its own column of the other buffer
+    }
     if (threadIdx.x == 0) {
         *d.cur ^= 1; *d.anc_cur ^= 1; d.counters[0] += 1;
         mg.tgt[1] += (unsigned)mg.G * mg.ntl; mg.tgt[2] += (unsigned)mg.G;
+        if (eager) mg.plan[3] = 0;
         mg_stamp(mg, 6);
     }
-}
-
-// guests more than half used: materialise the shard (frees all guests) — after the flip, when no peer reads my maps
-__global__ void __launch_bounds__(256) fs_mg_compact_kernel(FsDev d, const __grid_constant__ MgDev mg) {
-    if (!*d.gate || mg.plan[3] * 2 <= mg.n_guest) return;
-    const int ac = *d.anc_cur;
-    for (size_t t = (size_t)blockIdx.x * 256 + threadIdx.x; t < d.n; t += (size_t)gridDim.x * 256) {
-        for (size_t l = blockIdx.y; l < d.m; l += gridDim.y) {
-            const int st = d.lmstate[l];
-            if (st & 2) continue;
-            const size_t col = fs_anc_load(d, ac, l * d.n + t);
-            const double* __restrict__ s = fs_lm(d, st & 1);
-            double* __restrict__ o = fs_lm(d, (st & 1) ^ 1);
-#pragma unroll
-            for (int f = 0; f < 6; ++f) o[lm_index(d.ld, l, f, t)] = s[lm_index(d.ld, l, f, col)];
-        }
-    }
-}
-__global__ void fs_mg_compact_finish_kernel(FsDev d, const __grid_constant__ MgDev mg) {
-    if (!*d.gate || mg.plan[3] * 2 <= mg.n_guest) return;
-    for (size_t l = threadIdx.x; l < d.m; l += blockDim.x) { int st = d.lmstate[l]; if (!(st & 2)) d.lmstate[l] = ((st & 1) ^ 1) | 2; }
-    __syncthreads();
-    if (threadIdx.x == 0) { mg.plan[3] = 0; mg.plan[5] += 1; }
 }

@@ -647,7 +647,7 @@ static int fs_create_impl(const pfgpu_fs_config* cfg, size_t n, size_t n_global,
     h->cfg = *cfg; h->seed = seed; h->world = world; h->rank = rank;
     FsDev& d = h->d;
     d.n = n; d.n_global = n_global; d.offset = offset; d.m = m; d.eager = 0;
-    h->sh.n_guest = world > 1 ? std::max<size_t>(2048, n / 8) : 0;
+    h->sh.n_guest = world > 1 ? std::max<size_t>(2048, n / 4) : 0;
     if (world > 1) { const char* eg = getenv("PFGPU_GUEST_COLS"); if (eg && atoll(eg) > 0) h->sh.n_guest = (size_t)atoll(eg); }
     d.ld = n + h->sh.n_guest;
     h->lm_bytes = (m ? m : 1) * 6 * d.ld * sizeof(double);
@@ -1195,17 +1195,10 @@ extern "C" int pfgpu_fs_step(pfgpu_fs* h, const double u[2], const pfgpu_fs_obs*
         void* args[] = { (void*)&d, (void*)&h->fx, (void*)&h->mg, (void*)&nth, (void*)&seed, (void*)&rel, (void*)&last_po, (void*)&last_k };
         PF_CUDA(cudaLaunchCooperativeKernel((void*)fs_post_mg_kernel, dim3(h->mg.ntl), dim3(XS_NT), args, sizeof(MgShared), h->ctx.stream));
         h->ctx.launches++;
-        PF_LAUNCH(h->ctx, fs_mg_search_pose_kernel, cdiv_u(d.n, 256), 256, 0, d, h->mg);
-        PF_LAUNCH(h->ctx, fs_mg_plan_kernel, 1, 1024, 0, d, h->mg);
+        PF_LAUNCH(h->ctx, fs_mg_search_plan_kernel, cdiv_u(d.n, 256), 256, 0, d, h->mg);
         {
             dim3 grid(cdiv_u(d.n / 4, 256), MG_IMPORT_Y + cdiv_u(d.m, FS_COMPOSE_ROWS));
-            PF_LAUNCH(h->ctx, fs_mg_import_compose_kernel, grid, 256, 0, d, h->mg);
-        }
-        PF_LAUNCH(h->ctx, fs_mg_flip_kernel, 1, 256, 0, d, h->mg);
-        if (d.m) {
-            dim3 cgrid((unsigned)h->ctx.num_sms, 8);
-            PF_LAUNCH(h->ctx, fs_mg_compact_kernel, cgrid, 256, 0, d, h->mg);
-            PF_LAUNCH(h->ctx, fs_mg_compact_finish_kernel, 1, 256, 0, d, h->mg);
+            PF_LAUNCH(h->ctx, fs_mg_clone_kernel, grid, 256, 0, d, h->mg);
         }
         h->steps++;
         if (did) {
@@ -1235,6 +1228,19 @@ extern "C" int pfgpu_fs_step(pfgpu_fs* h, const double u[2], const pfgpu_fs_obs*
         PF_CUDA(cudaLaunchCooperativeKernel((void*)fs_post_kernel, dim3(nt), dim3(XS_NT), args, 0, h->ctx.stream));
         h->ctx.launches++;
         PF_LAUNCH(h->ctx, fs_search_pose_kernel, cdiv_u(d.n, 256), 256, 0, d);
+        if (d.m && d.n % 4 == 0 && h->compose_vec) {
+            dim3 grid(cdiv_u(d.n / 4, 256), cdiv_u(d.m, FS_COMPOSE_ROWS));
+            if (d.anc16) PF_LAUNCH(h->ctx, fs_compose_flip_kernel<unsigned short>, grid, 256, 0, d);
+            else         PF_LAUNCH(h->ctx, fs_compose_flip_kernel<uint32_t>, grid, 256, 0, d);
+            h->steps++;
+            if (did) {
+                int* hp = reinterpret_cast<int*>(h->h_pin + 32);
+                PF_CUDA(cudaMemcpyAsync(hp, d.gate, sizeof(int), cudaMemcpyDeviceToHost, h->ctx.stream));
+                PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+                *did = *hp;
+            }
+            return 0;
+        }
         if (d.m) {
             if (d.n % 4 == 0 && h->compose_vec) {
                 dim3 grid(cdiv_u(d.n / 4, 256), cdiv_u(d.m, FS_COMPOSE_ROWS));

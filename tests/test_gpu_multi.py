@@ -20,7 +20,7 @@ def n_gpus():
 
 # mode 2: peer-memory step (fs_mg.cuh, the default when the shard size allows it); mode 1: NCCL collectives (fs_sharded.cuh)
 @pytest.mark.parametrize("world,n,side,steps,mode,guests", [(2, 4096, 6, 16, 2, 0), (2, 1 << 16, 8, 6, 2, 0), (2, 4096, 6, 16, 1, 0),
-                                                            (2, 4000, 6, 12, 1, 0), (2, 4096, 6, 40, 2, 192), (2, 4096, 6, 40, 1, 192),
+                                                            (2, 4000, 6, 12, 1, 0), (2, 4096, 6, 40, 2, 40), (2, 4096, 6, 40, 1, 192),
                                                             (4, 8192, 6, 14, 2, 0), (8, 16384, 6, 14, 2, 0)])
 def test_sharded_fastslam_matches_oracle(world, n, side, steps, mode, guests):
     if n_gpus() < world:
@@ -28,7 +28,7 @@ def test_sharded_fastslam_matches_oracle(world, n, side, steps, mode, guests):
     env = dict(os.environ)
     env["PFGPU_SHARD_P2P"] = "1" if mode == 2 else "0"
     if guests:
-        env["PFGPU_GUEST_COLS"] = str(guests)       # few guest columns: the compaction path has to run
+        env["PFGPU_GUEST_COLS"] = str(guests)       # few guest columns: compaction (NCCL form) / eager rebuild (peer-memory form) has to run
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", "29541", os.path.join(ROOT, "tests", "mgpu_worker.py"), str(n), str(side), str(steps)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)

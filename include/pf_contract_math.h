@@ -143,38 +143,104 @@ PFC_HD double pfc_u01_open(uint64_t x) { return ((double)(x >> 11) + 0.5) * 1.11
 PFC_HD double pfc_u01_52(uint64_t x) { return pfc_u2d((x >> 12) | 0x3FF0000000000000ull) - 1.0; }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* Polynomial / reduction constants.  On the device they live in constant memory, so an FP64 instruction takes them as
+ * a constant-bank operand; as literals each one costs two 32-bit moves in front of the FMA that uses it (that was a
+ * quarter of the instructions of the EKF kernel).  Host and device read the same list: same bits either way.        */
+/* ------------------------------------------------------------------------------------------------ */
+#define PFC_CONST_LIST(X) \
+    X(LOG2E, 1.44269504088896338700e+00) \
+    X(LN2_HI, 6.93147180369123816490e-01) \
+    X(LN2_LO, 1.90821492927058770002e-10) \
+    X(E13, 1.6059043836821613e-10) \
+    X(E12, 2.08767569878681e-09) \
+    X(E11, 2.505210838544172e-08) \
+    X(E10, 2.755731922398589e-07) \
+    X(E9, 2.7557319223985893e-06) \
+    X(E8, 2.48015873015873e-05) \
+    X(E7, 1.984126984126984e-04) \
+    X(E6, 1.388888888888889e-03) \
+    X(E5, 8.333333333333333e-03) \
+    X(E4, 4.1666666666666664e-02) \
+    X(E3, 1.6666666666666666e-01) \
+    X(LG1, 6.666666666666735130e-01) \
+    X(LG2, 3.999999999940941908e-01) \
+    X(LG3, 2.857142874366239149e-01) \
+    X(LG4, 2.222219843214978396e-01) \
+    X(LG5, 1.818357216161805012e-01) \
+    X(LG6, 1.531383769920937332e-01) \
+    X(LG7, 1.479819860511658591e-01) \
+    X(S1, -1.66666666666666324348e-01) \
+    X(S2, 8.33333333332248946124e-03) \
+    X(S3, -1.98412698298579493134e-04) \
+    X(S4, 2.75573137070700676789e-06) \
+    X(S5, -2.50507602534068634195e-08) \
+    X(S6, 1.58969099521155010221e-10) \
+    X(C1, 4.16666666666666019037e-02) \
+    X(C2, -1.38888888888741095749e-03) \
+    X(C3, 2.48015872894767294178e-05) \
+    X(C4, -2.75573143513906633035e-07) \
+    X(C5, 2.08757232129817482790e-09) \
+    X(C6, -1.13596475577881948265e-11) \
+    X(TWO_OVER_PI, 6.36619772367581382433e-01) \
+    X(PIO2_1, 1.57079632679489655800e+00) \
+    X(PIO2_2, 6.12323399573676603587e-17) \
+    X(PIO2_3, -1.4973849048591698e-33) \
+    X(AT0, 3.33333333333329318027e-01) \
+    X(AT1, -1.99999999998764832476e-01) \
+    X(AT2, 1.42857142725034663711e-01) \
+    X(AT3, -1.11111104054623557880e-01) \
+    X(AT4, 9.09088713343650656196e-02) \
+    X(AT5, -7.69187620504482999495e-02) \
+    X(AT6, 6.66107313738753120669e-02) \
+    X(AT7, -5.83357013379057348645e-02) \
+    X(AT8, 4.97687799461593236017e-02) \
+    X(AT9, -3.65315727442169155270e-02) \
+    X(AT10, 1.62858201153657823623e-02)
+#define PFC_X_ENUM(n, v) PFC_K_##n,
+enum { PFC_CONST_LIST(PFC_X_ENUM) PFC_K_COUNT };
+#define PFC_X_VAL(n, v) v,
+static const double pfc_k_host[PFC_K_COUNT] = { PFC_CONST_LIST(PFC_X_VAL) };
+#ifdef __CUDACC__
+static __constant__ double pfc_k_dev[PFC_K_COUNT] = { PFC_CONST_LIST(PFC_X_VAL) };
+#endif
+#ifdef __CUDA_ARCH__
+#define PFC_K(n) pfc_k_dev[PFC_K_##n]
+#else
+#define PFC_K(n) pfc_k_host[PFC_K_##n]
+#endif
+
+/* ------------------------------------------------------------------------------------------------ */
 /* exp                                                                                              */
 /* ------------------------------------------------------------------------------------------------ */
 PFC_HD double pfc_exp(double x) {
     if (x != x) return x;
     if (x > 709.782712893384) return pfc_u2d(0x7FF0000000000000ull);
     if (x < -745.2) return 0.0;
-    const double LOG2E  = 1.44269504088896338700e+00;
-    const double LN2_HI = 6.93147180369123816490e-01;
-    const double LN2_LO = 1.90821492927058770002e-10;
+    const double LOG2E  = PFC_K(LOG2E);
+    const double LN2_HI = PFC_K(LN2_HI);
+    const double LN2_LO = PFC_K(LN2_LO);
     double kf = floor(fma(x, LOG2E, 0.5));
     double r  = fma(-kf, LN2_HI, x);
     r = fma(-kf, LN2_LO, r);
     /* q(r) = sum_{j=2..13} r^(j-2)/j!  (Taylor; |r| <= 0.3466 -> truncation < 2^-57) */
-    double q = 1.6059043836821613e-10;            /* 1/13! */
-    q = fma(q, r, 2.08767569878681e-09);          /* 1/12! */
-    q = fma(q, r, 2.505210838544172e-08);         /* 1/11! */
-    q = fma(q, r, 2.755731922398589e-07);         /* 1/10! */
-    q = fma(q, r, 2.7557319223985893e-06);        /* 1/9!  */
-    q = fma(q, r, 2.48015873015873e-05);          /* 1/8!  */
-    q = fma(q, r, 1.984126984126984e-04);         /* 1/7!  */
-    q = fma(q, r, 1.388888888888889e-03);         /* 1/6!  */
-    q = fma(q, r, 8.333333333333333e-03);         /* 1/5!  */
-    q = fma(q, r, 4.1666666666666664e-02);        /* 1/4!  */
-    q = fma(q, r, 1.6666666666666666e-01);        /* 1/3!  */
+    double q = PFC_K(E13);            /* 1/13! */
+    q = fma(q, r, PFC_K(E12));          /* 1/12! */
+    q = fma(q, r, PFC_K(E11));         /* 1/11! */
+    q = fma(q, r, PFC_K(E10));         /* 1/10! */
+    q = fma(q, r, PFC_K(E9));        /* 1/9!  */
+    q = fma(q, r, PFC_K(E8));          /* 1/8!  */
+    q = fma(q, r, PFC_K(E7));         /* 1/7!  */
+    q = fma(q, r, PFC_K(E6));         /* 1/6!  */
+    q = fma(q, r, PFC_K(E5));         /* 1/5!  */
+    q = fma(q, r, PFC_K(E4));        /* 1/4!  */
+    q = fma(q, r, PFC_K(E3));        /* 1/3!  */
     q = fma(q, r, 0.5);                           /* 1/2!  */
     double t = fma(r * r, q, r);
     double y = 1.0 + t;
-    int k = (int)kf;
-    if (k >= -1021 && k <= 1023) return y * pfc_pow2i(k);
-    if (k > 1023) return (y * pfc_pow2i(k - 1)) * 2.0;
-    /* subnormal result: one exact scaling, then a single correctly rounded multiply */
-    return (y * pfc_pow2i(k + 64)) * 5.421010862427522e-20;   /* 2^-64 */
+    /* y * 2^k in two steps, k = k1 + k2 with both halves in pow2i's range: the first product is exact (normal), the
+     * second rounds once — also when the result is subnormal or overflows — so no case split is needed */
+    const int k = (int)kf, k1 = k >> 1, k2 = k - k1;
+    return (y * pfc_pow2i(k1)) * pfc_pow2i(k2);
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -191,11 +257,11 @@ PFC_HD double pfc_log(double x) {
     uint64_t mant = ux & 0x000FFFFFFFFFFFFFull;
     double m = pfc_u2d(mant | 0x3FF0000000000000ull);          /* [1,2) */
     if (m > 1.4142135623730951) { m *= 0.5; k += 1; }           /* -> [sqrt2/2, sqrt2) */
-    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
-    const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01,
-                 Lg3 = 2.857142874366239149e-01, Lg4 = 2.222219843214978396e-01,
-                 Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
-                 Lg7 = 1.479819860511658591e-01;
+    const double LN2_HI = PFC_K(LN2_HI), LN2_LO = PFC_K(LN2_LO);
+    const double Lg1 = PFC_K(LG1), Lg2 = PFC_K(LG2),
+                 Lg3 = PFC_K(LG3), Lg4 = PFC_K(LG4),
+                 Lg5 = PFC_K(LG5), Lg6 = PFC_K(LG6),
+                 Lg7 = PFC_K(LG7);
     double f = m - 1.0;
     double s = PFC_DIV(f, 2.0 + f);
     double z = s * s, w = z * z;
@@ -211,17 +277,17 @@ PFC_HD double pfc_log(double x) {
 /* sin / cos                                                                                        */
 /* ------------------------------------------------------------------------------------------------ */
 PFC_HD double pfc_sin_kernel(double r) {
-    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
-                 S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
-                 S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+    const double S1 = PFC_K(S1), S2 = PFC_K(S2),
+                 S3 = PFC_K(S3), S4 = PFC_K(S4),
+                 S5 = PFC_K(S5), S6 = PFC_K(S6);
     double z = r * r;
     double p = fma(z, fma(z, fma(z, fma(z, fma(z, S6, S5), S4), S3), S2), S1);
     return fma(r * z, p, r);
 }
 PFC_HD double pfc_cos_kernel(double r) {
-    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
-                 C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
-                 C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    const double C1 = PFC_K(C1), C2 = PFC_K(C2),
+                 C3 = PFC_K(C3), C4 = PFC_K(C4),
+                 C5 = PFC_K(C5), C6 = PFC_K(C6);
     double z = r * r;
     double p = fma(z, fma(z, fma(z, fma(z, fma(z, C6, C5), C4), C3), C2), C1);
     double hz = 0.5 * z;
@@ -232,10 +298,10 @@ PFC_HD double pfc_cos_kernel(double r) {
  * with gracefully degrading accuracy; host and device still agree bit for bit. */
 PFC_HD void pfc_sincos(double x, double* s, double* c) {
     if (!(fabs(x) <= 1.7976931348623157e308)) { *s = *c = pfc_u2d(0x7FF8000000000000ull); return; }
-    const double TWO_OVER_PI = 6.36619772367581382433e-01;
-    const double P1 = 1.57079632679489655800e+00;      /* fl(pi/2)            */
-    const double P2 = 6.12323399573676603587e-17;      /* fl(pi/2 - P1)       */
-    const double P3 = -1.4973849048591698e-33;         /* fl(pi/2 - P1 - P2)  */
+    const double TWO_OVER_PI = PFC_K(TWO_OVER_PI);
+    const double P1 = PFC_K(PIO2_1);      /* fl(pi/2)            */
+    const double P2 = PFC_K(PIO2_2);      /* fl(pi/2 - P1)       */
+    const double P3 = PFC_K(PIO2_3);         /* fl(pi/2 - P1 - P2)  */
     double fn = floor(fma(x, TWO_OVER_PI, 0.5));
     double r = fma(-fn, P1, x);
     r = fma(-fn, P2, r);
@@ -258,41 +324,32 @@ PFC_HD double pfc_cos(double x) { double s, c; pfc_sincos(x, &s, &c); return c; 
 /* ------------------------------------------------------------------------------------------------ */
 PFC_HD double pfc_atan(double x) {
     if (x != x) return x;
-    const double aT0 = 3.33333333333329318027e-01, aT1 = -1.99999999998764832476e-01,
-                 aT2 = 1.42857142725034663711e-01, aT3 = -1.11111104054623557880e-01,
-                 aT4 = 9.09088713343650656196e-02, aT5 = -7.69187620504482999495e-02,
-                 aT6 = 6.66107313738753120669e-02, aT7 = -5.83357013379057348645e-02,
-                 aT8 = 4.97687799461593236017e-02, aT9 = -3.65315727442169155270e-02,
-                 aT10 = 1.62858201153657823623e-02;
+    const double aT0 = PFC_K(AT0), aT1 = PFC_K(AT1),
+                 aT2 = PFC_K(AT2), aT3 = PFC_K(AT3),
+                 aT4 = PFC_K(AT4), aT5 = PFC_K(AT5),
+                 aT6 = PFC_K(AT6), aT7 = PFC_K(AT7),
+                 aT8 = PFC_K(AT8), aT9 = PFC_K(AT9),
+                 aT10 = PFC_K(AT10);
     double ax = fabs(x);
-    double hi = 0.0, lo = 0.0, t;
-    int reduced = 1;
     if (ax >= 7.378697629483821e19) {                 /* 2^66 */
         double r = 1.57079632679489655800e+00 + 6.12323399573676603587e-17;
         return x < 0.0 ? -r : r;
     }
-    if (ax < 0.4375) {
-        if (ax < 7.450580596923828e-09) return x;     /* 2^-27 */
-        reduced = 0; t = ax;
-    } else if (ax < 0.6875) {
-        hi = 4.63647609000806093515e-01; lo = 2.26987774529616870924e-17;
-        t = PFC_DIV(2.0 * ax - 1.0, 2.0 + ax);
-    } else if (ax < 1.1875) {
-        hi = 7.85398163397448278999e-01; lo = 3.06161699786838301793e-17;
-        t = PFC_DIV(ax - 1.0, ax + 1.0);
-    } else if (ax < 2.4375) {
-        hi = 9.82793723247329054082e-01; lo = 1.39033110312309984516e-17;
-        t = PFC_DIV(ax - 1.5, 1.0 + 1.5 * ax);
-    } else {
-        hi = 1.57079632679489655800e+00; lo = 6.12323399573676603587e-17;
-        t = PFC_DIV(-1.0, ax);
-    }
+    if (ax < 7.450580596923828e-09) return x;         /* 2^-27 */
+    /* argument reduction atan(x) = hi + lo + atan(num/den), interval picked by selects: ONE division site and no
+     * divergent region.  The first interval uses num/den = ax/1 (exact) and hi = lo = 0, for which the general
+     * recombination below reduces, bit for bit, to t - t*(s1+s2). */
+    const int i1 = ax >= 0.4375, i2 = ax >= 0.6875, i3 = ax >= 1.1875, i4 = ax >= 2.4375;
+    double num = ax, den = 1.0, hi = 0.0, lo = 0.0;
+    if (i1) { num = 2.0 * ax - 1.0; den = 2.0 + ax;       hi = 4.63647609000806093515e-01; lo = 2.26987774529616870924e-17; }
+    if (i2) { num = ax - 1.0;       den = ax + 1.0;       hi = 7.85398163397448278999e-01; lo = 3.06161699786838301793e-17; }
+    if (i3) { num = ax - 1.5;       den = 1.0 + 1.5 * ax; hi = 9.82793723247329054082e-01; lo = 1.39033110312309984516e-17; }
+    if (i4) { num = -1.0;           den = ax;             hi = 1.57079632679489655800e+00; lo = 6.12323399573676603587e-17; }
+    const double t = PFC_DIV(num, den);
     double z = t * t, w = z * z;
     double s1 = z * fma(w, fma(w, fma(w, fma(w, fma(w, aT10, aT8), aT6), aT4), aT2), aT0);
     double s2 = w * fma(w, fma(w, fma(w, fma(w, aT9, aT7), aT5), aT3), aT1);
-    double r;
-    if (!reduced) r = t - t * (s1 + s2);
-    else          r = hi - ((t * (s1 + s2) - lo) - t);
+    double r = hi - ((t * (s1 + s2) - lo) - t);
     return x < 0.0 ? -r : r;
 }
 

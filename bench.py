@@ -19,6 +19,9 @@ import sys
 import tempfile
 import time
 
+# stdout carries exactly one JSON line: whatever NCCL wants to say (its version banner when NCCL_DEBUG is set) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -168,6 +171,21 @@ def run_reference(args, rank):
                                        f"{N_PARTICLES} particles x {sc.m} landmarks, {res} resamples in {args.steps} steps"},
             "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def load_traffic():
+    """DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture (profiles/*_traffic.json,
+    newest round last); null when no capture is committed."""
+    import glob
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "*_traffic.json")))
+    if not files:
+        return {"traffic": None}
+    try:
+        with open(files[-1]) as f:
+            t = json.load(f)
+        return {"traffic": t["dram_bytes_read"] + t["dram_bytes_write"], "traffic_source": f"{os.path.basename(files[-1])}: {t['kernel']}"}
+    except Exception:
+        return {"traffic": None}
 
 
 def workload_config(sc, n_gpus):
@@ -321,7 +339,7 @@ def run_ours(args, rank, world, local_rank):
                         "d2h_bytes_per_step": d2h / K},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "fs_predict_kernel + fs_ekf_kernel (predict + per-observation EKF, fs1.rs:245-256)", "achieved": achieved,
-                             "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, **load_traffic(),
                              "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": kernel_ms},
                 "clocks": clocks, "serial_fallbacks": int(st1.serial_fallbacks)}
         if cpu:

@@ -40,6 +40,7 @@ struct FxSharedT {
     double sm_d[XS_NT / 32];
     int sm_i[XS_NT / 32];
     XsSeg sm_s[XS_NT / 32];
+    int sm_j[XS_NT / 32];
     XsSeg carry_seg;
     int carry_nd;
     int ndl;                           // number of tiles holding dirty values
@@ -177,17 +178,19 @@ __device__ __noinline__ void fx_chain(const FxSlot& s, unsigned nt, F f, size_t 
     unsigned long long tp = 0;
     if (dbg) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tp));
     __syncthreads();
-    // ---- tile-level segmented scan: all threads fetch the aggregates (coalesced), ONE warp scans them from shared memory
-    // (nt <= FX_MAX_TILES = 16 tiles per lane), no block-wide scan primitives on this path
+    // ---- tile-level segmented scan over all nt tiles, by the whole CTA: thread t owns `per` consecutive tiles (one for
+    // nt <= 256), warps scan by shuffles, the 8 warp totals are combined by every thread.  (One warp doing all of it took
+    // 5 us per chain at 128 tiles and grew with the tile count, i.e. with the number of GPUs.)
     for (unsigned b = tid; b < nt; b += XS_NT) { sh.tnd[b] = s.tnd[b]; sh.tin[b] = s.ttail[b]; }
     if (tid == 0) { sh.s_run = 0.0; sh.ok = 1; sh.serial = pub.is_bad(flags); }
     __syncthreads();
-    if (tid < 32) {
-        const unsigned per = (nt + 31) / 32;
-        const unsigned b0 = tid * per, b1 = (b0 + per < nt) ? b0 + per : nt;
+    {
+        const int lane = tid & 31, wid = tid >> 5;
+        const unsigned per = (nt + XS_NT - 1) / XS_NT;
+        const unsigned b0 = (unsigned)tid * per < nt ? (unsigned)tid * per : nt, b1 = (b0 + per < nt) ? b0 + per : nt;
         XsSeg run = xs_seg_make(xs_identity(), 0);
-        int ndrun = 0, ntl = 0;                                // dirty values / dirty tiles in my lane's tiles
-        for (unsigned b = b0; b < b1; ++b) {                   // pass 1: lane totals
+        int ndrun = 0, ntl = 0;                                // dirty values / dirty tiles in my tiles
+        for (unsigned b = b0; b < b1; ++b) {                   // pass 1: my total
             int nd = sh.tnd[b]; int nde = nd < 0 ? 1 : nd;
             run = xs_seg_op(run, xs_seg_make(sh.tin[b], nde > 0));
             ndrun += nde; ntl += nde > 0 ? 1 : 0;
@@ -197,11 +200,19 @@ __device__ __noinline__ void fx_chain(const FxSlot& s, unsigned nt, F f, size_t 
         for (int o = 1; o < 32; o <<= 1) {
             XsSeg y = xs_seg_shfl_up(inc, o);
             int yn = __shfl_up_sync(0xffffffffu, ndinc, o), yt = __shfl_up_sync(0xffffffffu, ntinc, o);
-            if (tid >= o) { inc = xs_seg_op(y, inc); ndinc += yn; ntinc += yt; }
+            if (lane >= o) { inc = xs_seg_op(y, inc); ndinc += yn; ntinc += yt; }
         }
         XsSeg ex = xs_seg_shfl_up(inc, 1);
         int ndex = __shfl_up_sync(0xffffffffu, ndinc, 1), ntex = __shfl_up_sync(0xffffffffu, ntinc, 1);
-        if (tid == 0) { ex = xs_seg_make(xs_identity(), 0); ndex = 0; ntex = 0; }
+        if (lane == 0) { ex = xs_seg_make(xs_identity(), 0); ndex = 0; ntex = 0; }
+        if (lane == 31) { sh.sm_s[wid] = inc; sh.sm_i[wid] = ndinc; sh.sm_j[wid] = ntinc; }
+        __syncthreads();
+        XsSeg wex = xs_seg_make(xs_identity(), 0);
+        int wnd = 0, wnt = 0;
+        for (int w = 0; w < wid; ++w) { wex = xs_seg_op(wex, sh.sm_s[w]); wnd += sh.sm_i[w]; wnt += sh.sm_j[w]; }
+        ex = xs_seg_op(wex, ex); ndex += wnd; ntex += wnt;
+        if (tid == XS_NT - 1) { sh.carry_seg = xs_seg_op(wex, inc); sh.carry_nd = wnd + ndinc; sh.ndl = wnt + ntinc; }
+        __syncthreads();                                       // pass 2 overwrites sh.tin: every pass 1 is done
         for (unsigned b = b0; b < b1; ++b) {                   // pass 2: exclusive prefixes per tile + compact dirty-tile list
             int nd = sh.tnd[b]; int nde = nd < 0 ? 1 : nd;
             xs_t tl = sh.tin[b];
@@ -210,7 +221,6 @@ __device__ __noinline__ void fx_chain(const FxSlot& s, unsigned nt, F f, size_t 
             ex = xs_seg_op(ex, xs_seg_make(tl, nde > 0));
             ndex += nde;
         }
-        if (tid == 31) { sh.carry_seg = inc; sh.carry_nd = ndinc; sh.ndl = ntinc; }
     }
     __syncthreads();
     const int D = sh.carry_nd;

@@ -47,10 +47,47 @@ def run_pf(kind, rank, world, local, n_global, steps, uid):
         print(f"MGPU_OK kind={kind} world={world} n={n_global} resamples={resamples}")
 
 
+def run_edge(rank, world, local, uid):
+    """The single-GPU edge cases of tests/test_gpu_parity.py::test_fastslam_edge_cases, sharded."""
+    n, m = 1024 * world, 4
+    lm_xy = np.array([[5.0, 0.0], [0.0, 5.0], [5.0, 5.0], [-5.0, 2.0]])
+    g = rr.FastSlam1(n, m, rr.FsConfig(nth=n / 1.5), seed=11, device=local, shard=(uid, rank, world))
+    L = _oracle.load(libm=False)
+    o = _oracle.OracleFS(L, n, m, seed=11, nth=n / 1.5)
+    g.seed_map([0.0, 0.0, 0.0], lm_xy); o.seed_map([0.0, 0.0, 0.0], lm_xy)
+    lo, hi = rdist.shard_bounds(n, rank, world)
+
+    def same(tag):
+        gp, gl = g.state(); op, ol = o.state()
+        assert np.array_equal(gp, op[lo:hi]), f"rank {rank} {tag}: pose/weights differ"
+        assert np.array_equal(gl, ol[lo:hi]), f"rank {rank} {tag}: landmarks differ"
+
+    z = [(5.1, 0.02, 0), (5.0, 1.55, 1), (4.9, -0.01, 0)]          # duplicate lm_id
+    assert g.fastslam_update([1.0, 0.1], z) == bool(o.step([1.0, 0.1], z)); same("duplicate ids")
+    assert g.fastslam_update([1.0, 0.1], []) == bool(o.step([1.0, 0.1], [])); same("empty obs")
+    p, l = g.state(); p[:, 0] = 0.0; g.set_state(p, l)              # all-zero weights: every slot clones particle n-1
+    op, ol = o.state(); op[:, 0] = 0.0; o.set_state(op, ol)
+    assert g.fastslam_update([1.0, 0.1], z[:2]) is True and o.step([1.0, 0.1], z[:2]) == 1
+    assert np.all(g.last_indices() == n - 1); same("zero weights")
+    p, l = g.state(); l[:, 2, :] = [0.0, 0.0, 1000.0, 0.0, 0.0, 1000.0]; g.set_state(p, l)      # fresh + initialised landmarks
+    op, ol = o.state(); ol[:, 2, :] = [0.0, 0.0, 1000.0, 0.0, 0.0, 1000.0]; o.set_state(op, ol)
+    z2 = [(7.0, 0.8, 2), (5.0, 0.1, 0)]
+    for _ in range(6):
+        assert g.fastslam_update([1.0, 0.0], z2) == bool(o.step([1.0, 0.0], z2))
+    same("mixed fresh")
+    dist.barrier()
+    if rank == 0:
+        print(f"MGPU_OK edge world={world} mode={g.shard_mode()}")
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     dist.init_process_group("gloo", init_method="env://")
     uid = rdist.broadcast_unique_id(dist, rdist.nccl_unique_id, rank)
+    if sys.argv[1] == "edge":
+        run_edge(rank, world, local, uid)
+        dist.destroy_process_group()
+        return
     if sys.argv[1] in ("pf", "mcl"):
         run_pf(sys.argv[1], rank, world, local, int(sys.argv[2]), int(sys.argv[3]), uid)
         dist.destroy_process_group()

@@ -38,6 +38,19 @@ def test_sharded_fastslam_matches_oracle(world, n, side, steps, mode, guests):
         assert "compactions=0 " not in r.stdout, r.stdout[-2000:]
 
 
+@pytest.mark.parametrize("mode", [2, 1])
+def test_sharded_fastslam_edge_cases(mode):
+    """duplicate landmark ids, empty list, all-zero weights (every slot imports the last particle of the last rank), fresh landmarks"""
+    if n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ)
+    env["PFGPU_SHARD_P2P"] = "1" if mode == 2 else "0"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29543", os.path.join(ROOT, "tests", "mgpu_worker.py"), "edge"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "MGPU_OK edge" in r.stdout and f"mode={mode}" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 @pytest.mark.parametrize("kind,n,steps", [("pf", 1 << 14, 40), ("mcl", 1 << 15, 8)])
 def test_sharded_pf_matches_oracle(kind, n, steps):
     if n_gpus() < 2:

@@ -5,6 +5,7 @@
 #include "pf_kernels.cuh"
 #include "fs_kernels.cuh"
 #include "fs_post.cuh"
+#include "pf_kld.cuh"
 #include "fs_sharded.cuh"
 #include "fs_mg.cuh"
 #include <cstdlib>
@@ -125,6 +126,8 @@ struct pfgpu_pf {
     double* h_pin = nullptr;   // pinned scratch (>= 64 doubles)
     FsShard sh;                // multi-GPU state (world == 1: unused)
     int cur_host = 0;          // sharded mode: host mirror of *d.cur (the host knows every gate there)
+    bool adaptive = false;     // MCL with min_particles < max_particles: the particle count changes per step (pf_kld.cuh)
+    PfKld kld;
 };
 
 extern "C" void pfgpu_pf_default_config(pfgpu_pf_config* c, int mode) {
@@ -205,9 +208,9 @@ static int pf_refresh_cache(pfgpu_pf* h) {      // refresh_cache pf.rs:499-503
     return 0;
 }
 
-static int pf_alloc(pfgpu_pf* h) {
+static int pf_alloc(pfgpu_pf* h, size_t cap) {
     PfDev& d = h->d;
-    const size_t n = d.n;
+    const size_t n = cap;       // every per-particle array is sized for the largest generation
     PF_CUDA(cudaMalloc(&d.pose[0], n * sizeof(Pose4)));
     PF_CUDA(cudaMalloc(&d.pose[1], n * sizeof(Pose4)));
     PF_CUDA(cudaMalloc(&d.cur, sizeof(int)));
@@ -229,6 +232,18 @@ static int pf_alloc(pfgpu_pf* h) {
     h->obs_cap = 1024;
     PF_CUDA(cudaMalloc(&d.obs, h->obs_cap * 3 * sizeof(double)));
     PF_CUDA(cudaMallocHost(&h->h_pin, 64 * sizeof(double)));
+    if (h->adaptive) {
+        PfKld& k = h->kld;
+        k.cap = cap;
+        unsigned tc = 64;
+        while ((size_t)tc < 2 * cap + 16) tc <<= 1;
+        k.tcap = tc;
+        PF_CUDA(cudaMalloc(&k.keys, 3 * cap * sizeof(int)));
+        PF_CUDA(cudaMalloc(&k.owner, (size_t)tc * sizeof(int)));
+        PF_CUDA(cudaMalloc(&k.mint, (size_t)tc * sizeof(unsigned)));
+        PF_CUDA(cudaMalloc(&k.slot, cap * sizeof(int)));
+        PF_CUDA(cudaMalloc(&k.n_new, sizeof(unsigned)));
+    }
     return xs_work_alloc(h->xs, n);
 }
 
@@ -237,8 +252,9 @@ static int pf_create_impl(const pfgpu_pf_config* cfg, uint64_t seed, int device,
     *out = nullptr;
     int rc = pfgpu_pf_config_validate(cfg);
     if (rc) return rc;
-    if (cfg->mode == 1 && cfg->max_particles != cfg->n_particles) return PFGPU_ERR_UNSUPPORTED;   // KLD-adaptive N: SURVEY.md §8(f) row 3
-    if (cfg->n_particles > 0xFFFFFFFFull) return PFGPU_ERR_UNSUPPORTED;
+    const bool adaptive = cfg->mode == 1 && cfg->max_particles != cfg->n_particles;     // KLD-adaptive particle count, mcl.rs:322-365
+    if (adaptive && world > 1) return PFGPU_ERR_UNSUPPORTED;                            // a changing count is not sharded (yet)
+    if (cfg->n_particles > 0xFFFFFFFFull || (adaptive && cfg->max_particles > 0x7FFFFFFFull)) return PFGPU_ERR_UNSUPPORTED;
     if (world > 1 && (cfg->n_particles % (uint64_t)world) != 0) return PFGPU_ERR_INVALID;
     pfgpu_pf* h = new (std::nothrow) pfgpu_pf();
     if (!h) return PFGPU_ERR_CUDA;
@@ -246,7 +262,8 @@ static int pf_create_impl(const pfgpu_pf_config* cfg, uint64_t seed, int device,
     if (rc) { delete h; return rc; }
     h->cfg = *cfg; h->seed = seed; h->world = world; h->rank = rank;
     h->d.n_global = cfg->n_particles; h->d.n = cfg->n_particles / (uint64_t)world; h->d.offset = (size_t)rank * h->d.n;
-    rc = pf_alloc(h);
+    h->adaptive = adaptive;
+    rc = pf_alloc(h, adaptive ? (size_t)cfg->max_particles : h->d.n);
     if (rc) { pfgpu_pf_destroy(h); return rc; }
     if (world > 1) {
         FsShard& sh = h->sh;
@@ -286,6 +303,7 @@ extern "C" void pfgpu_pf_destroy(pfgpu_pf* h) {
     cudaFree(d.pose[0]); cudaFree(d.pose[1]); cudaFree(d.cur); cudaFree(d.w_raw); cudaFree(d.w); cudaFree(d.cum);
     cudaFree(d.idx); cudaFree(d.scal); cudaFree(d.gate); cudaFree(d.partial); cudaFree(d.obs); cudaFree(h->mom15); cudaFree(d.counters);
     if (h->h_pin) cudaFreeHost(h->h_pin);
+    cudaFree(h->kld.keys); cudaFree(h->kld.owner); cudaFree(h->kld.mint); cudaFree(h->kld.slot); cudaFree(h->kld.n_new);
     {
         FsShard& sh = h->sh;
         cudaFree(sh.t_loc); cudaFree(sh.t_all); cudaFree(sh.approx_off); cudaFree(sh.sum_loc); cudaFree(sh.sum_all); cudaFree(sh.s_start);
@@ -436,9 +454,31 @@ static int pf_normalize(pfgpu_pf* h) {
     PF_LAUNCH(h->ctx, pf_normalize_kernel, cdiv_u(h->d.n, PF_NT), PF_NT, 0, h->d);
     return 0;
 }
+// resample_adaptive with a changing particle count (mcl.rs:322-365), see pf_kld.cuh
+static int pf_resample_adaptive(pfgpu_pf* h) {
+    PfDev& d = h->d; PfKld& k = h->kld; Ctx& ctx = h->ctx;
+    PF_LAUNCH(ctx, pf_gate_kernel, 1, 1, 0, d, h->cfg.resample_threshold, h->cfg.mode);           // MCL resamples every step (mcl.rs:298)
+    int rc = xs_scan(ctx, h->xs, XsValArray{d.w}, XsSinkStore{d.cum}, d.n, d.n_global, 0.0, d.scal + 2);   // mcl.rs:328-333
+    if (rc) return rc;
+    PF_LAUNCH(ctx, pf_force_last_kernel, 1, 1, 0, d);                                             // mcl.rs:334-336
+    PF_CUDA(cudaMemsetAsync(k.owner, 0xFF, (size_t)k.tcap * sizeof(int), ctx.stream));
+    PF_CUDA(cudaMemsetAsync(k.mint, 0xFF, (size_t)k.tcap * sizeof(unsigned), ctx.stream));
+    PF_LAUNCH(ctx, pf_kld_draw_kernel, cdiv_u(k.cap, PF_NT), PF_NT, 0, d, h->seed, k);
+    PF_LAUNCH(ctx, pf_kld_insert_kernel, cdiv_u(k.cap, PF_NT), PF_NT, 0, k);
+    PF_LAUNCH(ctx, pf_kld_stop_kernel, 1, 1024, 0, k, (unsigned long long)h->cfg.n_particles, (unsigned long long)h->cfg.max_particles,
+              h->cfg.kld_epsilon, h->cfg.kld_z);
+    PF_LAUNCH(ctx, pf_kld_gather_kernel, cdiv_u(k.cap, PF_NT), PF_NT, 0, d, k);
+    PF_LAUNCH(ctx, pf_flip_kernel, 1, 1, 0, d);
+    unsigned* hp = reinterpret_cast<unsigned*>(h->h_pin + 34);
+    PF_CUDA(cudaMemcpyAsync(hp, k.n_new, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx.stream));
+    PF_CUDA(cudaStreamSynchronize(ctx.stream));                    // the next launches are sized by the new count
+    d.n = d.n_global = (size_t)*hp;
+    return 0;
+}
 static int pf_resample_impl(pfgpu_pf* h) {
     PfDev& d = h->d;
     if (h->world > 1) return pf_resample_sharded(h);
+    if (h->adaptive) return pf_resample_adaptive(h);
     int rc = xs_total(h->ctx, h->xs, PfValWSq{d.w}, d.n, d.n_global, 0.0, d.scal + 1);        // calc_n_eff pf.rs:416-423
     if (rc) return rc;
     PF_LAUNCH(h->ctx, pf_gate_kernel, 1, 1, 0, d, h->cfg.resample_threshold, h->cfg.mode);

@@ -208,9 +208,29 @@ def test_mcl_converges_like_reference_test():
     assert np.hypot(est[0] - x[0], est[1] - x[1]) < 1.0
 
 
-def test_mcl_adaptive_is_reported_unsupported():
-    with pytest.raises(rr.InvalidParameter):
-        rr.MonteCarloLocalizer(rr.MonteCarloLocalizationConfig(100, 5000))
+@pytest.mark.parametrize("nmin,nmax,k,eps", [(100, 5000, 4, 0.05), (50, 400, 8, 0.05), (1000, 200000, 4, 0.0005), (64, 64 + 1, 4, 0.05)])
+def test_mcl_kld_adaptive_bit_exact(oracle, nmin, nmax, k, eps):
+    """resample_adaptive with min < max (mcl.rs:322-365; 100 / 5000 is the reference's default config): the particle count
+    follows the KLD bound; count, ancestry and particles equal the oracle's at every step."""
+    init = (0.0, 0.0, 0.0, 1.0)
+    g = rr.MonteCarloLocalizer.try_with_initial_state(
+        init, rr.MonteCarloLocalizationConfig(nmin, nmax, eps, 2.326, 0.25, 0.05, 0.02, 0.1), seed=3)
+    o = OraclePF(oracle, nmin, range_noise=0.25, velocity_noise=0.05, yaw_rate_noise=0.02, dt=0.1, seed=3, mode=1, max_particles=nmax,
+                 kld_epsilon=eps)
+    o.L.orc_pf_set_fast_search(o.h, 1)
+    o.init_state(init)
+    sc = scenarios.PfScenario("c2", steps=25)
+    counts = []
+    for t in range(25):
+        obs = sc.obs[t][:: 360 // k][:k]
+        ge = g.try_step(sc.controls[t], obs)
+        oe, _ = o.step(sc.controls[t], obs)
+        assert g.particle_count() == o.count(), f"step {t}: count {g.particle_count()} vs oracle {o.count()} (history {counts})"
+        assert np.array_equal(g.last_indices(), o.last_indices()), f"step {t}"
+        np.testing.assert_allclose(ge, oe, rtol=RTOL, atol=1e-9)
+        counts.append(o.count())
+    _pf_compare(g, o, "kld end")
+    assert min(counts) >= nmin and max(counts) <= nmax and (len(set(counts)) > 1 or nmax == nmin + 1), counts
 
 
 # ------------------------------------------------------------------------------------------------

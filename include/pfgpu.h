@@ -30,7 +30,7 @@ extern "C" {
 
 #define PFGPU_OK                 0
 #define PFGPU_ERR_INVALID      (-1)   /* RoboticsError::InvalidParameter                       */
-#define PFGPU_ERR_UNSUPPORTED  (-2)   /* valid in the reference, not yet built here (documented) */
+#define PFGPU_ERR_UNSUPPORTED  (-2)   /* valid in the reference, not built here: KLD-adaptive MCL on more than one GPU */
 #define PFGPU_ERR_NO_DEVICE     1000  /* no CUDA device / extension cannot run: fail loudly      */
 #define PFGPU_ERR_CUDA          1001
 #define PFGPU_ERR_NCCL          1002
@@ -109,6 +109,11 @@ void pfgpu_fs_default_config(pfgpu_fs_config* cfg);
 /* create_particles(n, m) fs1.rs:302-306 */
 int  pfgpu_fs_create(const pfgpu_fs_config* cfg, size_t n_particles, size_t n_landmarks, uint64_t seed,
                      int device, pfgpu_fs** out);
+/* Sharded over `world` GPUs of one NVLink domain, one process per GPU; collective over all ranks (same arguments
+ * everywhere).  The step then runs over peer memory: kernels push / pull through NVLink and synchronise with cross-GPU
+ * barriers, there is no NCCL call and no host synchronisation per step, so every rank must issue the same sequence of
+ * pfgpu_fs_step calls; a rank that stops surfaces as PFGPU_ERR_CUDA at the others' next pfgpu_fs_sync (no hang).
+ * Falls back to NCCL collectives when peer mapping is unavailable or the shard size is not a multiple of 512. */
 int  pfgpu_fs_create_sharded(const pfgpu_fs_config* cfg, size_t n_particles_global, size_t n_landmarks,
                              uint64_t seed, int device, const void* nccl_unique_id, int rank, int world,
                              pfgpu_fs** out);

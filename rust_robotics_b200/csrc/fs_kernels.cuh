@@ -389,32 +389,7 @@ __global__ void __launch_bounds__(256) fs_compose_anc_kernel(FsDev d) {
 template <class AncT> struct AncVec4;
 template <> struct AncVec4<unsigned short> { typedef ushort4 type; };
 template <> struct AncVec4<uint32_t> { typedef uint4 type; };
-template <class AncT>
-__global__ void __launch_bounds__(256) fs_compose_anc_vec_kernel(FsDev d) {
-    if (!*d.gate) return;
-    typedef typename AncVec4<AncT>::type V;
-    const size_t q = (size_t)blockIdx.x * 256 + threadIdx.x;           // quad of slots
-    const size_t t = q * 4;
-    if (t >= d.n) return;
-    const int ac = *d.anc_cur;
-    const AncT* __restrict__ src = reinterpret_cast<const AncT*>(fs_anc(d, ac));
-    AncT* __restrict__ dst = reinterpret_cast<AncT*>(fs_anc(d, ac ^ 1));
-    const uint4 jj = *reinterpret_cast<const uint4*>(d.idx + t);
-    const size_t l0 = (size_t)blockIdx.y * FS_COMPOSE_ROWS;
-#pragma unroll
-    for (int rr = 0; rr < FS_COMPOSE_ROWS; ++rr) {
-        const size_t l = l0 + rr;
-        if (l >= d.m) break;
-        V o;
-        if (d.lmstate[l] & 2) { o.x = (AncT)jj.x; o.y = (AncT)jj.y; o.z = (AncT)jj.z; o.w = (AncT)jj.w; }
-        else {
-            const AncT* __restrict__ row = src + l * d.n;
-            o.x = row[jj.x]; o.y = row[jj.y]; o.z = row[jj.z]; o.w = row[jj.w];
-        }
-        *reinterpret_cast<V*>(dst + l * d.n + t) = o;
-    }
-}
-// the same with the ping-pong flip (fs_flip_kernel) done by the last CTA to finish: one launch fewer per step
+// ... and the ping-pong flip (fs_flip_kernel) is done by the last CTA to finish: one launch fewer per step
 template <class AncT>
 __global__ void __launch_bounds__(256) fs_compose_flip_kernel(FsDev d) {
     if (!*d.gate) return;
@@ -447,35 +422,6 @@ __global__ void __launch_bounds__(256) fs_compose_flip_kernel(FsDev d) {
     if (!s_last) return;                                           // every other CTA has read lmstate / anc_cur by now
     for (size_t l = threadIdx.x; l < d.m; l += blockDim.x) d.lmstate[l] &= 1;
     if (threadIdx.x == 0) { *d.cur ^= 1; *d.anc_cur ^= 1; d.counters[0] += 1; d.counters[2] = 0; }
-}
-//   each landmark's ancestry column with this resample's ancestry (see fs_compose_anc_kernel).  A CTA = 256 slots, all m
-//   landmarks (coalesced 2 or 4 B per particle and landmark in each direction).
-template <class AncT>
-__global__ void __launch_bounds__(256) fs_resample_apply_kernel(FsDev d) {
-    if (!*d.gate) return;
-    const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (t >= d.n) return;
-    const double r = d.rcomb[t];
-    const double* __restrict__ c = d.cum;
-    size_t lo = 0, hi = d.n;
-    while (lo < hi) {
-        size_t mid = lo + ((hi - lo) >> 1);
-        if (c[mid] < r) lo = mid + 1; else hi = mid;
-    }
-    const size_t j = lo < d.n ? lo : d.n - 1;
-    d.idx[t] = (uint32_t)j;
-    const int cur = *d.cur;
-    fs_px(d, cur ^ 1)[t] = fs_px(d, cur)[j];
-    fs_py(d, cur ^ 1)[t] = fs_py(d, cur)[j];
-    fs_pyaw(d, cur ^ 1)[t] = fs_pyaw(d, cur)[j];
-    d.w[t] = 1.0 / (double)d.n_global;                      // fs1.rs:228
-    const int ac = *d.anc_cur;
-    const AncT* __restrict__ src = reinterpret_cast<const AncT*>(fs_anc(d, ac));
-    AncT* __restrict__ dst = reinterpret_cast<AncT*>(fs_anc(d, ac ^ 1));
-    const size_t n = d.n;
-#pragma unroll 4
-    for (size_t l = 0; l < d.m; ++l)
-        dst[l * n + t] = (d.lmstate[l] & 2) ? (AncT)j : src[l * n + j];
 }
 __global__ void fs_flip_kernel(FsDev d) {
     if (!*d.gate) return;

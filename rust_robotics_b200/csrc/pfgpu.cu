@@ -1281,16 +1281,10 @@ extern "C" int pfgpu_fs_step(pfgpu_fs* h, const double u[2], const pfgpu_fs_obs*
             }
             return 0;
         }
-        if (d.m) {
-            if (d.n % 4 == 0 && h->compose_vec) {
-                dim3 grid(cdiv_u(d.n / 4, 256), cdiv_u(d.m, FS_COMPOSE_ROWS));
-                if (d.anc16) PF_LAUNCH(h->ctx, fs_compose_anc_vec_kernel<unsigned short>, grid, 256, 0, d);
-                else         PF_LAUNCH(h->ctx, fs_compose_anc_vec_kernel<uint32_t>, grid, 256, 0, d);
-            } else {
-                dim3 grid(cdiv_u(d.n, 256), cdiv_u(d.m, FS_COMPOSE_ROWS));
-                if (d.anc16) PF_LAUNCH(h->ctx, fs_compose_anc_kernel<unsigned short>, grid, 256, 0, d);
-                else         PF_LAUNCH(h->ctx, fs_compose_anc_kernel<uint32_t>, grid, 256, 0, d);
-            }
+        if (d.m) {      // particle counts that are not a multiple of 4 (or PFGPU_COMPOSE_VEC=0): one slot per thread, separate flip
+            dim3 grid(cdiv_u(d.n, 256), cdiv_u(d.m, FS_COMPOSE_ROWS));
+            if (d.anc16) PF_LAUNCH(h->ctx, fs_compose_anc_kernel<unsigned short>, grid, 256, 0, d);
+            else         PF_LAUNCH(h->ctx, fs_compose_anc_kernel<uint32_t>, grid, 256, 0, d);
         }
         PF_LAUNCH(h->ctx, fs_flip_kernel, 1, 256, 0, d);
         h->steps++;

@@ -72,4 +72,16 @@ extern "C" {
     pub fn pfgpu_fs_step(h: *mut pfgpu_fs, u: *const f64, z: *const pfgpu_fs_obs, k: usize, did_resample: *mut c_int) -> c_int;
     pub fn pfgpu_fs_best(h: *mut pfgpu_fs, index_global: *mut usize, pose_w4: *mut f64) -> c_int;
     pub fn pfgpu_fs_particle_landmarks(h: *mut pfgpu_fs, index_local: usize, lm6: *mut f64) -> c_int;
+    pub fn pfgpu_fs_count(h: *mut pfgpu_fs, n_local: *mut usize, n_global: *mut usize, n_landmarks: *mut usize) -> c_int;
+    pub fn pfgpu_fs_sync(h: *mut pfgpu_fs) -> c_int;
+    pub fn pfgpu_pf_sync(h: *mut pfgpu_pf) -> c_int;
+    // multi-GPU: one process per GPU; rank 0 makes the id, the host program broadcasts its 128 bytes, every rank creates
+    // its shard with the GLOBAL particle count (INTEGRATION.md "Multi-GPU")
+    pub fn pfgpu_device_count(count: *mut c_int) -> c_int;
+    pub fn pfgpu_nccl_unique_id(out128: *mut c_void) -> c_int;
+    pub fn pfgpu_fs_create_sharded(cfg: *const pfgpu_fs_config, n_particles_global: usize, n_landmarks: usize, seed: u64,
+                                   device: c_int, nccl_unique_id: *const c_void, rank: c_int, world: c_int,
+                                   out: *mut *mut pfgpu_fs) -> c_int;
+    /// 0 = one GPU, 1 = sharded over NCCL collectives, 2 = sharded over peer memory (NVLink)
+    pub fn pfgpu_fs_shard_mode(h: *mut pfgpu_fs, mode: *mut c_int) -> c_int;
 }

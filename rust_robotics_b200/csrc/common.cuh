@@ -43,6 +43,29 @@ struct Ctx {
         }                                                                                               \
     } while (0)
 
+// Programmatic dependent launch (sm_90+): the launch may be set up while the previous kernel of the stream still runs; the
+// kernel itself waits (pf_grid_dep_sync, its FIRST statement) until that kernel has completed and its writes are visible.
+// Takes the scheduling latency between the dependent kernels of a step off the timeline; everything else is unchanged.
+#define PF_LAUNCH_PDL(ctx, pdl, kernel, grid, block, smem, ...)                                          \
+    do {                                                                                                \
+        cudaLaunchConfig_t c__ = {};                                                                    \
+        c__.gridDim = dim3(grid); c__.blockDim = dim3(block); c__.dynamicSmemBytes = (smem); c__.stream = (ctx).stream; \
+        cudaLaunchAttribute a__[1];                                                                     \
+        a__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                 \
+        a__[0].val.programmaticStreamSerializationAllowed = 1;                                          \
+        c__.attrs = a__; c__.numAttrs = (pdl) ? 1 : 0;                                                  \
+        cudaError_t e__ = cudaLaunchKernelEx(&c__, kernel, __VA_ARGS__);                                \
+        (ctx).launches++;                                                                               \
+        if (e__ != cudaSuccess) {                                                                       \
+            snprintf(g_pfgpu_err, sizeof(g_pfgpu_err), "%s:%d: launch %s -> %s", __FILE__, __LINE__,    \
+                     #kernel, cudaGetErrorString(e__));                                                 \
+            return PFGPU_ERR_CUDA;                                                                      \
+        }                                                                                               \
+    } while (0)
+#ifdef __CUDACC__
+__device__ __forceinline__ void pf_grid_dep_sync() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 static inline unsigned int cdiv_u(size_t a, size_t b) { return (unsigned int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------------------------------

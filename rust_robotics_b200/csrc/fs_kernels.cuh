@@ -211,6 +211,8 @@ __global__ void __launch_bounds__(FS_NT) fs_step_kernel(FsDev d, const __grid_co
 #define FS2_MAX_OBS 32
 __global__ void __launch_bounds__(256) fs_predict_kernel(FsDev d, double u0, double u1, double dt, double sq0, double sq1,
                                                          uint64_t seed, uint32_t call) {
+    pf_grid_dep_sync();
+
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= d.n) return;
     const int cur = *d.cur;
@@ -231,6 +233,8 @@ __global__ void __launch_bounds__(256) fs_predict_kernel(FsDev d, double u0, dou
 // <= 14 warps per SM; (448,1): up to 128 registers, one CTA per SM.  Chosen at run time by the host (PFGPU_EKF_VARIANT).
 template <bool PARAM_OBS, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) fs_ekf_kernel(FsDev d, const __grid_constant__ FsObsParam po, double r00, double r11, int k_obs) {
+    pf_grid_dep_sync();
+
     extern __shared__ double s_v2[];
     double* s_lik = s_v2;                                                          // [k_obs][32]
     unsigned* s_mask = reinterpret_cast<unsigned*>(s_lik + (size_t)k_obs * 32);    // [k_obs]
@@ -331,6 +335,8 @@ __global__ void __launch_bounds__(256) fs_search_kernel(FsDev d) {
 
 // index walk + pose clone in one pass (used after the fused post kernel)
 __global__ void __launch_bounds__(256) fs_search_pose_kernel(FsDev d) {
+    pf_grid_dep_sync();
+
     if (!*d.gate) return;
     const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (t >= d.n) return;
@@ -367,6 +373,8 @@ __global__ void __launch_bounds__(256) fs_gather_pose_kernel(FsDev d) {
 #define FS_COMPOSE_ROWS 16
 template <class AncT>
 __global__ void __launch_bounds__(256) fs_compose_anc_kernel(FsDev d) {
+    pf_grid_dep_sync();
+
     if (!*d.gate) return;
     const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (t >= d.n) return;
@@ -392,6 +400,8 @@ template <> struct AncVec4<uint32_t> { typedef uint4 type; };
 // ... and the ping-pong flip (fs_flip_kernel) is done by the last CTA to finish: one launch fewer per step
 template <class AncT>
 __global__ void __launch_bounds__(256) fs_compose_flip_kernel(FsDev d) {
+    pf_grid_dep_sync();
+
     if (!*d.gate) return;
     typedef typename AncVec4<AncT>::type V;
     __shared__ int s_last;
@@ -424,6 +434,8 @@ __global__ void __launch_bounds__(256) fs_compose_flip_kernel(FsDev d) {
     if (threadIdx.x == 0) { *d.cur ^= 1; *d.anc_cur ^= 1; d.counters[0] += 1; d.counters[2] = 0; }
 }
 __global__ void fs_flip_kernel(FsDev d) {
+    pf_grid_dep_sync();
+
     if (!*d.gate) return;
     for (size_t l = threadIdx.x; l < d.m; l += blockDim.x) d.lmstate[l] &= 1;     // no landmark is identity-mapped any more
     if (threadIdx.x == 0) { *d.cur ^= 1; *d.anc_cur ^= 1; d.counters[0] += 1; }

@@ -658,6 +658,7 @@ struct pfgpu_fs {
     bool fused_post = false;
     unsigned fx_nt = 0;
     bool step_v2 = true;           // observation-parallel step kernel (PFGPU_STEP_V2=0 selects the one-thread-per-particle form)
+    bool pdl = true;               // programmatic dependent launch for the kernels of a step (PFGPU_PDL=0 turns it off)
     bool compose_vec = true;       // 4 slots per thread in the ancestry composition (PFGPU_COMPOSE_VEC=0: one)
     int ekf_variant = 3;           // register budget of fs_ekf_kernel: 0 = 64 regs, 1 = 72 regs (2 CTAs/SM), 2 = up to 128 regs (1 CTA/SM)
     FsShard sh;                    // multi-GPU state (world == 1: unused)
@@ -759,6 +760,7 @@ static int fs_create_impl(const pfgpu_fs_config* cfg, size_t n, size_t n_global,
     rc = xs_work_alloc(h->xs, n);
     if (rc) return fail(rc);
     { const char* e2 = getenv("PFGPU_STEP_V2"); h->step_v2 = !(e2 && e2[0] == '0'); }
+    { const char* e5 = getenv("PFGPU_PDL"); h->pdl = !(e5 && e5[0] == '0'); }
     { const char* e4 = getenv("PFGPU_COMPOSE_VEC"); h->compose_vec = !(e4 && e4[0] == '0'); }
     { const char* e3 = getenv("PFGPU_EKF_VARIANT"); if (e3 && e3[0] >= '0' && e3[0] <= '4') h->ekf_variant = e3[0] - '0'; }
     {   // fused post-step kernel: usable when one co-resident wave covers all tiles
@@ -1198,14 +1200,14 @@ extern "C" int pfgpu_fs_step(pfgpu_fs* h, const double u[2], const pfgpu_fs_obs*
             if (h->step_v2 && kk <= FS2_MAX_OBS) {
                 // observation-parallel form: predict at full occupancy, then 32 particles x kk warps per CTA
                 if (do_predict)
-                    PF_LAUNCH(h->ctx, fs_predict_kernel, cdiv_u(d.n, 256), 256, 0, d, u[0], u[1], h->cfg.dt, sqrt(h->cfg.q00),
-                              sqrt(h->cfg.q11), h->seed, h->n_step);
+                    PF_LAUNCH_PDL(h->ctx, h->pdl, fs_predict_kernel, cdiv_u(d.n, 256), 256, 0, d, u[0], u[1], h->cfg.dt, sqrt(h->cfg.q00),
+                                  sqrt(h->cfg.q11), h->seed, (uint32_t)h->n_step);
                 if (kk) {
                     size_t smem = kk * 32 * sizeof(double) + kk * sizeof(unsigned) + 8;
                     const int var = kk <= 14 ? h->ekf_variant : 0;
                     if (var == 1)      PF_LAUNCH(h->ctx, (fs_ekf_kernel<true, 448, 2>), cdiv_u(d.n, 32), (unsigned)(32 * kk), smem, d, po, h->cfg.r00, h->cfg.r11, (int)kk);
                     else if (var == 2) PF_LAUNCH(h->ctx, (fs_ekf_kernel<true, 448, 1>), cdiv_u(d.n, 32), (unsigned)(32 * kk), smem, d, po, h->cfg.r00, h->cfg.r11, (int)kk);
-                    else if (var == 3) PF_LAUNCH(h->ctx, (fs_ekf_kernel<true, 448, 3>), cdiv_u(d.n, 32), (unsigned)(32 * kk), smem, d, po, h->cfg.r00, h->cfg.r11, (int)kk);
+                    else if (var == 3) PF_LAUNCH_PDL(h->ctx, h->pdl, (fs_ekf_kernel<true, 448, 3>), cdiv_u(d.n, 32), (unsigned)(32 * kk), smem, d, po, h->cfg.r00, h->cfg.r11, (int)kk);
                     else if (var == 4) PF_LAUNCH(h->ctx, (fs_ekf_kernel<true, 448, 4>), cdiv_u(d.n, 32), (unsigned)(32 * kk), smem, d, po, h->cfg.r00, h->cfg.r11, (int)kk);
                     else               PF_LAUNCH(h->ctx, (fs_ekf_kernel<true, 1024, 1>), cdiv_u(d.n, 32), (unsigned)(32 * kk), smem, d, po, h->cfg.r00, h->cfg.r11, (int)kk);
                 }
@@ -1267,11 +1269,11 @@ extern "C" int pfgpu_fs_step(pfgpu_fs* h, const double u[2], const pfgpu_fs_obs*
         void* args[] = { (void*)&d, (void*)&h->fx, (void*)&nth, (void*)&seed, (void*)&nt, (void*)&rel, (void*)&last_po, (void*)&last_k };
         PF_CUDA(cudaLaunchCooperativeKernel((void*)fs_post_kernel, dim3(nt), dim3(XS_NT), args, 0, h->ctx.stream));
         h->ctx.launches++;
-        PF_LAUNCH(h->ctx, fs_search_pose_kernel, cdiv_u(d.n, 256), 256, 0, d);
+        PF_LAUNCH_PDL(h->ctx, h->pdl, fs_search_pose_kernel, cdiv_u(d.n, 256), 256, 0, d);
         if (d.m && d.n % 4 == 0 && h->compose_vec) {
             dim3 grid(cdiv_u(d.n / 4, 256), cdiv_u(d.m, FS_COMPOSE_ROWS));
-            if (d.anc16) PF_LAUNCH(h->ctx, fs_compose_flip_kernel<unsigned short>, grid, 256, 0, d);
-            else         PF_LAUNCH(h->ctx, fs_compose_flip_kernel<uint32_t>, grid, 256, 0, d);
+            if (d.anc16) PF_LAUNCH_PDL(h->ctx, h->pdl, fs_compose_flip_kernel<unsigned short>, grid, 256, 0, d);
+            else         PF_LAUNCH_PDL(h->ctx, h->pdl, fs_compose_flip_kernel<uint32_t>, grid, 256, 0, d);
             h->steps++;
             if (did) {
                 int* hp = reinterpret_cast<int*>(h->h_pin + 32);

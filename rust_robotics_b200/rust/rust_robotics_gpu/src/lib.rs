@@ -5,5 +5,7 @@
 //! switches by changing `use rust_robotics_localization::ParticleFilterLocalizer` to
 //! `use rust_robotics_gpu::ParticleFilterLocalizer`.  NOT COMPILED HERE (no Rust toolchain in the build image).
 pub mod fastslam1;
+pub mod monte_carlo_localization;
 pub mod particle_filter;
+pub use monte_carlo_localization::{MonteCarloLocalizationConfig, MonteCarloLocalizer};
 pub use particle_filter::{ParticleFilterConfig, ParticleFilterLocalizer};

@@ -95,7 +95,8 @@ impl ParticleFilterLocalizer {
     pub fn set_range_noise(&mut self, s: f64) -> RoboticsResult<()> { status(unsafe { sys::pfgpu_pf_set_range_noise(self.h, s) })?; self.config.range_noise = s; Ok(()) }
     pub fn get_particles(&mut self) -> &[Particle] {                                               // pf.rs:244 (lazy D2H)
         if self.dirty {
-            let n = self.config.n_particles;
+            let (mut n, mut ng) = (0usize, 0usize);
+            let _ = unsafe { sys::pfgpu_pf_count(self.h, &mut n, &mut ng) };
             let mut aos = vec![0.0f64; 5 * n];
             let _ = unsafe { sys::pfgpu_pf_download(self.h, aos.as_mut_ptr(), n) };
             self.particles = aos.chunks(5).map(|c| Particle { x: c[0], y: c[1], yaw: c[2], v: c[3], w: c[4] }).collect();

@@ -19,7 +19,9 @@ extern "C" void xs_seq_scan(const double* v, size_t n, double* out) {
 }
 
 // stats: [0] dirty count, [1] certificate violations (must be 0), [2] universal-identity count
-extern "C" int xs_emul_scan(const double* v, size_t n, size_t tile, double* out, double* total, long long* stats) {
+// toff_in: optional approximate tile prefixes supplied by the caller (the fused kernels derive them from sums they already
+// hold instead of summing these very values first, see fs_post.cuh fx_classify_at); null = from pairwise tile sums of v
+static int xs_emul_scan_impl(const double* v, size_t n, size_t tile, const double* toff_in, double* out, double* total, long long* stats) {
     const double rel = xs_margin(n);
     size_t nt = (n + tile - 1) / tile;
     std::vector<double> tsum(nt), toff(nt);
@@ -27,6 +29,7 @@ extern "C" int xs_emul_scan(const double* v, size_t n, size_t tile, double* out,
     { // pass B: a *different* order again: offsets from a pairwise-ish running sum
         double acc = 0.0; for (size_t b = 0; b < nt; ++b) { toff[b] = acc; acc = tsum[b] + acc; }
     }
+    if (toff_in) for (size_t b = 0; b < nt; ++b) toff[b] = toff_in[b];
     std::vector<xs_t> tail(nt); std::vector<int> anyd(nt); std::vector<std::vector<Dirty>> ent(nt);
     long long nd = 0, viol = 0, nid = 0;
     const size_t chunk = 8;   // "per-thread items"
@@ -79,3 +82,32 @@ extern "C" int xs_emul_scan(const double* v, size_t n, size_t tile, double* out,
     stats[0] = nd; stats[1] = viol; stats[2] = nid;
     return ok;
 }
+
+extern "C" int xs_emul_scan(const double* v, size_t n, size_t tile, double* out, double* total, long long* stats) {
+    return xs_emul_scan_impl(v, n, tile, nullptr, out, total, stats);
+}
+// scan of w_i / S with the tile prefixes taken from the tile sums of w, divided by S afterwards
+// (fs_post.cuh: the CDF from the tile sums of w scaled by 1/S2; fs_mg.cuh: S2 from the tile sums of w_raw scaled by 1/S)
+extern "C" int xs_emul_scan_scaled(const double* w, size_t n, double S, size_t tile, double* v_out, double* out, double* total, long long* stats) {
+    size_t nt = (n + tile - 1) / tile;
+    std::vector<double> v(n), toff(nt);
+    for (size_t i = 0; i < n; ++i) v[i] = S > 0.0 ? w[i] / S : w[i];
+    double acc = 0.0;
+    for (size_t b = 0; b < nt; ++b) {
+        size_t lo = b * tile, hi = lo + tile < n ? lo + tile : n;
+        toff[b] = S > 0.0 ? acc / S : acc;
+        acc = pairwise(w + lo, hi - lo) + acc;
+    }
+    for (size_t i = 0; i < n; ++i) v_out[i] = v[i];
+    return xs_emul_scan_impl(v.data(), n, tile, toff.data(), out, total, stats);
+}
+// the systematic comb r0, 1/n, 1/n, ... (fs1.rs:219-230) with closed-form tile prefixes r0 + (b*tile - 1)/n
+extern "C" int xs_emul_scan_comb(double r0, double inv, size_t n, size_t tile, double* v_out, double* out, double* total, long long* stats) {
+    size_t nt = (n + tile - 1) / tile;
+    std::vector<double> v(n), toff(nt);
+    for (size_t i = 0; i < n; ++i) v[i] = i == 0 ? r0 : inv;
+    for (size_t b = 0; b < nt; ++b) toff[b] = b == 0 ? 0.0 : r0 + ((double)(b * tile) - 1.0) * inv;
+    for (size_t i = 0; i < n; ++i) v_out[i] = v[i];
+    return xs_emul_scan_impl(v.data(), n, tile, toff.data(), out, total, stats);
+}
+

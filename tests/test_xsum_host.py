@@ -23,6 +23,8 @@ def emul():
     L = C.CDLL(LIB)
     L.xs_emul_scan.argtypes = [dp, C.c_size_t, C.c_size_t, dp, dp, C.POINTER(C.c_longlong)]
     L.xs_seq_scan.argtypes = [dp, C.c_size_t, dp]
+    L.xs_emul_scan_scaled.argtypes = [dp, C.c_size_t, C.c_double, C.c_size_t, dp, dp, dp, C.POINTER(C.c_longlong)]
+    L.xs_emul_scan_comb.argtypes = [C.c_double, C.c_double, C.c_size_t, C.c_size_t, dp, dp, dp, C.POINTER(C.c_longlong)]
     return L
 
 
@@ -98,3 +100,39 @@ def test_xsum_random_fuzz(emul):
             w = np.where(rng.uniform(size=n) < 0.5, 0.0, rng.uniform(size=n) * 10.0 ** rng.integers(-320, 0, n).astype(float))
         out, ref, tot, ok, st = run(emul, w, int(rng.choice([32, 128, 1024])))
         assert ok == 1 and np.array_equal(out, ref), f"trial {trial}"
+
+
+# ---- derived tile prefixes (fs_post.cuh fx_classify_at): the approximate prefix that steers the classification comes from
+# sums the kernel already holds, not from tile sums of the summed values themselves ----
+@pytest.mark.parametrize("name,v", list(cases()), ids=[c[0] for c in cases()])
+@pytest.mark.parametrize("tile", [64, 512])
+def test_xsum_scaled_prefixes_bit_exact(emul, name, v, tile):
+    """cumsum(w_i / S) with tile prefixes = (tile sums of w) / S, for S = the sequential sum of w (the resample's
+    re-normalisation, fs1.rs:207) and for an S a few ulps off"""
+    w = np.ascontiguousarray(v, dtype=np.float64)
+    seq = np.empty_like(w)
+    emul.xs_seq_scan(w.ctypes.data_as(dp), w.size, seq.ctypes.data_as(dp))
+    for S in (float(seq[-1]), float(np.nextafter(seq[-1], np.inf)), 0.0):
+        vv, out, ref = np.empty_like(w), np.empty_like(w), np.empty_like(w)
+        tot = C.c_double(); st = (C.c_longlong * 3)()
+        ok = emul.xs_emul_scan_scaled(w.ctypes.data_as(dp), w.size, S, tile, vv.ctypes.data_as(dp), out.ctypes.data_as(dp), C.byref(tot), st)
+        if not np.all(np.isfinite(vv)):
+            continue                                   # w / S overflowed: the kernels take the exact serial walk for such input
+        emul.xs_seq_scan(vv.ctypes.data_as(dp), vv.size, ref.ctypes.data_as(dp))
+        assert ok == 1 and st[1] == 0, f"certificate violated ({name}, S={S})"
+        assert np.array_equal(out, ref), f"{name}, S={S}: scan differs at {np.flatnonzero(out != ref)[:5]}"
+
+
+@pytest.mark.parametrize("n", [1, 7, 1000, 4096, 65536, 100003, 1 << 20])
+@pytest.mark.parametrize("tile", [512])
+def test_xsum_comb_closed_form_prefixes_bit_exact(emul, n, tile):
+    """r_t = r0 + 1/n + 1/n + ... accumulated left to right (fs1.rs:219-230) with closed-form tile prefixes"""
+    rng = np.random.default_rng(n)
+    inv = 1.0 / n
+    for r0 in (0.0, inv * rng.uniform(), float(np.nextafter(inv, 0.0)), inv * 2.0 ** -30):
+        vv, out, ref = np.empty(n), np.empty(n), np.empty(n)
+        tot = C.c_double(); st = (C.c_longlong * 3)()
+        ok = emul.xs_emul_scan_comb(r0, inv, n, tile, vv.ctypes.data_as(dp), out.ctypes.data_as(dp), C.byref(tot), st)
+        emul.xs_seq_scan(vv.ctypes.data_as(dp), n, ref.ctypes.data_as(dp))
+        assert ok == 1 and st[1] == 0 and np.array_equal(out, ref), f"n={n} r0={r0}"
+

@@ -760,7 +760,7 @@ static int fs_create_impl(const pfgpu_fs_config* cfg, size_t n, size_t n_global,
     rc = xs_work_alloc(h->xs, n);
     if (rc) return fail(rc);
     { const char* e2 = getenv("PFGPU_STEP_V2"); h->step_v2 = !(e2 && e2[0] == '0'); }
-    { const char* e5 = getenv("PFGPU_PDL"); h->pdl = !(e5 && e5[0] == '0') && world == 1; }   // sharded steps: not measured with it yet
+    { const char* e5 = getenv("PFGPU_PDL"); h->pdl = (e5 && e5[0] == '2') || (!(e5 && e5[0] == '0') && world == 1); }   // sharded steps: not measured with it yet (PFGPU_PDL=2 forces it)
     { const char* e4 = getenv("PFGPU_COMPOSE_VEC"); h->compose_vec = !(e4 && e4[0] == '0'); }
     { const char* e3 = getenv("PFGPU_EKF_VARIANT"); if (e3 && e3[0] >= '0' && e3[0] <= '4') h->ekf_variant = e3[0] - '0'; }
     {   // fused post-step kernel: usable when one co-resident wave covers all tiles

@@ -42,8 +42,8 @@ struct MgDev {
 template <class T>
 __device__ __forceinline__ T* mg_at(const MgDev& mg, int g, size_t off) { return reinterpret_cast<T*>(mg.peer[g] + off); }
 
-// spin until *ctr has reached target (wrap-safe); gives up after some tens of seconds (a rank may legitimately be late by
-// as much as its host is: first-launch module loading, a descheduled process) so that a missing peer is an error, not a hang
+// spin until *ctr has reached target (wrap-safe); gives up after about 15 s (a rank may legitimately be late by as
+// much as its host is: first-launch module loading, a descheduled process) so that a missing peer is an error, not a hang
 __device__ __forceinline__ bool mg_wait(const unsigned* ctr, unsigned target, int* err) {
     unsigned long long spins = 0;
     for (;;) {
@@ -51,7 +51,7 @@ __device__ __forceinline__ bool mg_wait(const unsigned* ctr, unsigned target, in
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
         if ((int)(v - target) >= 0) return true;
         if (*(volatile int*)err) return false;
-        if (++spins > (1ull << 27)) { *err = 2; return false; }
+        if (++spins > (1ull << 24)) { *err = 2; return false; }      // ~1 us per probe: about 15 s
         __nanosleep(100);
     }
 }

@@ -102,11 +102,18 @@ def obs_arrays(rr, sc):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's algorithm (oracle port, glibc libm like the Rust reference), all host threads
 # ------------------------------------------------------------------------------------------------
+NTH_MODE = "default"       # --nth: default = particles/1.5 (BASELINE config 3 as surveyed), literal = fs1.rs:21's 66.67, every = resample every step
+
+
+def nth_value(n):
+    return {"default": n / 1.5, "literal": 100.0 / 1.5, "every": float(n) + 1.0}[NTH_MODE]
+
+
 def cpu_run(sc, n, steps, warmup, threads, t0_step=0):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import _oracle
     L = _oracle.load(libm=True)
-    o = _oracle.OracleFS(L, n, sc.m, seed=42, nth=n / 1.5)
+    o = _oracle.OracleFS(L, n, sc.m, seed=42, nth=nth_value(n))
     L.orc_fs_set_threads(o.h, threads)
     o.seed_map(sc.start, sc.landmarks)
     arrs = [o.obs_array(z) for z in sc.obs]
@@ -191,7 +198,9 @@ def load_traffic():
 def workload_config(sc, n_gpus):
     return {"workload": "FastSLAM 1.0 (fs1.rs fastslam_update), BASELINE config 3", "particles_per_gpu": N_PARTICLES,
             "particles": N_PARTICLES * n_gpus, "landmarks": sc.m, "mean_obs_per_step": round(sc.mean_k(), 2),
-            "nth": "particles/1.5", "start": "initialised map (cov 10 I), poses at truth", "seed": 42,
+            "nth": {"default": "particles/1.5", "literal": "66.67 (fs1.rs:21; never resamples at this particle count)",
+                    "every": "particles + 1 (stress variant: resample every step)"}[NTH_MODE],
+            "start": "initialised map (cov 10 I), poses at truth", "seed": 42,
             "parallelism": f"particle shards x{n_gpus}", "l2": "flushed (256 MiB memset) before every timed step"}
 
 
@@ -211,7 +220,7 @@ def run_ours(args, rank, world, local_rank):
     sc = make_scenario(total)
     arrs = obs_arrays(rr, sc)
     n_global = N_PARTICLES * world
-    cfg = rr.FsConfig(nth=n_global / 1.5)
+    cfg = rr.FsConfig(nth=nth_value(n_global))
     if world > 1:
         import numpy as np
         import torch
@@ -436,9 +445,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs)")
     ap.add_argument("--workload", default="fastslam", choices=["fastslam", "mcl", "pf"],
                     help="fastslam = BASELINE config 3 (default, the headline); mcl = config 2; pf = one point of the config-5 sweep")
+    ap.add_argument("--nth", default="default", choices=["default", "literal", "every"],
+                    help="fastslam workload: resample threshold — particles/1.5 (default), the reference's literal 66.67, or every step")
     ap.add_argument("--particles", type=int, default=1 << 20, help="mcl / pf workloads only")
     ap.add_argument("--threshold", type=float, default=1.0, help="pf workload: resample_threshold (1.0 = resample every step)")
     args = ap.parse_args()
+    global NTH_MODE
+    NTH_MODE = args.nth
     if args.warmup < 3:
         args.warmup = 3
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)

@@ -49,6 +49,13 @@ struct FsDev {
     int anc16 = 0;                           // 1: ancestry columns hold u16 (n <= 65 536)
     size_t ld = 0;                           // column stride of the landmark arrays: n, plus the GUEST columns of sharded mode
                                              // (maps imported from other ranks live in columns [n, ld) until the next compaction)
+    // ANCESTRY LOG (PFGPU_ANC_LOG=1, one GPU; model + rules in tests/test_anclog_model.py): a resample does not compose the
+    // ancestry rows at all, it appends its index array to a ring of `alog` generations; row l (explicit or identity) is valid
+    // for generation gen[l], and a reader at generation G = counters[0] first walks its slot back to gen[l] through the logged
+    // maps.  Every `alog` resamples all rows are recomposed to the current generation, so no walk is longer than the ring.
+    int alog = 0;                            // 0: off (every resample composes every row); else the ring size R
+    uint32_t* idxlog = nullptr;              // [R][n] index arrays of the last R resamples; slot g % R maps generation g+1 -> g
+    int* gen = nullptr;                      // [m] generation for which row l / its identity flag is valid
 };
 
 // Observation lists of up to FS_PARAM_OBS entries travel inside the kernel's launch parameters (no H2D copy).
@@ -67,6 +74,33 @@ __device__ __forceinline__ size_t fs_anc_load(const FsDev& d, int c, size_t k) {
     return d.anc16 ? (size_t)reinterpret_cast<const unsigned short*>(p)[k] : (size_t)p[k];
 }
 __device__ __forceinline__ size_t lm_index(size_t n, size_t l, int f, size_t i) { return (l * 6 + (size_t)f) * n + i; }
+// ancestry log: slot i of generation G -> the slot it descends from in generation gen[l]
+template <bool ALOG>
+__device__ __forceinline__ size_t fs_walk_back(const FsDev& d, size_t l, size_t i, unsigned G) {
+    if (!ALOG) return i;
+    size_t j = i;
+    const unsigned R = (unsigned)d.alog, gl = (unsigned)d.gen[l];
+    for (unsigned g = G; g != gl; --g) j = d.idxlog[(size_t)((g - 1u) % R) * d.n + j];
+    return j;
+}
+// landmark l may be updated in place: its row is the identity AND belongs to the current generation
+template <bool ALOG>
+__device__ __forceinline__ bool fs_row_fresh(const FsDev& d, size_t l, int st, unsigned G) {
+    return (st & 2) != 0 && (!ALOG || (unsigned)d.gen[l] == G);
+}
+// column that holds landmark l of the particle in slot i (current generation)
+template <bool ALOG>
+__device__ __forceinline__ size_t fs_lm_col(const FsDev& d, size_t l, size_t i, int st, unsigned G) {
+    const size_t j = fs_walk_back<ALOG>(d, l, i, G);
+    return (st & 2) ? j : fs_anc_load(d, *d.anc_cur, l * d.n + j);
+}
+// bookkeeping after an EKF launch updated landmark l: it now lives in the other buffer, own columns, current generation
+__device__ __forceinline__ void fs_mark_updated(const FsDev& d, int l) {
+    const int st = d.lmstate[l];
+    const unsigned G = d.counters[0];
+    const bool fresh = d.alog ? fs_row_fresh<true>(d, (size_t)l, st, G) : fs_row_fresh<false>(d, (size_t)l, st, G);
+    if (!fresh) { d.lmstate[l] = ((st & 1) ^ 1) | 2; if (d.alog) d.gen[l] = (int)G; }
+}
 
 // normalize_angle fs1.rs:80-89.  The reference loops without bound (and would spin forever on +-inf); the
 // device caps the loop at 2^22 turns, i.e. |angle| up to ~2.6e7 rad behaves exactly like the reference.
@@ -177,10 +211,11 @@ __global__ void __launch_bounds__(FS_NT) fs_step_kernel(FsDev d, const __grid_co
         const size_t l = (size_t)s_obs_fs[j].lm_id;
         const double zd = s_obs_fs[j].d, za = s_obs_fs[j].angle;
         const int st = d.lmstate[l];
-        const bool ident = (st & 2) != 0;
+        const unsigned G = d.counters[0];
+        const bool ident = d.alog ? fs_row_fresh<true>(d, l, st, G) : (st & 2) != 0;     // in place only if the row is fresh
         const double* __restrict__ src = fs_lm(d, st & 1);
         double* __restrict__ dst = fs_lm(d, ident ? (st & 1) : ((st & 1) ^ 1));
-        const size_t col = ident ? i : fs_anc_load(d, anc_c, l * n + i);       // lazy clone: read the ancestor's copy
+        const size_t col = ident ? i : (d.alog ? fs_lm_col<true>(d, l, i, st, G) : fs_anc_load(d, anc_c, l * n + i));   // lazy clone: read the ancestor's copy
         FsLm L;
         L.x = src[lm_index(d.ld, l, 0, col)]; L.y = src[lm_index(d.ld, l, 1, col)];
         L.c00 = src[lm_index(d.ld, l, 2, col)]; L.c01 = src[lm_index(d.ld, l, 3, col)];
@@ -231,7 +266,7 @@ __global__ void __launch_bounds__(256) fs_predict_kernel(FsDev d, double u0, dou
 
 // MAXT/MINB: launch bounds = register budget.  (1024,1): 64 registers, any k_obs <= 32; (448,2): 72 registers, two CTAs of
 // <= 14 warps per SM; (448,1): up to 128 registers, one CTA per SM.  Chosen at run time by the host (PFGPU_EKF_VARIANT).
-template <bool PARAM_OBS, int MAXT, int MINB>
+template <bool PARAM_OBS, int MAXT, int MINB, bool ALOG = false>
 __global__ void __launch_bounds__(MAXT, MINB) fs_ekf_kernel(FsDev d, const __grid_constant__ FsObsParam po, double r00, double r11, int k_obs) {
     pf_grid_dep_sync();
 
@@ -246,14 +281,15 @@ __global__ void __launch_bounds__(MAXT, MINB) fs_ekf_kernel(FsDev d, const __gri
     const FsObsDev ob = PARAM_OBS ? po.o[wj] : d.obs[wj];
     const size_t l = (size_t)ob.lm_id;
     const int st = d.lmstate[l];
-    const bool ident = (st & 2) != 0;
+    const unsigned G = ALOG ? d.counters[0] : 0u;                                  // ancestry log: current generation
+    const bool ident = fs_row_fresh<ALOG>(d, l, st, G);                            // update in place (own column, same buffer)
     const size_t ld = d.ld;
     const double* __restrict__ src = fs_lm(d, st & 1) + l * 6 * ld;
     double* __restrict__ dst = fs_lm(d, ident ? (st & 1) : ((st & 1) ^ 1)) + l * 6 * ld + i;
     bool wrote_cov = false;
     double lik = 1.0;
     if (valid) {
-        const size_t col = ident ? i : fs_anc_load(d, *d.anc_cur, l * n + i);     // lazy clone: the ancestor's copy
+        const size_t col = ident ? i : (ALOG ? fs_lm_col<ALOG>(d, l, i, st, G) : fs_anc_load(d, *d.anc_cur, l * n + i));     // lazy clone: the ancestor's copy
         const double* __restrict__ sp = src + col;
         FsLm L;
         L.x = sp[0]; L.y = sp[ld]; L.c00 = sp[2 * ld]; L.c01 = sp[3 * ld]; L.c10 = sp[4 * ld]; L.c11 = sp[5 * ld];
@@ -279,8 +315,7 @@ template <bool PARAM_OBS>
 __global__ void fs_lmstate_after_step_kernel(FsDev d, const __grid_constant__ FsObsParam po, int k_obs) {
     for (int j = threadIdx.x; j < k_obs; j += blockDim.x) {
         int l = PARAM_OBS ? po.o[j].lm_id : d.obs[j].lm_id;
-        int st = d.lmstate[l];
-        if (!(st & 2)) d.lmstate[l] = ((st & 1) ^ 1) | 2;
+        fs_mark_updated(d, l);
     }
 }
 
@@ -349,6 +384,7 @@ __global__ void __launch_bounds__(256) fs_search_pose_kernel(FsDev d) {
     }
     const size_t j = lo < d.n ? lo : d.n - 1;
     d.idx[t] = (uint32_t)j;
+    if (d.alog) d.idxlog[(size_t)(d.counters[0] % (unsigned)d.alog) * d.n + t] = (uint32_t)j;   // ancestry log: generation G+1 -> G
     const int cur = *d.cur;
     fs_px(d, cur ^ 1)[t] = fs_px(d, cur)[j];
     fs_py(d, cur ^ 1)[t] = fs_py(d, cur)[j];
@@ -401,12 +437,16 @@ template <> struct AncVec4<uint32_t> { typedef uint4 type; };
 template <class AncT>
 __global__ void __launch_bounds__(256) fs_compose_flip_kernel(FsDev d) {
     pf_grid_dep_sync();
-
     if (!*d.gate) return;
     typedef typename AncVec4<AncT>::type V;
     __shared__ int s_last;
+    const unsigned G = d.counters[0];
+    // ancestry log: rows are left stale (the resample's index array is in the ring); only every alog-th resample recomposes
+    // all of them to the new generation G + 1, walking each slot back through the ring to the row's own generation
+    const bool alog = d.alog != 0;
+    const bool compose = !alog || (G + 1u) % (unsigned)d.alog == 0u;
     const size_t t = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
-    if (t < d.n) {
+    if (compose && t < d.n) {
         const int ac = *d.anc_cur;
         const AncT* __restrict__ src = reinterpret_cast<const AncT*>(fs_anc(d, ac));
         AncT* __restrict__ dst = reinterpret_cast<AncT*>(fs_anc(d, ac ^ 1));
@@ -416,11 +456,16 @@ __global__ void __launch_bounds__(256) fs_compose_flip_kernel(FsDev d) {
         for (int rr = 0; rr < FS_COMPOSE_ROWS; ++rr) {
             const size_t l = l0 + rr;
             if (l >= d.m) break;
+            uint4 j4 = jj;                                         // slots of generation G
+            if (alog) {
+                j4.x = (unsigned)fs_walk_back<true>(d, l, jj.x, G); j4.y = (unsigned)fs_walk_back<true>(d, l, jj.y, G);
+                j4.z = (unsigned)fs_walk_back<true>(d, l, jj.z, G); j4.w = (unsigned)fs_walk_back<true>(d, l, jj.w, G);
+            }
             V o;
-            if (d.lmstate[l] & 2) { o.x = (AncT)jj.x; o.y = (AncT)jj.y; o.z = (AncT)jj.z; o.w = (AncT)jj.w; }
+            if (d.lmstate[l] & 2) { o.x = (AncT)j4.x; o.y = (AncT)j4.y; o.z = (AncT)j4.z; o.w = (AncT)j4.w; }
             else {
                 const AncT* __restrict__ row = src + l * d.n;
-                o.x = row[jj.x]; o.y = row[jj.y]; o.z = row[jj.z]; o.w = row[jj.w];
+                o.x = row[j4.x]; o.y = row[j4.y]; o.z = row[j4.z]; o.w = row[j4.w];
             }
             *reinterpret_cast<V*>(dst + l * d.n + t) = o;
         }
@@ -429,9 +474,9 @@ __global__ void __launch_bounds__(256) fs_compose_flip_kernel(FsDev d) {
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(&d.counters[2], 1u) + 1u == gridDim.x * gridDim.y) ? 1 : 0;
     __syncthreads();
-    if (!s_last) return;                                           // every other CTA has read lmstate / anc_cur by now
-    for (size_t l = threadIdx.x; l < d.m; l += blockDim.x) d.lmstate[l] &= 1;
-    if (threadIdx.x == 0) { *d.cur ^= 1; *d.anc_cur ^= 1; d.counters[0] += 1; d.counters[2] = 0; }
+    if (!s_last) return;                                           // every other CTA has read lmstate / anc_cur / gen by now
+    if (compose) for (size_t l = threadIdx.x; l < d.m; l += blockDim.x) { d.lmstate[l] &= 1; if (alog) d.gen[l] = (int)(G + 1u); }
+    if (threadIdx.x == 0) { *d.cur ^= 1; if (compose) *d.anc_cur ^= 1; d.counters[0] = G + 1u; d.counters[2] = 0; }
 }
 __global__ void fs_flip_kernel(FsDev d) {
     pf_grid_dep_sync();
@@ -491,12 +536,16 @@ __global__ void __launch_bounds__(256) fs_pack_lm_kernel(FsDev d, double* aos, s
     size_t ip = e / (d.m * 6), rem = e % (d.m * 6);
     size_t l = rem / 6; int f = (int)(rem % 6);
     const int st = d.lmstate[l];
-    const size_t col = (st & 2) ? (i0 + ip) : fs_anc_load(d, *d.anc_cur, l * d.n + i0 + ip);   // materialise through the ancestry
+    const size_t col = d.alog ? fs_lm_col<true>(d, l, i0 + ip, st, d.counters[0])
+                              : ((st & 2) ? (i0 + ip) : fs_anc_load(d, *d.anc_cur, l * d.n + i0 + ip));   // materialise through the ancestry
     aos[e] = fs_lm(d, st & 1)[lm_index(d.ld, l, f, col)];
 }
 __global__ void fs_lmstate_reset_kernel(FsDev d) {     // every landmark identity-mapped in buffer 0 (eager mode: *cur) after init/upload/seed
     const int buf = d.eager ? *d.cur : 0;
-    for (size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x; l < d.m; l += (size_t)gridDim.x * blockDim.x) d.lmstate[l] = buf | 2;
+    for (size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x; l < d.m; l += (size_t)gridDim.x * blockDim.x) {
+        d.lmstate[l] = buf | 2;
+        if (d.alog) d.gen[l] = (int)d.counters[0];             // identity of the CURRENT generation
+    }
 }
 // create_particles fs1.rs:302-306: Particle::new (fs1.rs:54-62) with Landmark::new (fs1.rs:34-40)
 __global__ void __launch_bounds__(256) fs_init_kernel(FsDev d, double init_weight) {

@@ -130,11 +130,7 @@ __global__ void __launch_bounds__(XS_NT, 2) fs_post_mg_kernel(FsDev d, FxWork fw
 #define MG_BARRIER() do { if (!mg_barrier(mg, target, &s_ok)) { MG_FINISH(); return; } } while (0)
     if (bl == 0 && tid == 0 && fw.dbg) fw.dbg[31] += 1;
     if (bl == 0 && tid == 0) mg_stamp(mg, 0);
-    if (bl == 0 && tid < k_obs) {           // lazy-clone bookkeeping of the EKF launch that just ran
-        const int l = po.o[tid].lm_id;
-        const int st = d.lmstate[l];
-        if (!(st & 2)) d.lmstate[l] = ((st & 1) ^ 1) | 2;
-    }
+    if (bl == 0 && tid < k_obs) fs_mark_updated(d, po.o[tid].lm_id);   // lazy-clone bookkeeping of the EKF launch that just ran
     double v[FX_ITEMS];
 #pragma unroll
     for (int k = 0; k < FX_ITEMS; ++k) { size_t i = firstl + k; v[k] = i < n ? d.w_raw[i] : 0.0; }

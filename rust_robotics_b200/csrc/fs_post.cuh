@@ -374,11 +374,7 @@ __global__ void __launch_bounds__(XS_NT, 2) fs_post_kernel(FsDev d, FxWork fw, d
     const size_t n = d.n;
     unsigned long long t_prev = fx_now();
     if (b == 0 && tid == 0) { fw.flags[0] = 0; if (fw.dbg) fw.dbg[31] += 1; }
-    if (b == 0 && tid < k_obs) {           // lazy-clone bookkeeping of the EKF launch that just ran (see fs_lmstate_after_step_kernel)
-        const int l = po.o[tid].lm_id;
-        const int st = d.lmstate[l];
-        if (!(st & 2)) d.lmstate[l] = ((st & 1) ^ 1) | 2;
-    }
+    if (b == 0 && tid < k_obs) fs_mark_updated(d, po.o[tid].lm_id);   // lazy-clone bookkeeping of the EKF launch that just ran
     double v[FX_ITEMS];
 #pragma unroll
     for (int k = 0; k < FX_ITEMS; ++k) { size_t i = first + k; v[k] = i < n ? d.w_raw[i] : 0.0; }

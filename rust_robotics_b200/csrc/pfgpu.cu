@@ -793,6 +793,17 @@ static int fs_create_impl(const pfgpu_fs_config* cfg, size_t n, size_t n_global,
             }
         }
     }
+    {   // ancestry log (PFGPU_ANC_LOG=1; fs_kernels.cuh FsDev::alog): resamples stop composing the ancestry rows
+        const char* ea = getenv("PFGPU_ANC_LOG");
+        if (ea && ea[0] == '1' && world == 1 && h->fused_post && n % 4 == 0 && h->compose_vec && m > 0) {
+            int R = 32;
+            const char* er = getenv("PFGPU_ANC_LOG_R");
+            if (er && atoi(er) >= 1 && atoi(er) <= 4096) R = atoi(er);
+            if (cudaMalloc(&d.idxlog, (size_t)R * n * sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&d.gen, m * sizeof(int)) != cudaSuccess ||
+                cudaMemset(d.gen, 0, m * sizeof(int)) != cudaSuccess) return fail(PFGPU_ERR_CUDA);
+            d.alog = R;
+        }
+    }
     if (world > 1) {
         FsShard& sh = h->sh;
         sh.rank = rank; sh.world = world;
@@ -919,7 +930,7 @@ extern "C" void pfgpu_fs_destroy(pfgpu_fs* h) {
     for (int b = 0; b < 2; ++b) { cudaFree(d.px[b]); cudaFree(d.py[b]); cudaFree(d.pyaw[b]); cudaFree(d.lm[b]); }
     cudaFree(d.cur); cudaFree(d.w); cudaFree(d.w_raw); cudaFree(d.cum); cudaFree(d.rcomb); cudaFree(d.idx); cudaFree(d.scal);
     cudaFree(d.gate); cudaFree(d.obs); cudaFree(d.best_w); cudaFree(d.best_i); cudaFree(d.counters);
-    cudaFree(d.anc[0]); cudaFree(d.anc[1]); cudaFree(d.anc_cur); cudaFree(d.lmstate);
+    cudaFree(d.anc[0]); cudaFree(d.anc[1]); cudaFree(d.anc_cur); cudaFree(d.lmstate); cudaFree(d.idxlog); cudaFree(d.gen);
     for (int sl = 0; sl < FX_SLOTS; ++sl) { cudaFree(h->fx.slot[sl].tsum); cudaFree(h->fx.slot[sl].ttail); cudaFree(h->fx.slot[sl].tnd); cudaFree(h->fx.slot[sl].ent); }
     cudaFree(h->fx.flags); cudaFree(h->fx.dbg);
     {
@@ -1205,6 +1216,10 @@ extern "C" int pfgpu_fs_step(pfgpu_fs* h, const double u[2], const pfgpu_fs_obs*
                 if (kk) {
                     size_t smem = kk * 32 * sizeof(double) + kk * sizeof(unsigned) + 8;
                     const int var = kk <= 14 ? h->ekf_variant : 0;
+                    if (d.alog) {      // ancestry log: the read path walks the ring (two instantiations: 3 CTAs/SM up to 14 observations, else 1)
+                        if (kk <= 14) PF_LAUNCH_PDL(h->ctx, h->pdl, (fs_ekf_kernel<true, 448, 3, true>), cdiv_u(d.n, 32), (unsigned)(32 * kk), smem, d, po, h->cfg.r00, h->cfg.r11, (int)kk);
+                        else          PF_LAUNCH_PDL(h->ctx, h->pdl, (fs_ekf_kernel<true, 1024, 1, true>), cdiv_u(d.n, 32), (unsigned)(32 * kk), smem, d, po, h->cfg.r00, h->cfg.r11, (int)kk);
+                    } else
                     if (var == 1)      PF_LAUNCH(h->ctx, (fs_ekf_kernel<true, 448, 2>), cdiv_u(d.n, 32), (unsigned)(32 * kk), smem, d, po, h->cfg.r00, h->cfg.r11, (int)kk);
                     else if (var == 2) PF_LAUNCH(h->ctx, (fs_ekf_kernel<true, 448, 1>), cdiv_u(d.n, 32), (unsigned)(32 * kk), smem, d, po, h->cfg.r00, h->cfg.r11, (int)kk);
                     else if (var == 3) PF_LAUNCH_PDL(h->ctx, h->pdl, (fs_ekf_kernel<true, 448, 3>), cdiv_u(d.n, 32), (unsigned)(32 * kk), smem, d, po, h->cfg.r00, h->cfg.r11, (int)kk);

@@ -6,6 +6,7 @@ sequential f64 sums exactly (xsum), particles, weights, landmarks and indices ar
 BIT EQUALITY; only estimate/covariance (tree-order sums on the device) use the 1e-6 tolerance.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -242,6 +243,30 @@ def _fs_compare(g, o, what, landmarks=True):
     assert np.array_equal(gp, op), f"{what}: pose/weight rows {np.flatnonzero((gp != op).any(axis=1))[:5]}"
     if landmarks:
         assert np.array_equal(gl, ol), f"{what}: landmarks differ for particles {np.flatnonzero((gl != ol).any(axis=(1, 2)))[:5]}"
+
+
+@pytest.mark.skipif(os.environ.get("PFGPU_TEST_ANC_LOG") != "1",
+                    reason="ancestry-log form of the lazy clone (PFGPU_ANC_LOG=1): written without GPU time in round 1, opt-in until measured")
+@pytest.mark.parametrize("n,side,steps,ring", [(1024, 6, 60, 4), (4096, 8, 40, 32), (1 << 16, 16, 6, 2), (1024, 6, 40, 1)])
+def test_fastslam_ancestry_log_bit_exact(oracle, n, side, steps, ring, monkeypatch):
+    """same trajectories with resamples that only log their index array (rules: tests/test_anclog_model.py)"""
+    monkeypatch.setenv("PFGPU_ANC_LOG", "1")
+    monkeypatch.setenv("PFGPU_ANC_LOG_R", str(ring))
+    sc = scenarios.FastSlamScenario(side, (10.0 * side / 2 - 5.0, 10.0 * side / 2 - 5.0, 0.0), (1.0, 0.025), steps)
+    g = rr.FastSlam1(n, sc.m, rr.FsConfig(nth=n / 1.5), seed=7)
+    o = OracleFS(oracle, n, sc.m, seed=7, nth=n / 1.5)
+    g.seed_map(sc.start, sc.landmarks); o.seed_map(sc.start, sc.landmarks)
+    resamples = 0
+    for t in range(steps):
+        did = g.fastslam_update(sc.control, sc.obs[t])
+        assert did == bool(o.step(sc.control, sc.obs[t])), f"step {t}"
+        if did:
+            resamples += 1
+            assert np.array_equal(g.last_indices(), o.last_indices()), f"step {t}"
+        if t % 7 == 0:
+            _fs_compare(g, o, f"step {t}")
+    _fs_compare(g, o, "end")
+    assert resamples > ring
 
 
 @pytest.mark.parametrize("n,side,steps", [(64, 4, 30), (1000, 6, 25), (4096, 8, 20), (1 << 16, 16, 4)])

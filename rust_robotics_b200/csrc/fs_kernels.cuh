@@ -437,14 +437,50 @@ template <> struct AncVec4<uint32_t> { typedef uint4 type; };
 template <class AncT>
 __global__ void __launch_bounds__(256) fs_compose_flip_kernel(FsDev d) {
     pf_grid_dep_sync();
+
+    if (!*d.gate) return;
+    typedef typename AncVec4<AncT>::type V;
+    __shared__ int s_last;
+    const size_t t = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (t < d.n) {
+        const int ac = *d.anc_cur;
+        const AncT* __restrict__ src = reinterpret_cast<const AncT*>(fs_anc(d, ac));
+        AncT* __restrict__ dst = reinterpret_cast<AncT*>(fs_anc(d, ac ^ 1));
+        const uint4 jj = *reinterpret_cast<const uint4*>(d.idx + t);
+        const size_t l0 = (size_t)blockIdx.y * FS_COMPOSE_ROWS;
+#pragma unroll
+        for (int rr = 0; rr < FS_COMPOSE_ROWS; ++rr) {
+            const size_t l = l0 + rr;
+            if (l >= d.m) break;
+            V o;
+            if (d.lmstate[l] & 2) { o.x = (AncT)jj.x; o.y = (AncT)jj.y; o.z = (AncT)jj.z; o.w = (AncT)jj.w; }
+            else {
+                const AncT* __restrict__ row = src + l * d.n;
+                o.x = row[jj.x]; o.y = row[jj.y]; o.z = row[jj.z]; o.w = row[jj.w];
+            }
+            *reinterpret_cast<V*>(dst + l * d.n + t) = o;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&d.counters[2], 1u) + 1u == gridDim.x * gridDim.y) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;                                           // every other CTA has read lmstate / anc_cur by now
+    for (size_t l = threadIdx.x; l < d.m; l += blockDim.x) d.lmstate[l] &= 1;
+    if (threadIdx.x == 0) { *d.cur ^= 1; *d.anc_cur ^= 1; d.counters[0] += 1; d.counters[2] = 0; }
+}
+// the same kernel for the ANCESTRY LOG form (FsDev::alog != 0): most resamples only flip; see the comment inside
+template <class AncT>
+__global__ void __launch_bounds__(256) fs_compose_flip_alog_kernel(FsDev d) {
+    pf_grid_dep_sync();
     if (!*d.gate) return;
     typedef typename AncVec4<AncT>::type V;
     __shared__ int s_last;
     const unsigned G = d.counters[0];
     // ancestry log: rows are left stale (the resample's index array is in the ring); only every alog-th resample recomposes
     // all of them to the new generation G + 1, walking each slot back through the ring to the row's own generation
-    const bool alog = d.alog != 0;
-    const bool compose = !alog || (G + 1u) % (unsigned)d.alog == 0u;
+    const bool alog = true;
+    const bool compose = (G + 1u) % (unsigned)d.alog == 0u;
     const size_t t = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
     if (compose && t < d.n) {
         const int ac = *d.anc_cur;

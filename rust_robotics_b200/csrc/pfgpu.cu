@@ -1287,8 +1287,13 @@ extern "C" int pfgpu_fs_step(pfgpu_fs* h, const double u[2], const pfgpu_fs_obs*
         PF_LAUNCH_PDL(h->ctx, h->pdl, fs_search_pose_kernel, cdiv_u(d.n, 256), 256, 0, d);
         if (d.m && d.n % 4 == 0 && h->compose_vec) {
             dim3 grid(cdiv_u(d.n / 4, 256), cdiv_u(d.m, FS_COMPOSE_ROWS));
-            if (d.anc16) PF_LAUNCH_PDL(h->ctx, h->pdl, fs_compose_flip_kernel<unsigned short>, grid, 256, 0, d);
-            else         PF_LAUNCH_PDL(h->ctx, h->pdl, fs_compose_flip_kernel<uint32_t>, grid, 256, 0, d);
+            if (d.alog) {
+                if (d.anc16) PF_LAUNCH_PDL(h->ctx, h->pdl, fs_compose_flip_alog_kernel<unsigned short>, grid, 256, 0, d);
+                else         PF_LAUNCH_PDL(h->ctx, h->pdl, fs_compose_flip_alog_kernel<uint32_t>, grid, 256, 0, d);
+            } else {
+                if (d.anc16) PF_LAUNCH_PDL(h->ctx, h->pdl, fs_compose_flip_kernel<unsigned short>, grid, 256, 0, d);
+                else         PF_LAUNCH_PDL(h->ctx, h->pdl, fs_compose_flip_kernel<uint32_t>, grid, 256, 0, d);
+            }
             h->steps++;
             if (did) {
                 int* hp = reinterpret_cast<int*>(h->h_pin + 32);

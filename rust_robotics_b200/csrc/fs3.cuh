@@ -1,0 +1,790 @@
+// fs3.cuh — FastSLAM 1.0 step (fs1.rs = crates/rust_robotics_slam/src/fastslam1.rs) in TWO kernels per step, the same on
+// one GPU and on G GPUs of one NVLink domain:
+//
+//   fs3_ekf_kernel    predict_particle (fs1.rs:123-137) + update_landmark (fs1.rs:140-183) for every (particle, observation)
+//                     pair + the weight products in observation order (fs1.rs:250-256).  A CTA owns 64 particles (two per
+//                     lane: 128-bit loads/stores of adjacent columns, two independent dependency chains per thread) and runs
+//                     one warp per observation.  Its epilogue pushes the 64 unnormalised weights and their (tree) partial
+//                     sum to EVERY rank.
+//   fs3_post_kernel   everything after the per-particle work (fs1.rs:258-265, resample fs1.rs:206-234): exact sequential
+//                     sums S, S2, the CDF (x3_core.h), normalisation, N_eff gate, the comb in closed form, index search,
+//                     pose clone and the lazy clone of the maps — one launch of <= 148 co-resident CTAs that synchronise
+//                     through a counter in global memory (one such barrier for a step that does not resample, four for one
+//                     that does).  Every rank runs it on ALL n_glob weights (they are 8 B per particle), so the ranks never
+//                     wait for each other inside it.
+//
+// HBM layout per rank (n local particles, column stride ld = n rounded up to 64, m landmarks):
+//   px, py, pyaw [2][ld]        pose columns (ping-pong across resamples; st->cur selects the live set)
+//   lm [2][m][6][ld]            landmark EKF state, field-major: the six fields of landmark l are six contiguous columns
+//   rows [2][m][ld] (u32)       LAZY CLONE BY GENERATION.  The reference's resample deep-copies every particle's map
+//                               (particles[j].clone(), fs1.rs:227: 48*m bytes per particle).  Here a resample moves no map
+//                               data at all.  Landmarks whose last EKF update happened in the same inter-resample period
+//                               share one ancestry row: rows[r][i] = (rank << 28 | column) where slot i's copy of those
+//                               landmarks lives.  lmst[l] = buffer bit | (row + 1) << 1, row + 1 == 0: "identity" (slot i's
+//                               copy is column i of its own rank).  A resample composes only the LIVE rows (a handful:
+//                               one per period in which some not-since-observed landmark was last updated),
+//                               rows'[r][t] = rows[r]@(ancestor of t), and gives the identity landmarks one new row that
+//                               holds the ancestors themselves.  The next EKF update of a landmark reads through its row
+//                               (over NVLink when the ancestor lives on another rank), writes column i of the OTHER buffer
+//                               and the landmark is "identity" again.
+//   wraw_all [2][n_glob], part_all [2][n_glob/64]   this step's unnormalised weights of ALL particles and their 64-particle
+//                               partial sums (double-buffered by step parity; every rank's EKF epilogue writes its slice
+//                               into every rank's copy)
+// Cross-rank protocol (G > 1): arrive[g] = step+1 is stored into every peer after rank g's EKF pushed its weights; the post
+// kernel of step s waits for all arrive == s+1.  done[g] = step+1 after rank g's post kernel; the EKF kernel of step s+1
+// waits for all done == s+1 (rows / poses / maps of a peer are only read between those two points, when nobody writes them).
+#pragma once
+#include "common.cuh"
+#include "x3_core.h"
+#include "../../include/fs_ekf_math.h"
+
+#define FS3_MAXG 8
+#define FS3_MAX_OBS 32            // observations per EKF launch (one warp each)
+#define FS3_MAX_TILES 160
+#define FS3_ENT_TILE 32           // dirty values itemised per tile (more: that sum takes the serial walk)
+#define FS3_ENT_CAP 1024          // ... per sum
+#define FS3_SLOTS 5               // S, Q (border only), S2, cdf, comb (n not a power of two)
+#define FS3_SPIN_LIMIT (1u << 27)
+
+struct Fs3Obs { double d, angle; int lm_id; int pad; };
+struct Fs3ObsParam { Fs3Obs o[FS3_MAX_OBS]; };
+
+struct Fs3State {                 // device-resident; written by the last CTA of a launch, read by the next launch
+    int cur, rcur;                // live pose buffer / live rows buffer
+    unsigned resamples;           // resamples so far = Philox call index of the next comb draw (fs1.rs:220)
+    int gate;                     // last step resampled
+    unsigned ekf_done, post_done; // CTA completion counters
+    unsigned bar_count, bar_gen;  // grid barrier of the post kernel
+    int err;                      // sticky: 1 = a barrier or a peer flag timed out
+    int serial_walks, cert_fail, dirty_last, border_cnt, pad0;
+    double S, Q, neff, S2, r0;
+};
+struct Fs3Rec {                   // mapped pinned host memory: what a caller reads after a step (one 64-byte record)
+    unsigned long long seq;       // step + 1, written last
+    unsigned long long best_idx;  // get_best_particle fs1.rs:269-274 (global slot; the LAST maximum)
+    double best_w, bx, by, byaw, neff;
+    int gate, err;
+};
+
+struct Fs3Dev {
+    unsigned n, n_glob, off, m, ld;           // local / global particles, first global slot, landmarks, column stride
+    int G, rank;
+    unsigned npart;                           // partial sums per rank (= ld / 64)
+    Fs3State* st;
+    int* lmst;                                // [m]
+    char* peer[FS3_MAXG];                     // arena base of every rank (peer[rank] = own)
+    size_t o_flags, o_wraw[2], o_part[2], o_px[2], o_py[2], o_pyaw[2], o_rows[2], o_lm[2];   // offsets inside an arena
+    double *px[2], *py[2], *pyaw[2], *lm[2];  // own arena
+    unsigned* rows[2];
+    double* wraw[2]; double* part[2];         // own copies of wraw_all / part_all
+    double* w;                                // [ld] normalised weights of the local slots (Particle::weight)
+    double* wn_all;                           // [n_glob] normalised weights of all slots (post-kernel scratch, fallback walks)
+    double* cum_all;                          // [n_glob] exact CDF
+    double* rcomb_all;                        // [n_glob] exact comb (only when n_glob is not a power of two)
+    unsigned* idx;                            // [ld] global ancestor of local slot t at the last resample
+    unsigned long long* tileP; int* tileD; double* tileQ;      // [FS3_SLOTS][FS3_MAX_TILES] tile aggregates
+    unsigned long long* entP; double* entV; int* entL;         // [FS3_SLOTS][FS3_MAX_TILES][FS3_ENT_TILE]
+    double* tileBw; unsigned* tileBi;         // [FS3_MAX_TILES] best (weight, global slot) per tile
+    int* flagsg;                              // [FS3_SLOTS] "bad value seen" per sum (reset by the post kernel's last CTA)
+    Fs3Rec* rec;
+    unsigned long long* trace;                // optional [32] phase timestamps (PFGPU_POST_TRACE)
+};
+
+__device__ __forceinline__ unsigned fs3_ref(int rank, unsigned col) { return ((unsigned)rank << 28) | col; }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) { unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned* fs3_flag(const Fs3Dev& d, int owner, int which, int src) {
+    return reinterpret_cast<unsigned*>(d.peer[owner] + d.o_flags + ((size_t)which * FS3_MAXG + (size_t)src) * 128);
+}
+// wait until every peer's flag `which` in MY arena has reached `target` (flags only grow)
+__device__ __forceinline__ void fs3_wait_peers(const Fs3Dev& d, int which, unsigned target) {
+    for (int g = 0; g < d.G; ++g) {
+        if (g == d.rank) continue;
+        const unsigned* f = fs3_flag(d, d.rank, which, g);
+        unsigned spins = 0;
+        while ((int)(ld_acquire_sys(f) - target) < 0) {
+            if (++spins > FS3_SPIN_LIMIT) { d.st->err = 1; break; }
+            __nanosleep(40);
+        }
+    }
+}
+__device__ __forceinline__ void fs3_signal_peers(const Fs3Dev& d, int which, unsigned value) {   // call with >= G threads
+    const int g = threadIdx.x;
+    if (g < d.G && g != d.rank) { __threadfence_system(); st_release_sys(fs3_flag(d, g, which, d.rank), value); }
+}
+
+// =====================================================================================================================
+// EKF kernel
+// =====================================================================================================================
+__device__ __noinline__ double fs3_update_slow(FsLm* L, double px, double py, double pyaw, double z0, double z1, double r00, double r11) {
+    int wrote;
+    return fs_update_landmark(L, px, py, pyaw, z0, z1, r00, r11, &wrote);   // 1.0 whenever the weight is left alone
+}
+
+// flags: bit 0 = first launch of the step (predict; weights start from Particle::weight), bit 1 = last launch of the step
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+fs3_ekf_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsParam po, double u0, double u1, double dt,
+               double sq0, double sq1, double r00, double r11, uint64_t seed, uint32_t call, int k_obs, int flags, unsigned step) {
+    pf_grid_dep_sync();
+    extern __shared__ double s_dyn[];
+    double* s_pose = s_dyn;                     // [3][64]
+    double* s_lik = s_dyn + 192;                // [k_obs][64]
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31, wj = threadIdx.x >> 5;
+    const unsigned i0 = blockIdx.x * 64u + 2u * (unsigned)lane;     // local slots i0, i0 + 1 (inside the padded stride)
+    Fs3State* st = d.st;
+    if (d.G > 1) {                              // peers' rows / poses / maps are stable once their previous post kernel is over
+        if (threadIdx.x == 0) fs3_wait_peers(d, 1, step);
+        __syncthreads();
+    }
+    const int cur = st->cur, rcur = st->rcur, par = (int)(step & 1u);
+    const size_t ld = d.ld;
+    // ---- landmark loads first (they do not depend on the pose) ----
+    FsLm L[2];
+    Fs3Obs ob; ob.d = 0.0; ob.angle = 0.0; ob.lm_id = 0; ob.pad = 0;
+    bool ident = true; int buf = 0; size_t lbase = 0;
+    if (k_obs > 0) {
+        ob = po.o[wj];
+        const int s = d.lmst[ob.lm_id];
+        ident = (s >> 1) == 0; buf = s & 1;
+        lbase = (size_t)ob.lm_id * 6 * ld;
+        if (ident) {
+            const double* p = d.lm[buf] + lbase + i0;
+            const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + ld);
+            const double2 c = *reinterpret_cast<const double2*>(p + 2 * ld), e = *reinterpret_cast<const double2*>(p + 3 * ld);
+            const double2 f = *reinterpret_cast<const double2*>(p + 4 * ld), g = *reinterpret_cast<const double2*>(p + 5 * ld);
+            L[0].x = a.x; L[1].x = a.y; L[0].y = b.x; L[1].y = b.y; L[0].c00 = c.x; L[1].c00 = c.y;
+            L[0].c01 = e.x; L[1].c01 = e.y; L[0].c10 = f.x; L[1].c10 = f.y; L[0].c11 = g.x; L[1].c11 = g.y;
+        } else {                                // lazy clone: read the ancestors' copies through the landmark's row
+            const uint2 ref = *reinterpret_cast<const uint2*>(d.rows[rcur] + (size_t)((s >> 1) - 1) * ld + i0);
+            const unsigned rr[2] = { ref.x, ref.y };
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const double* base = d.G > 1 ? reinterpret_cast<const double*>(d.peer[rr[q] >> 28] + d.o_lm[buf]) : d.lm[buf];
+                const double* p = base + lbase + (rr[q] & 0x0FFFFFFFu);
+                L[q].x = p[0]; L[q].y = p[ld]; L[q].c00 = p[2 * ld]; L[q].c01 = p[3 * ld]; L[q].c10 = p[4 * ld]; L[q].c11 = p[5 * ld];
+            }
+        }
+    }
+    // ---- predict_particle + motion_model fs1.rs:70-77,123-137: warp 0, in place, shared with the other warps ----
+    if (wj == 0) {
+        double2 X = *reinterpret_cast<const double2*>(d.px[cur] + i0), Y = *reinterpret_cast<const double2*>(d.py[cur] + i0);
+        double2 A = *reinterpret_cast<const double2*>(d.pyaw[cur] + i0);
+        if (flags & 1) {
+            double xs[2] = { X.x, X.y }, ys[2] = { Y.x, Y.y }, as[2] = { A.x, A.y };
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                double z0, z1;
+                pfc_normal_pair(pfc_rng_block(seed, PFC_STREAM_FS_PREDICT, call, (uint64_t)d.off + i0 + q), &z0, &z1);
+                const double un0 = u0 + z0 * sq0;                      // fs1.rs:129
+                const double un1 = u1 + z1 * sq1;                      // fs1.rs:130
+                double s, c;
+                pfc_sincos(as[q], &s, &c);
+                xs[q] = xs[q] + un0 * dt * c;                          // motion_model fs1.rs:73-75
+                ys[q] = ys[q] + un0 * dt * s;
+                as[q] = fs_normalize_angle(as[q] + un1 * dt);
+            }
+            X = make_double2(xs[0], xs[1]); Y = make_double2(ys[0], ys[1]); A = make_double2(as[0], as[1]);
+            *reinterpret_cast<double2*>(d.px[cur] + i0) = X; *reinterpret_cast<double2*>(d.py[cur] + i0) = Y;
+            *reinterpret_cast<double2*>(d.pyaw[cur] + i0) = A;
+        }
+        *reinterpret_cast<double2*>(s_pose + 2 * lane) = X; *reinterpret_cast<double2*>(s_pose + 64 + 2 * lane) = Y;
+        *reinterpret_cast<double2*>(s_pose + 128 + 2 * lane) = A;
+    }
+    __syncthreads();
+    if (k_obs > 0) {
+        const double2 X = *reinterpret_cast<const double2*>(s_pose + 2 * lane), Y = *reinterpret_cast<const double2*>(s_pose + 64 + 2 * lane);
+        const double2 A = *reinterpret_cast<const double2*>(s_pose + 128 + 2 * lane);
+        const double px[2] = { X.x, X.y }, py[2] = { Y.x, Y.y }, pyaw[2] = { A.x, A.y };
+        double lik[2] = { 1.0, 1.0 };
+        int ok[2];
+        fs_update_landmark_fastw<2>(L, px, py, pyaw, ob.d, ob.angle, r00, r11, lik, ok);
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+            if (!ok[q] && i0 + q < d.n) lik[q] = fs3_update_slow(&L[q], px[q], py[q], pyaw[q], ob.d, ob.angle, r00, r11);
+        double* o = d.lm[ident ? buf : (buf ^ 1)] + lbase + i0;       // own columns; the other buffer when read through a row
+        *reinterpret_cast<double2*>(o) = make_double2(L[0].x, L[1].x);
+        *reinterpret_cast<double2*>(o + ld) = make_double2(L[0].y, L[1].y);
+        *reinterpret_cast<double2*>(o + 2 * ld) = make_double2(L[0].c00, L[1].c00);
+        *reinterpret_cast<double2*>(o + 3 * ld) = make_double2(L[0].c01, L[1].c01);
+        *reinterpret_cast<double2*>(o + 4 * ld) = make_double2(L[0].c10, L[1].c10);
+        *reinterpret_cast<double2*>(o + 5 * ld) = make_double2(L[0].c11, L[1].c11);
+        *reinterpret_cast<double2*>(s_lik + wj * 64 + 2 * lane) = make_double2(lik[0], lik[1]);
+    }
+    __syncthreads();
+    // ---- weights: w = (((w * l_0) * l_1) ...) in observation order (fs1.rs:181 inside the loops fs1.rs:250-256) ----
+    if (wj == 0) {
+        const double* wsrc = (flags & 1) ? d.w : d.wraw[par] + d.off;
+        const double2 W = *reinterpret_cast<const double2*>(wsrc + i0);
+        double w0 = W.x, w1 = W.y;
+        for (int j = 0; j < k_obs; ++j) {
+            const double2 l = *reinterpret_cast<const double2*>(s_lik + j * 64 + 2 * lane);
+            w0 = w0 * l.x; w1 = w1 * l.y;
+        }
+        const bool v0 = i0 < d.n, v1 = i0 + 1 < d.n;
+        if (!v0) w0 = 0.0;
+        if (!v1) w1 = 0.0;
+        const double psum = warp_sum(w0 + w1);                           // honest (tree-order) sum: steers x3_classify only
+        for (int g = 0; g < d.G; ++g) {
+            double* wr = (d.G > 1 ? reinterpret_cast<double*>(d.peer[g] + d.o_wraw[par]) : d.wraw[par]) + d.off;
+            if (v1) *reinterpret_cast<double2*>(wr + i0) = make_double2(w0, w1);
+            else if (v0) wr[i0] = w0;
+            if (lane == 0) {
+                double* pp = d.G > 1 ? reinterpret_cast<double*>(d.peer[g] + d.o_part[par]) : d.part[par];
+                pp[(size_t)d.rank * d.npart + blockIdx.x] = psum;
+            }
+        }
+    }
+    // ---- completion: the last CTA does the lazy-clone bookkeeping and tells the peers ----
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (d.G > 1) __threadfence_system(); else __threadfence();
+        s_last = (atomicAdd(&st->ekf_done, 1u) + 1u == gridDim.x) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int j = threadIdx.x; j < k_obs; j += blockDim.x) {               // updated landmarks: own columns of the other buffer
+        const int l = po.o[j].lm_id, s = d.lmst[l];
+        if (s >> 1) d.lmst[l] = (s & 1) ^ 1;
+    }
+    if (threadIdx.x == 0) st->ekf_done = 0;
+    if ((flags & 2) && d.G > 1) fs3_signal_peers(d, 0, step + 1u);
+}
+
+// =====================================================================================================================
+// post kernel
+// =====================================================================================================================
+template <int NT>
+struct Fs3Sh {
+    double sd[NT / 32]; unsigned long long su[NT / 32]; int si[NT / 32];
+    unsigned long long tP[FS3_MAX_TILES], tPoff[FS3_MAX_TILES];
+    int tD[FS3_MAX_TILES], tDoff[FS3_MAX_TILES];
+    unsigned long long eP[FS3_ENT_CAP]; double eV[FS3_ENT_CAP]; int eL[FS3_ENT_CAP];
+    double bef[FS3_ENT_CAP], aft[FS3_ENT_CAP];
+    double total, tbase, bcast;
+    unsigned long long Ptot;
+    int D, fail, last;
+    unsigned rowbits[32]; unsigned short rowlist[1024]; int nrows, newrow;
+};
+
+__device__ __forceinline__ void fs3_grid_sync(Fs3State* st, unsigned nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned gen = ld_acquire_gpu(&st->bar_gen);
+        __threadfence();
+        if (atomicAdd(&st->bar_count, 1u) + 1u == nblocks) {
+            st->bar_count = 0;
+            __threadfence();
+            atomicAdd(&st->bar_gen, 1u);
+        } else {
+            unsigned spins = 0;
+            while (ld_acquire_gpu(&st->bar_gen) == gen) { if (++spins > FS3_SPIN_LIMIT) { st->err = 1; break; } }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// exclusive prefix over the block's threads (thread order) of a double; *tot = block total (tree order, same in every CTA)
+template <int NT>
+__device__ __forceinline__ double fs3_scan_d(double x, double* tot, double* sm) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double inc = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = y + inc; }
+    double ex = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) ex = 0.0;
+    __syncthreads();
+    if (lane == 31) sm[wid] = inc;
+    __syncthreads();
+    double woff = 0.0, t = 0.0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) { const double s = sm[w]; if (w < wid) woff += s; t += s; }
+    *tot = t;
+    return woff + ex;
+}
+// the same for a (u64 increment sum, int count) pair
+template <int NT>
+__device__ __forceinline__ void fs3_scan_ui(unsigned long long p, int c, unsigned long long* pex, int* cex, unsigned long long* ptot, int* ctot,
+                                            unsigned long long* smu, int* smi) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned long long ip = p; int ic = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, ip, o); const int z = __shfl_up_sync(0xffffffffu, ic, o);
+        if (lane >= o) { ip += y; ic += z; }
+    }
+    __syncthreads();
+    if (lane == 31) { smu[wid] = ip; smi[wid] = ic; }
+    __syncthreads();
+    unsigned long long wp = 0, tp = 0; int wc = 0, tc = 0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) { const unsigned long long a = smu[w]; const int b = smi[w]; if (w < wid) { wp += a; wc += b; } tp += a; tc += b; }
+    *pex = wp + ip - p; *cex = wc + ic - c; *ptot = tp; *ctot = tc;
+}
+template <int NT>
+__device__ __forceinline__ double fs3_block_sum(double x, double* sm) {    // tree order, identical in every CTA; valid in all threads
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    x = warp_sum(x);
+    __syncthreads();
+    if (lane == 0) sm[wid] = x;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) t += sm[w];
+    return t;
+}
+
+// value i of the sum `slot`, recomputed from global memory (serial walks only)
+__device__ __forceinline__ double fs3_value(const Fs3Dev& d, int slot, size_t i, int par, double S2, double r0, double inv) {
+    if (slot == 0) return __ldcg(d.wraw[par] + i);
+    const double w = slot == 4 ? 0.0 : __ldcg(d.wn_all + i);
+    if (slot == 1) return w * w;
+    if (slot == 2) return w;
+    if (slot == 3) return S2 > 0.0 ? w / S2 : w;
+    return i == 0 ? r0 : inv;
+}
+
+// One exact sequential sum over the n_glob values held tile-wise in shared memory (thread t owns values t*K .. t*K+K-1 of its
+// tile, stored at vals[k*NT + t]).  toff = approximate sum of everything in front of this tile.  Returns the exact total
+// (identical in every CTA); with out != nullptr also stores the exact inclusive prefix of every value to out[global index].
+// Contains ONE grid barrier.
+template <int NT>
+__device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const double* vals, unsigned K, unsigned nt, double toff, int slot,
+                                        unsigned m32, double* out, int par, double S2, double r0, double inv, double extraQ) {
+    const int tid = threadIdx.x;
+    const unsigned b = blockIdx.x;
+    const size_t T = (size_t)NT * K;
+    Fs3State* st = d.st;
+    // ---- approximate prefixes, classification, tile aggregate ----
+    double ts = 0.0; bool bad = false;
+    for (unsigned k = 0; k < K; ++k) { const double v = vals[k * NT + tid]; ts += v; if (!(v >= 0.0) || !(v <= 1.7976931348623157e308)) bad = true; }
+    double btot;
+    const double excl = fs3_scan_d<NT>(ts, &btot, sh.sd);
+    unsigned long long P = 0; int nd = 0;
+    {
+        double a = toff + excl;
+        for (unsigned k = 0; k < K; ++k) {
+            const double v = vals[k * NT + tid], a1 = a + v;
+            unsigned long long inc; int lvl;
+            if (x3_classify(v, a, a1, m32, &inc, &lvl)) nd++; else P += inc;
+            a = a1;
+        }
+    }
+    unsigned long long Pex, Ptile; int dex, ndtile;
+    fs3_scan_ui<NT>(P, nd, &Pex, &dex, &Ptile, &ndtile, sh.su, sh.si);
+    const size_t sb = (size_t)slot * FS3_MAX_TILES + b;
+    if (nd > 0 && ndtile <= FS3_ENT_TILE) {                 // rare: itemise this thread's dirty values
+        double a = toff + excl; unsigned long long Pr = Pex; int e = dex;
+        for (unsigned k = 0; k < K; ++k) {
+            const double v = vals[k * NT + tid], a1 = a + v;
+            unsigned long long inc; int lvl;
+            if (x3_classify(v, a, a1, m32, &inc, &lvl)) { const size_t o = sb * FS3_ENT_TILE + e; d.entP[o] = Pr; d.entV[o] = v; d.entL[o] = lvl; e++; }
+            else Pr += inc;
+            a = a1;
+        }
+    }
+    if (bad) d.flagsg[slot] = 1;
+    if (tid == 0) { d.tileP[sb] = Ptile; d.tileD[sb] = ndtile <= FS3_ENT_TILE ? ndtile : -1; if (slot == 0) d.tileQ[b] = extraQ; }
+    fs3_grid_sync(st, nt);
+    // ---- chain: every CTA evaluates it (tens of entries) ----
+    if (tid == 0) { sh.fail = __ldcg(d.flagsg + slot); }
+    __syncthreads();
+    {
+        unsigned long long tp = 0; int td = 0;
+        if ((unsigned)tid < nt) { tp = __ldcg(d.tileP + (size_t)slot * FS3_MAX_TILES + tid); td = __ldcg(d.tileD + (size_t)slot * FS3_MAX_TILES + tid); }
+        if (td < 0) { sh.fail = 1; td = 0; }
+        unsigned long long pex, ptot; int cex, ctot;
+        fs3_scan_ui<NT>(tp, td, &pex, &cex, &ptot, &ctot, sh.su, sh.si);
+        if ((unsigned)tid < nt) { sh.tPoff[tid] = pex; sh.tDoff[tid] = cex; sh.tD[tid] = td; }
+        if (tid == 0) { sh.Ptot = ptot; sh.D = ctot; if (ctot > FS3_ENT_CAP) sh.fail = 1; }
+    }
+    __syncthreads();
+    const int D = sh.D;
+    if (!sh.fail) {
+        if ((unsigned)tid < nt) {
+            const int c = sh.tD[tid], o0 = sh.tDoff[tid];
+            const size_t g0 = ((size_t)slot * FS3_MAX_TILES + tid) * FS3_ENT_TILE;
+            for (int e = 0; e < c; ++e) { sh.eP[o0 + e] = sh.tPoff[tid] + __ldcg(d.entP + g0 + e); sh.eV[o0 + e] = __ldcg(d.entV + g0 + e); sh.eL[o0 + e] = __ldcg(d.entL + g0 + e); }
+        }
+        __syncthreads();
+        if (tid == 0) {                                       // the serial part: one integer add + one FP add per dirty value
+            double s = 0.0; unsigned long long prev = 0;
+            for (int o = 0; o < D; ++o) {
+                const unsigned long long p = sh.eP[o];
+                sh.bef[o] = s;
+                s = pfc_u2d(pfc_d2u(s) + (p - prev)) + sh.eV[o];
+                sh.aft[o] = s; prev = p;
+            }
+            int ok = 1;
+            sh.total = x3_apply(s, sh.Ptot - prev, -1, &ok);
+            if (!ok) sh.fail = 1;
+            if (b == 0) st->dirty_last = D;
+        }
+        __syncthreads();
+        for (int o = tid; o < D; o += NT) {                   // certificates of the clean runs, in parallel
+            const unsigned long long dp = sh.eP[o] - (o ? sh.eP[o - 1] : 0ull);
+            int ok = 1;
+            (void)x3_apply(sh.bef[o], dp, sh.eL[o], &ok);
+            if (!ok) sh.fail = 1;
+        }
+        __syncthreads();
+    }
+    if (sh.fail) {                                            // exact by construction: one thread walks all values in order
+        if (tid == 0) {
+            double s = 0.0;
+            const size_t lo = (size_t)b * T;
+            for (size_t i = 0; i < d.n_glob; ++i) { if (i == lo) sh.tbase = s; s = s + fs3_value(d, slot, i, par, S2, r0, inv); }
+            if (lo >= d.n_glob) sh.tbase = s;
+            sh.total = s;
+            if (b == 0) { st->serial_walks += 1; }
+            if (out) {
+                double c = sh.tbase;
+                for (size_t i = lo; i < lo + T && i < d.n_glob; ++i) { c = c + fs3_value(d, slot, i, par, S2, r0, inv); out[i] = c; }
+            }
+        }
+        __syncthreads();
+        return sh.total;
+    }
+    if (out) {                                                // exact inclusive prefix of every value of this tile
+        int ko = sh.tDoff[b] + dex;
+        double base = ko ? sh.aft[ko - 1] : 0.0;
+        unsigned long long Pb = ko ? sh.eP[ko - 1] : 0ull, Pc = sh.tPoff[b] + Pex;
+        double a = toff + excl;
+        int ok = 1;
+        const size_t g0 = (size_t)b * T + (size_t)tid * K;
+        for (unsigned k = 0; k < K; ++k) {
+            const double v = vals[k * NT + tid], a1 = a + v;
+            unsigned long long inc; int lvl; double c;
+            if (x3_classify(v, a, a1, m32, &inc, &lvl)) { base = sh.aft[ko]; Pb = sh.eP[ko]; ko++; c = base; }
+            else { Pc += inc; c = x3_apply(base, Pc - Pb, inc ? lvl : -1, &ok); }
+            if (g0 + k < d.n_glob) out[g0 + k] = c;
+            a = a1;
+        }
+        if (!ok) atomicAdd(&st->cert_fail, 1);
+    }
+    return sh.total;
+}
+
+#define FS3_TRACE(k) do { if (d.trace && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); d.trace[k] += t__ - t_prev; t_prev = t__; } } while (0)
+
+// lower bound of r in the exact CDF, clamped: "while r > cum_sum[j+1] && j < n-1 { j += 1 }" (fs1.rs:224-226) with r and j both
+// non-decreasing over the slots, i.e. the first j with c_j >= r.  Searched inside [lo, hi) (c_{lo-1} < r guaranteed by the caller).
+__device__ __forceinline__ unsigned fs3_lower_bound(const double* c, unsigned lo, unsigned hi, double r) {
+    while (lo < hi) { const unsigned mid = lo + ((hi - lo) >> 1); if (c[mid] < r) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+// warp-cooperative 32-way search of one r over [0, n): returns the lower bound (all lanes)
+__device__ __forceinline__ unsigned fs3_warp_search(const double* c, unsigned n, double r) {
+    const int lane = threadIdx.x & 31;
+    unsigned lo = 0, hi = n;                                  // answer in [lo, hi]
+    while (hi - lo > 32) {
+        const unsigned step = (hi - lo + 32) / 33;            // probes lo + (lane+1)*step - 1
+        const unsigned long long pi = (unsigned long long)lo + (unsigned long long)(lane + 1) * step - 1ull;
+        const bool below = pi < hi ? (c[pi] < r) : false;     // monotone: a prefix of lanes is "below"
+        const unsigned mask = __ballot_sync(0xffffffffu, below);
+        const int cnt = __popc(mask);
+        const unsigned nlo = cnt ? lo + (unsigned)cnt * step : lo;
+        const unsigned long long nh = (unsigned long long)lo + (unsigned long long)(cnt + 1) * step - 1ull;
+        hi = nh < hi ? (unsigned)nh : hi;
+        lo = nlo;
+    }
+    {
+        const unsigned pi = lo + (unsigned)lane;
+        const bool below = pi < hi ? (c[pi] < r) : false;
+        lo += (unsigned)__popc(__ballot_sync(0xffffffffu, below));
+    }
+    return lo;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 1)
+fs3_post_kernel(const __grid_constant__ Fs3Dev d, double nth, uint64_t seed, unsigned step, unsigned K, unsigned m32, int log2n) {
+    pf_grid_dep_sync();
+    extern __shared__ double vals[];                          // [K][NT]
+    __shared__ Fs3Sh<NT> sh;
+    Fs3State* st = d.st;
+    const int tid = threadIdx.x;
+    const unsigned b = blockIdx.x, nt = gridDim.x;
+    const size_t T = (size_t)NT * K, ng = d.n_glob;
+    const int par = (int)(step & 1u);
+    unsigned long long t_prev = 0;
+    if (d.trace && b == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_prev));
+    if (d.G > 1) {                                            // every rank's weights of this step are in my copy
+        if (tid == 0) fs3_wait_peers(d, 0, step + 1u);
+        __syncthreads();
+    }
+    // ---- load this tile's weights; approximate sum of everything in front of the tile from the 64-particle partials ----
+    const size_t g0 = (size_t)b * T + (size_t)tid * K;
+    double q = 0.0;
+    for (unsigned k = 0; k < K; ++k) { const double v = g0 + k < ng ? __ldcg(d.wraw[par] + g0 + k) : 0.0; vals[k * NT + tid] = v; q += v * v; }
+    double toff;
+    {
+        // partials are indexed rank * npart + cta; global slot i belongs to partial (i / n) * npart + (i % n) / 64
+        const size_t first = (size_t)b * T;                   // a multiple of 64 (and of n when it crosses ranks: n % T or T % n == 0 is NOT required)
+        double acc = 0.0;
+        const size_t np_total = (size_t)d.G * d.npart;
+        for (size_t p = tid; p < np_total; p += NT) {
+            const size_t slot0 = (p / d.npart) * (size_t)d.n + (p % d.npart) * 64;      // first global slot of partial p
+            if (slot0 < first) acc += __ldcg(d.part[par] + p);
+        }
+        toff = fs3_block_sum<NT>(acc, sh.sd);
+    }
+    const double qtile = fs3_block_sum<NT>(q, sh.sd);
+    FS3_TRACE(0);
+    // ---------------- S = sum w_raw (normalize_weights fs1.rs:196-203) ----------------
+    const double S = fs3_xsum<NT>(d, sh, vals, K, nt, toff, 0, m32, nullptr, par, 0.0, 0.0, 0.0, qtile);
+    FS3_TRACE(1);
+    // w = w_raw / S; best particle of the tile (LAST maximum, fs1.rs:269-274)
+    double bw = -1.0; unsigned bi = 0;
+    for (unsigned k = 0; k < K; ++k) {
+        double v = vals[k * NT + tid];
+        if (S > 0.0) v = v / S;
+        vals[k * NT + tid] = v;
+        const size_t i = g0 + k;
+        if (i < ng) {
+            d.wn_all[i] = v;
+            if (i >= d.off && i < (size_t)d.off + d.n) d.w[i - d.off] = v;
+            if (v >= bw) { bw = v; bi = (unsigned)i; }
+        }
+    }
+    {   // block arg-max with "last wins among equals"
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ow = __shfl_xor_sync(0xffffffffu, bw, o); const unsigned oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ow > bw || (ow == bw && oi > bi)) { bw = ow; bi = oi; }
+        }
+        __syncthreads();
+        if ((tid & 31) == 0) { sh.sd[tid >> 5] = bw; sh.si[tid >> 5] = (int)bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < NT / 32; ++w) { const double ow = sh.sd[w]; const unsigned oi = (unsigned)sh.si[w]; if (ow > bw || (ow == bw && oi > bi)) { bw = ow; bi = oi; } }
+            d.tileBw[b] = bw; d.tileBi[b] = bi;
+        }
+    }
+    // ---------------- gate: neff = 1 / sum w^2 < NTH (compute_neff fs1.rs:186-193, fs1.rs:262-263) ----------------
+    // Only the DECISION feeds back into the state.  Q is first taken from the tree-order sums of w_raw^2 published with the
+    // aggregates of S: sum (w_raw_i / S)^2 differs from the reference's sequential sum of fl(w_raw_i / S)^2 by at most
+    // (n + 64) 2^-51 relatively; only when neff lands that close to NTH is the exact sequential sum walked.
+    double Q;
+    {
+        const double qs = (unsigned)tid < nt ? __ldcg(d.tileQ + tid) : 0.0;
+        Q = fs3_block_sum<NT>(qs, sh.sd);
+        if (S > 0.0) Q = (Q / S) / S;
+    }
+    double neff = Q > 0.0 ? 1.0 / Q : 0.0;
+    const double slack = 16.0 * (double)(ng + 64) * 2.220446049250313e-16;
+    if (!(fabs(neff - nth) > slack * fmax(fabs(nth), fabs(neff)))) {     // rare; the same decision in every CTA
+        fs3_grid_sync(st, nt);                                 // wn_all is complete
+        if (tid == 0) {
+            double s = 0.0;
+            for (size_t i = 0; i < ng; ++i) { const double w = __ldcg(d.wn_all + i); s = s + w * w; }
+            sh.bcast = s;
+            if (b == 0) st->border_cnt += 1;
+        }
+        __syncthreads();
+        Q = sh.bcast;
+        neff = Q > 0.0 ? 1.0 / Q : 0.0;
+    }
+    const int gate = neff < nth ? 1 : 0;
+    FS3_TRACE(2);
+    double S2 = 0.0, r0 = 0.0;
+    const double inv = 1.0 / (double)ng;
+    if (gate) {
+        // ---------------- resample() re-normalises first (fs1.rs:207) ----------------
+        const double toff2 = S > 0.0 ? toff / S : toff;
+        S2 = fs3_xsum<NT>(d, sh, vals, K, nt, toff2, 2, m32, nullptr, par, 0.0, 0.0, 0.0, 0.0);
+        FS3_TRACE(3);
+        if (S2 > 0.0) for (unsigned k = 0; k < K; ++k) vals[k * NT + tid] = vals[k * NT + tid] / S2;
+        // ---------------- cum_sum fs1.rs:213-216 ----------------
+        const double toff3 = S2 > 0.0 ? toff2 / S2 : toff2;
+        (void)fs3_xsum<NT>(d, sh, vals, K, nt, toff3, 3, m32, d.cum_all, par, S2, 0.0, 0.0, 0.0);
+        FS3_TRACE(4);
+        // ---------------- the comb r, r + 1/n, ... accumulated sequentially (fs1.rs:219-230) ----------------
+        {
+            const double u01 = pfc_u01_52(pfc_blk_u64(pfc_rng_block(seed, PFC_STREAM_FS_RESAMPLE, st->resamples, 0), 0));
+            r0 = u01 * (inv - 0.0) + 0.0;                      // Uniform::new(0, 1/n).sample
+        }
+        if (log2n < 0) {                                       // n not a power of two: every add rounds -> exact scan
+            for (unsigned k = 0; k < K; ++k) { const size_t i = g0 + k; vals[k * NT + tid] = i < ng ? (i == 0 ? r0 : inv) : 0.0; }
+            const double toff4 = b == 0 ? 0.0 : r0 + ((double)((size_t)b * T) - 1.0) * inv;
+            __syncthreads();
+            (void)fs3_xsum<NT>(d, sh, vals, K, nt, toff4, 4, m32, d.rcomb_all, par, S2, r0, inv, 0.0);
+        }
+        fs3_grid_sync(st, nt);                                 // the whole CDF (and comb) is visible
+        FS3_TRACE(5);
+        // ---------------- index walk, pose clone, lazy map clone for this CTA's share of the local slots ----------------
+        // live rows: one bit per row some landmark still reads through; identity landmarks get ONE new row
+        if (tid < 32) sh.rowbits[tid] = 0u;
+        if (tid == 0) sh.newrow = -1;
+        __syncthreads();
+        int any_ident = 0;
+        for (unsigned l = tid; l < d.m; l += NT) { const int s = d.lmst[l]; if (s >> 1) atomicOr(&sh.rowbits[((s >> 1) - 1) >> 5], 1u << (((s >> 1) - 1) & 31)); else any_ident = 1; }
+        any_ident = __syncthreads_or(any_ident);
+        if (tid < 32) {
+            const unsigned bits = sh.rowbits[tid];
+            int cnt = __popc(bits), incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += y; }
+            int pos = incl - cnt;
+            for (unsigned x = bits; x; x &= x - 1) sh.rowlist[pos++] = (unsigned short)(tid * 32 + __ffs(x) - 1);
+            if (tid == 31) sh.nrows = incl;
+            // first free row id (m >= 1 rows exist; with an identity landmark at most m - 1 rows are live)
+            const unsigned fr = ~bits;
+            const unsigned has = __ballot_sync(0xffffffffu, fr != 0u);
+            if (any_ident && tid == __ffs(has) - 1) sh.newrow = tid * 32 + __ffs(fr) - 1;
+        }
+        __syncthreads();
+        const int nrows = sh.nrows, newrow = sh.newrow;
+        const int cur = st->cur, rcur = st->rcur;
+        const double ninv = (double)ng;
+        const unsigned per = (d.n + nt - 1) / nt;              // local slots per CTA
+        const unsigned t_lo = b * per, t_hi = min(d.n, t_lo + per);
+        const double* cdf = d.cum_all;
+        for (unsigned tb = t_lo + (tid & ~31); tb < t_hi; tb += NT) {       // a warp takes 32 consecutive slots
+            const unsigned t = tb + (tid & 31);
+            const size_t tg = (size_t)d.off + t;
+            const bool valid = t < t_hi;
+            double r = 0.0;
+            if (valid) r = log2n >= 0 ? x3_comb_pow2(r0, inv, ninv, tg) : d.rcomb_all[tg];
+            // the warp's first and last slot bracket every lane's answer
+            const double r_first = __shfl_sync(0xffffffffu, r, 0);
+            const int lastlane = min(31, (int)(t_hi - 1 - tb));
+            const double r_last = __shfl_sync(0xffffffffu, r, lastlane);
+            const unsigned jlo = fs3_warp_search(cdf, (unsigned)ng, r_first);
+            const unsigned jhi = fs3_warp_search(cdf, (unsigned)ng, r_last);
+            if (!valid) continue;
+            unsigned j = fs3_lower_bound(cdf, jlo, jhi, r);
+            if (j >= ng) j = (unsigned)ng - 1;
+            d.idx[t] = j;
+            const int jr = (int)(j / d.n); const unsigned jc = j % d.n;                 // owner rank and column of the ancestor
+            const double* sx = d.G > 1 ? reinterpret_cast<const double*>(d.peer[jr] + d.o_px[cur]) : d.px[cur];
+            const double* sy = d.G > 1 ? reinterpret_cast<const double*>(d.peer[jr] + d.o_py[cur]) : d.py[cur];
+            const double* sa = d.G > 1 ? reinterpret_cast<const double*>(d.peer[jr] + d.o_pyaw[cur]) : d.pyaw[cur];
+            d.px[cur ^ 1][t] = sx[jc]; d.py[cur ^ 1][t] = sy[jc]; d.pyaw[cur ^ 1][t] = sa[jc];     // particles[j].clone() fs1.rs:227
+            d.w[t] = inv;                                                                // fs1.rs:228
+            const unsigned* srows = d.G > 1 ? reinterpret_cast<const unsigned*>(d.peer[jr] + d.o_rows[rcur]) : d.rows[rcur];
+            unsigned* drows = d.rows[rcur ^ 1];
+            for (int x = 0; x < nrows; ++x) { const size_t ro = (size_t)sh.rowlist[x] * d.ld; drows[ro + t] = srows[ro + jc]; }
+            if (newrow >= 0) drows[(size_t)newrow * d.ld + t] = fs3_ref(jr, jc);
+        }
+        FS3_TRACE(6);
+    }
+    // ---------------- completion: the last CTA flips the state, writes the record, tells the peers ----------------
+    __syncthreads();
+    if (tid == 0) { __threadfence(); sh.last = (atomicAdd(&st->post_done, 1u) + 1u == nt) ? 1 : 0; }
+    __syncthreads();
+    if (!sh.last) return;
+    __threadfence();
+    if (gate) {
+        const int newrow = sh.newrow;
+        for (unsigned l = tid; l < d.m; l += NT) { const int s = d.lmst[l]; if ((s >> 1) == 0) d.lmst[l] = (s & 1) | ((newrow + 1) << 1); }
+    }
+    if (tid < FS3_SLOTS) d.flagsg[tid] = 0;
+    if (tid < 32) {
+        // best particle: the last maximum over the tiles (no resample) / the last slot (after a resample every weight is 1/n)
+        double bw2 = -1.0; unsigned bi2 = 0;
+        for (unsigned x = tid; x < nt; x += 32) { const double ow = __ldcg(d.tileBw + x); const unsigned oi = __ldcg(d.tileBi + x); if (ow > bw2 || (ow == bw2 && oi > bi2)) { bw2 = ow; bi2 = oi; } }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ow = __shfl_xor_sync(0xffffffffu, bw2, o); const unsigned oi = __shfl_xor_sync(0xffffffffu, bi2, o);
+            if (ow > bw2 || (ow == bw2 && oi > bi2)) { bw2 = ow; bi2 = oi; }
+        }
+        unsigned src = bi2;                                    // slot whose pose (in the buffer live BEFORE the flip) is reported
+        if (gate) {
+            bi2 = (unsigned)ng - 1; bw2 = inv;
+            const double rl = log2n >= 0 ? x3_comb_pow2(r0, inv, (double)ng, ng - 1) : d.rcomb_all[ng - 1];
+            src = fs3_warp_search(d.cum_all, (unsigned)ng, rl);
+            if (src >= ng) src = (unsigned)ng - 1;
+        }
+        if (tid == 0) {
+            const int cur = st->cur;
+            const int jr = (int)(src / d.n); const unsigned jc = src % d.n;
+            const double* sx = d.G > 1 ? reinterpret_cast<const double*>(d.peer[jr] + d.o_px[cur]) : d.px[cur];
+            const double* sy = d.G > 1 ? reinterpret_cast<const double*>(d.peer[jr] + d.o_py[cur]) : d.py[cur];
+            const double* sa = d.G > 1 ? reinterpret_cast<const double*>(d.peer[jr] + d.o_pyaw[cur]) : d.pyaw[cur];
+            Fs3Rec* rec = d.rec;
+            rec->best_idx = bi2; rec->best_w = bw2; rec->bx = sx[jc]; rec->by = sy[jc]; rec->byaw = sa[jc];
+            rec->neff = neff; rec->gate = gate; rec->err = st->err;
+            st->S = S; st->Q = Q; st->neff = neff; st->S2 = S2; st->r0 = r0; st->gate = gate;
+            if (gate) { st->cur ^= 1; st->rcur ^= 1; st->resamples += 1; }
+            st->post_done = 0;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long*>(&rec->seq) = (unsigned long long)step + 1ull;
+        }
+    }
+    __syncthreads();
+    if (d.G > 1) fs3_signal_peers(d, 1, step + 1u);
+}
+
+// =====================================================================================================================
+// set-up / transfer kernels
+// =====================================================================================================================
+// column that holds landmark l of local slot i: own column, or through the landmark's row (maybe on another rank)
+__device__ __forceinline__ const double* fs3_lm_src(const Fs3Dev& d, size_t l, unsigned i, int s, int rcur) {
+    const int buf = s & 1;
+    if ((s >> 1) == 0) return d.lm[buf] + l * 6 * d.ld + i;
+    const unsigned ref = d.rows[rcur][(size_t)((s >> 1) - 1) * d.ld + i];
+    const double* base = d.G > 1 ? reinterpret_cast<const double*>(d.peer[ref >> 28] + d.o_lm[buf]) : d.lm[buf];
+    return base + l * 6 * d.ld + (ref & 0x0FFFFFFFu);
+}
+// AoS <-> SoA converters for upload/download (pose_w: n x 4 = (weight, x, y, yaw); lm: n x m x 6 particle-major like Vec<Particle>)
+__global__ void __launch_bounds__(256) fs3_unpack_pose_kernel(const __grid_constant__ Fs3Dev d, const double* pose_w) {
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= d.n) return;
+    const int cur = d.st->cur;
+    d.w[i] = pose_w[4 * (size_t)i]; d.px[cur][i] = pose_w[4 * (size_t)i + 1]; d.py[cur][i] = pose_w[4 * (size_t)i + 2]; d.pyaw[cur][i] = pose_w[4 * (size_t)i + 3];
+}
+__global__ void __launch_bounds__(256) fs3_pack_pose_kernel(const __grid_constant__ Fs3Dev d, double* pose_w) {
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= d.n) return;
+    const int cur = d.st->cur;
+    pose_w[4 * (size_t)i] = d.w[i]; pose_w[4 * (size_t)i + 1] = d.px[cur][i]; pose_w[4 * (size_t)i + 2] = d.py[cur][i]; pose_w[4 * (size_t)i + 3] = d.pyaw[cur][i];
+}
+__global__ void __launch_bounds__(256) fs3_unpack_lm_kernel(const __grid_constant__ Fs3Dev d, const double* aos, size_t i0, size_t cnt) {
+    const size_t e = (size_t)blockIdx.x * 256 + threadIdx.x, tot = cnt * d.m * 6;
+    if (e >= tot) return;
+    const size_t ip = e / ((size_t)d.m * 6), rem = e % ((size_t)d.m * 6), l = rem / 6, f = rem % 6;
+    d.lm[0][(l * 6 + f) * d.ld + i0 + ip] = aos[e];
+}
+__global__ void __launch_bounds__(256) fs3_pack_lm_kernel(const __grid_constant__ Fs3Dev d, double* aos, size_t i0, size_t cnt) {
+    const size_t e = (size_t)blockIdx.x * 256 + threadIdx.x, tot = cnt * d.m * 6;
+    if (e >= tot) return;
+    const size_t ip = e / ((size_t)d.m * 6), rem = e % ((size_t)d.m * 6), l = rem / 6, f = rem % 6;
+    aos[e] = fs3_lm_src(d, l, (unsigned)(i0 + ip), d.lmst[l], d.st->rcur)[f * d.ld];     // materialise through the rows
+}
+__global__ void fs3_lmst_reset_kernel(const __grid_constant__ Fs3Dev d) {        // every landmark: own columns of buffer 0
+    for (unsigned l = blockIdx.x * blockDim.x + threadIdx.x; l < d.m; l += gridDim.x * blockDim.x) d.lmst[l] = 0;
+}
+// create_particles fs1.rs:302-306: Particle::new (fs1.rs:54-62) with Landmark::new (fs1.rs:34-40)
+__global__ void __launch_bounds__(256) fs3_init_kernel(const __grid_constant__ Fs3Dev d, double init_weight) {
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= d.n) return;
+    d.w[i] = init_weight;
+    d.px[0][i] = 0.0; d.py[0][i] = 0.0; d.pyaw[0][i] = 0.0;
+    for (size_t l = 0; l < d.m; ++l) {
+        double* p = d.lm[0] + l * 6 * d.ld + i;
+        p[0] = 0.0; p[d.ld] = 0.0; p[2 * (size_t)d.ld] = 1000.0; p[3 * (size_t)d.ld] = 0.0; p[4 * (size_t)d.ld] = 0.0; p[5 * (size_t)d.ld] = 1000.0;
+    }
+}
+// pfgpu_fs_seed_map: initialised map for benchmarks/tests (see include/pfgpu.h)
+__global__ void __launch_bounds__(256) fs3_seed_pose_kernel(const __grid_constant__ Fs3Dev d, double x, double y, double yaw) {
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= d.n) return;
+    const int cur = d.st->cur;
+    d.px[cur][i] = x; d.py[cur][i] = y; d.pyaw[cur][i] = yaw;
+    d.w[i] = 1.0 / (double)d.n_glob;
+}
+__global__ void __launch_bounds__(256) fs3_seed_lm_kernel(const __grid_constant__ Fs3Dev d, const double* lm_xy, double sigma, double cov0, uint64_t seed) {
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    const size_t l = blockIdx.y;
+    if (i >= d.n) return;
+    double z0, z1;
+    pfc_normal_pair(pfc_rng_block(seed, PFC_STREAM_INIT_A, 0, ((uint64_t)d.off + i) * d.m + l), &z0, &z1);
+    double* p = d.lm[0] + l * 6 * d.ld + i;
+    p[0] = lm_xy[2 * l] + sigma * z0; p[d.ld] = lm_xy[2 * l + 1] + sigma * z1;
+    p[2 * (size_t)d.ld] = cov0; p[3 * (size_t)d.ld] = 0.0; p[4 * (size_t)d.ld] = 0.0; p[5 * (size_t)d.ld] = cov0;
+}

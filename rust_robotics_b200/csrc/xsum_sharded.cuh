@@ -1,10 +1,6 @@
-// fs_sharded.cuh — FastSLAM 1.0 with the particles sharded over G GPUs (one process per GPU).
+// xsum_sharded.cuh — the exact sequential-order sum / scan (xsum.cuh) over particles sharded across G GPUs (one process per
+// GPU, NCCL): used by the sharded ParticleFilterLocalizer / MonteCarloLocalizer.
 //
-// Rank g owns the contiguous block [g*n/G, (g+1)*n/G) of the particle index space and of every landmark column.
-// predict / EKF are embarrassingly parallel (Philox is keyed by the GLOBAL particle index).  The couplings are the
-// reference's sequential sums and the resample; they stay BIT-IDENTICAL to the single-GPU (and CPU) result:
-//
-//   exact global sum / scan (xs_*_sharded)
 //     1. local approximate tile sums -> local total T_g            | ncclAllGather of G doubles   (approximate offsets)
 //     2. classify with the GLOBAL approximate prefix, margin from the GLOBAL n; reduce the shard to its SUMMARY: the
 //        ordered list of its dirty values with the integer increment of the clean run in front of each, plus the
@@ -12,20 +8,10 @@
 //     3. every rank walks the summaries of ranks 0..G-1 in order with genuine FP adds (tens of entries): this yields
 //        the exact prefix at its own shard start, the exact value after each of its dirty values, and the exact
 //        global total — without a rank-to-rank dependency chain.
-//   resample (gate known after one host sync; all ranks take the same branch)
-//     ncclAllGather of the exact CDF slices and of the pose columns; every rank searches its own output slots in the
-//     global CDF (same lower bound as fs_search_kernel); ncclAllGather of the ancestry; particles whose ancestor lives
-//     on another rank receive that particle's whole map through grouped ncclSend/ncclRecv (all-to-all-v; systematic
-//     ancestries are monotone, so each (source, destination) pair is one contiguous run of slots).  The lazy clone of
-//     the single-GPU path carries over: imported maps are parked in GUEST columns [n, ld) of every landmark array and the
-//     composed ancestry points at them; a guest column stays referenced until the landmarks that point at it are
-//     rewritten, so guests are only recycled wholesale, by a compaction (one eager materialisation of the shard) when
-//     they run out (every few dozen resamples at balanced weights).
 #pragma once
 #include <nccl.h>
 #include "common.cuh"
 #include "xsum.cuh"
-#include "fs_kernels.cuh"
 
 #define PF_NCCL(call)                                                                                   \
     do {                                                                                                \
@@ -186,111 +172,3 @@ static int xs_scan_sharded(Ctx& ctx, XsWork& w, FsShard& sh, F f, S sink, size_t
     return 0;
 }
 
-// ---- resample kernels -------------------------------------------------------------------------------------------------
-struct FsValCombG {     // the comb over GLOBAL slot indices: r0 at slot 0, 1/n elsewhere (fs1.rs:219-230)
-    const double* scal; double inv; size_t offset;
-    __device__ __forceinline__ double operator()(size_t i) const { return (offset + i) == 0 ? scal[6] : inv; }
-};
-__global__ void __launch_bounds__(256) sh_search_kernel(FsDev d, const double* cum_all) {
-    const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (t >= d.n) return;
-    const double r = d.rcomb[t];
-    size_t lo = 0, hi = d.n_global;
-    while (lo < hi) {
-        size_t mid = lo + ((hi - lo) >> 1);
-        if (cum_all[mid] < r) lo = mid + 1; else hi = mid;
-    }
-    d.idx[t] = (uint32_t)(lo < d.n_global ? lo : d.n_global - 1);
-}
-__global__ void __launch_bounds__(256) sh_pack_pose_kernel(FsDev d, double* out3) {     // [px | py | pyaw] of my shard
-    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= d.n) return;
-    const int cur = *d.cur;
-    out3[i] = fs_px(d, cur)[i]; out3[d.n + i] = fs_py(d, cur)[i]; out3[2 * d.n + i] = fs_pyaw(d, cur)[i];
-}
-// pose_all layout after ncclAllGather of [px|py|pyaw] blocks: rank g's block at g*3*nl
-__global__ void __launch_bounds__(256) sh_gather_pose_kernel(FsDev d, const double* pose_all) {
-    const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (t >= d.n) return;
-    const int cur = *d.cur;
-    const size_t j = d.idx[t], nl = d.n;
-    const size_t g = j / nl, jl = j % nl;
-    const double* blk = pose_all + g * 3 * nl;
-    fs_px(d, cur ^ 1)[t] = blk[jl]; fs_py(d, cur ^ 1)[t] = blk[nl + jl]; fs_pyaw(d, cur ^ 1)[t] = blk[2 * nl + jl];
-    d.w[t] = 1.0 / (double)d.n_global;
-}
-// pack the whole maps of `cnt` of my particles (local slots idx_all[t0+q] - rank*nl) for a peer, materialised through
-// the lazy-clone ancestry: out[q][l][f]
-__global__ void __launch_bounds__(256) sh_pack_map_kernel(FsDev d, const uint32_t* idx_all, size_t t0, size_t cnt, int rank, double* out) {
-    const size_t rows = 6 * d.m;
-    const size_t e = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (e >= cnt * rows) return;
-    const size_t q = e / rows, row = e % rows;
-    const size_t l = row / 6; const int f = (int)(row % 6);
-    const size_t jl = (size_t)idx_all[t0 + q] - (size_t)rank * d.n;
-    const int st = d.lmstate[l];
-    const size_t col = (st & 2) ? jl : fs_anc_load(d, *d.anc_cur, l * d.n + jl);
-    out[e] = fs_lm(d, st & 1)[lm_index(d.ld, l, f, col)];
-}
-struct ShRecvTable { unsigned long long t0[SH_MAX_WORLD]; unsigned long long base[SH_MAX_WORLD]; unsigned long long cnt[SH_MAX_WORLD]; unsigned long long gcol[SH_MAX_WORLD]; };
-// imported maps -> guest columns [gcol[g], gcol[g]+cnt[g]) of every landmark's CURRENT buffer
-__global__ void __launch_bounds__(256) sh_unpack_guest_kernel(FsDev d, const double* recvbuf, ShRecvTable tab, int src_rank) {
-    const size_t rows = 6 * d.m;
-    const size_t cnt = (size_t)tab.cnt[src_rank];
-    const size_t e = (size_t)blockIdx.x * 256 + threadIdx.x;      // element = row * cnt + q  (q fastest: coalesced column writes)
-    if (e >= cnt * rows) return;
-    const size_t row = e / cnt, q = e % cnt;
-    const size_t l = row / 6; const int f = (int)(row % 6);
-    const int st = d.lmstate[l];
-    fs_lm(d, st & 1)[lm_index(d.ld, l, f, (size_t)tab.gcol[src_rank] + q)] = recvbuf[(size_t)tab.base[src_rank] + q * rows + row];
-}
-// lazy clone in sharded mode: anc'[l][t] = the guest column for imported slots, the composed local ancestry otherwise
-__global__ void __launch_bounds__(256) sh_compose_anc_kernel(FsDev d, ShRecvTable tab, int rank) {
-    const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (t >= d.n) return;
-    const int ac = *d.anc_cur;
-    const uint32_t* __restrict__ src = fs_anc(d, ac);
-    uint32_t* __restrict__ dst = fs_anc(d, ac ^ 1);
-    const size_t nl = d.n;
-    const size_t j = d.idx[t];
-    const size_t g = j / nl;
-    const size_t l0 = (size_t)blockIdx.y * FS_COMPOSE_ROWS;
-    if ((int)g == rank) {
-        const uint32_t jl = (uint32_t)(j - g * nl);
-#pragma unroll
-        for (int rr = 0; rr < FS_COMPOSE_ROWS; ++rr) {
-            size_t l = l0 + rr;
-            if (l < d.m) dst[l * nl + t] = (d.lmstate[l] & 2) ? jl : src[l * nl + jl];
-        }
-    } else {
-        const size_t tg = (size_t)rank * nl + t;
-        const uint32_t gc = (uint32_t)((size_t)tab.gcol[g] + (tg - (size_t)tab.t0[g]));
-#pragma unroll
-        for (int rr = 0; rr < FS_COMPOSE_ROWS; ++rr) { size_t l = l0 + rr; if (l < d.m) dst[l * nl + t] = gc; }
-    }
-}
-// compaction: materialise every landmark for every slot into its other buffer (identity-mapped afterwards); frees all guests
-__global__ void __launch_bounds__(256) sh_compact_kernel(FsDev d) {
-    const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (t >= d.n) return;
-    const int ac = *d.anc_cur;
-    const size_t l0 = (size_t)blockIdx.y * 4;
-    for (int rr = 0; rr < 4; ++rr) {
-        const size_t l = l0 + rr;
-        if (l >= d.m) break;
-        const int st = d.lmstate[l];
-        if (st & 2) continue;                                    // already identity-mapped: stays where it is
-        const size_t col = fs_anc_load(d, ac, l * d.n + t);
-        const double* __restrict__ s = fs_lm(d, st & 1);
-        double* __restrict__ o = fs_lm(d, (st & 1) ^ 1);
-#pragma unroll
-        for (int f = 0; f < 6; ++f) o[lm_index(d.ld, l, f, t)] = s[lm_index(d.ld, l, f, col)];
-    }
-}
-__global__ void sh_compact_finish_kernel(FsDev d) {
-    for (size_t l = threadIdx.x; l < d.m; l += blockDim.x) { int st = d.lmstate[l]; if (!(st & 2)) d.lmstate[l] = ((st & 1) ^ 1) | 2; }
-}
-__global__ void sh_flip_kernel(FsDev d) {
-    for (size_t l = threadIdx.x; l < d.m; l += blockDim.x) d.lmstate[l] &= 1;     // no landmark is identity-mapped any more
-    if (threadIdx.x == 0) { *d.cur ^= 1; *d.anc_cur ^= 1; d.counters[0] += 1; }
-}

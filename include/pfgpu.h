@@ -30,7 +30,7 @@ extern "C" {
 
 #define PFGPU_OK                 0
 #define PFGPU_ERR_INVALID      (-1)   /* RoboticsError::InvalidParameter                       */
-#define PFGPU_ERR_UNSUPPORTED  (-2)   /* valid in the reference, not built here: KLD-adaptive MCL on more than one GPU */
+#define PFGPU_ERR_UNSUPPORTED  (-2)   /* valid in the reference, not built here (KLD-adaptive MCL on more than one GPU, > 1024 landmarks, ...) */
 #define PFGPU_ERR_NO_DEVICE     1000  /* no CUDA device / extension cannot run: fail loudly      */
 #define PFGPU_ERR_CUDA          1001
 #define PFGPU_ERR_NCCL          1002
@@ -52,7 +52,7 @@ typedef struct {
     double   dt;                 /* 0.1                                                    */
     int32_t  mode;               /* 0 = ParticleFilterLocalizer, 1 = MonteCarloLocalizer   */
     int32_t  _pad;
-    uint64_t max_particles;      /* mcl only (5000); mode 1 currently requires == n_particles */
+    uint64_t max_particles;      /* mcl only (5000); > n_particles: KLD-adaptive particle count (mcl.rs:322-365) */
     double   kld_epsilon;        /* mcl only (0.05)                                        */
     double   kld_z;              /* mcl only (2.326)                                       */
 } pfgpu_pf_config;
@@ -109,14 +109,22 @@ void pfgpu_fs_default_config(pfgpu_fs_config* cfg);
 /* create_particles(n, m) fs1.rs:302-306 */
 int  pfgpu_fs_create(const pfgpu_fs_config* cfg, size_t n_particles, size_t n_landmarks, uint64_t seed,
                      int device, pfgpu_fs** out);
-/* Sharded over `world` GPUs of one NVLink domain, one process per GPU; collective over all ranks (same arguments
- * everywhere).  The step then runs over peer memory: kernels push / pull through NVLink and synchronise with cross-GPU
- * barriers, there is no NCCL call and no host synchronisation per step, so every rank must issue the same sequence of
- * pfgpu_fs_step calls; a rank that stops surfaces as PFGPU_ERR_CUDA at the others' next pfgpu_fs_sync (no hang).
- * Falls back to NCCL collectives when peer mapping is unavailable or the shard size is not a multiple of 512. */
+/* Sharded over `world` (<= 8) GPUs of one NVLink domain, one process per GPU; collective over all ranks (same arguments
+ * everywhere; n_particles_global / world must be a multiple of 64).  NCCL is used once, here, to exchange the cudaIpc handles of
+ * the per-rank arenas.  The step itself runs over peer memory: every rank's EKF kernel pushes its 8 bytes per particle of
+ * unnormalised weight into every rank's copy, every rank's post kernel evaluates the exact sums / CDF / resample indices
+ * of ALL particles, and ancestors that live on another rank are read through NVLink when (and only when) one of their
+ * landmarks is next observed — no NCCL call, no host synchronisation and no map copy per step.  Every rank must issue the
+ * same sequence of pfgpu_fs_step calls; a rank that stops surfaces as PFGPU_ERR_CUDA at the others' next synchronising
+ * call (spins time out; no hang). */
 int  pfgpu_fs_create_sharded(const pfgpu_fs_config* cfg, size_t n_particles_global, size_t n_landmarks,
                              uint64_t seed, int device, const void* nccl_unique_id, int rank, int world,
                              pfgpu_fs** out);
+/* The same sharded engine with all `world` ranks inside ONE process (no NCCL): out[r] runs on devices[r]; devices may
+ * repeat (several ranks on one GPU — what the single-GPU parity tests use to exercise every cross-rank path).  One host
+ * thread drives the ranks: issue each step to every handle with did_resample == NULL before synchronising any of them. */
+int  pfgpu_fs_create_sharded_local(const pfgpu_fs_config* cfg, size_t n_particles_global, size_t n_landmarks,
+                                   uint64_t seed, const int* devices, int world, pfgpu_fs** out);
 void pfgpu_fs_destroy(pfgpu_fs*);
 /* Vec<Particle> <-> device (fs1.rs:44-51).  pose_w: n x (weight, x, y, yaw); lm (nullable): n x m x
  * (x, y, c00, c01, c10, c11), particle-major AoS exactly like the reference's memory order. */
@@ -135,6 +143,7 @@ int  pfgpu_fs_best(pfgpu_fs*, size_t* index_global, double pose_w4[4]);
 int  pfgpu_fs_particle_landmarks(pfgpu_fs*, size_t index_local, double* lm6);
 int  pfgpu_fs_last_indices(pfgpu_fs*, uint32_t* idx, size_t cap, size_t* n);
 int  pfgpu_fs_last_neff(pfgpu_fs*, double* neff);
+int  pfgpu_fs_last_gate(pfgpu_fs*, int* did_resample);     /* whether the last step resampled (fs1.rs:263); synchronises */
 int  pfgpu_fs_count(pfgpu_fs*, size_t* n_local, size_t* n_global, size_t* n_landmarks);
 int  pfgpu_fs_sync(pfgpu_fs*);
 
@@ -158,8 +167,8 @@ int  pfgpu_pf_stats(pfgpu_pf*, pfgpu_stats*);
 int  pfgpu_fs_stats(pfgpu_fs*, pfgpu_stats*);
 /* debug (PFGPU_POST_TRACE=1): accumulated per-phase times [ns] of the fused post-step kernel; out32[31] = launches */
 int  pfgpu_fs_post_trace(pfgpu_fs*, unsigned long long* out32);
-/* how the coupled part of the step runs: 0 = one GPU, 1 = sharded over NCCL collectives, 2 = sharded over peer memory
-   (NVLink loads/stores/atomics inside the kernels; no NCCL call and no host sync per step) */
+/* how the coupled part of the step runs: 0 = one GPU, 2 = sharded over peer memory (NVLink loads / stores inside the kernels;
+   no NCCL call and no host sync per step) */
 int  pfgpu_fs_shard_mode(pfgpu_fs*, int* mode);
 int  pfgpu_pf_time_main_kernel(pfgpu_pf*, int on);
 int  pfgpu_fs_time_main_kernel(pfgpu_fs*, int on);

@@ -57,9 +57,9 @@ EXPORTS = [
     "pfgpu_pf_destroy", "pfgpu_pf_init_state", "pfgpu_pf_upload", "pfgpu_pf_download", "pfgpu_pf_count",
     "pfgpu_pf_predict", "pfgpu_pf_update", "pfgpu_pf_resample", "pfgpu_pf_step", "pfgpu_pf_estimate",
     "pfgpu_pf_neff", "pfgpu_pf_set_range_noise", "pfgpu_pf_last_indices", "pfgpu_pf_sync",
-    "pfgpu_fs_default_config", "pfgpu_fs_create", "pfgpu_fs_create_sharded", "pfgpu_fs_destroy",
+    "pfgpu_fs_default_config", "pfgpu_fs_create", "pfgpu_fs_create_sharded", "pfgpu_fs_create_sharded_local", "pfgpu_fs_destroy",
     "pfgpu_fs_upload", "pfgpu_fs_download", "pfgpu_fs_seed_map", "pfgpu_fs_step", "pfgpu_fs_best", "pfgpu_fs_particle_landmarks",
-    "pfgpu_fs_last_indices", "pfgpu_fs_last_neff", "pfgpu_fs_count", "pfgpu_fs_sync",
+    "pfgpu_fs_last_indices", "pfgpu_fs_last_neff", "pfgpu_fs_last_gate", "pfgpu_fs_count", "pfgpu_fs_sync",
     "pfgpu_nccl_unique_id", "pfgpu_pf_stats", "pfgpu_fs_stats", "pfgpu_pf_time_main_kernel",
     "pfgpu_fs_time_main_kernel", "pfgpu_pf_mark", "pfgpu_pf_elapsed_ms", "pfgpu_fs_mark", "pfgpu_fs_elapsed_ms",
     "pfgpu_pf_flush_l2", "pfgpu_fs_flush_l2", "pfgpu_fs_post_trace", "pfgpu_fs_shard_mode",
@@ -106,6 +106,8 @@ def load_library():
     L.pfgpu_fs_create.argtypes = [C.POINTER(_FsCfg), C.c_size_t, C.c_size_t, C.c_uint64, C.c_int, C.POINTER(vp)]
     L.pfgpu_fs_create_sharded.argtypes = [C.POINTER(_FsCfg), C.c_size_t, C.c_size_t, C.c_uint64, C.c_int, vp, C.c_int,
                                           C.c_int, C.POINTER(vp)]
+    L.pfgpu_fs_create_sharded_local.argtypes = [C.POINTER(_FsCfg), C.c_size_t, C.c_size_t, C.c_uint64, C.POINTER(C.c_int), C.c_int,
+                                                C.POINTER(vp)]
     L.pfgpu_fs_destroy.argtypes = [vp]
     L.pfgpu_fs_destroy.restype = None
     L.pfgpu_fs_upload.argtypes = [vp, c_dp, c_dp, C.c_size_t]
@@ -116,6 +118,7 @@ def load_library():
     L.pfgpu_fs_particle_landmarks.argtypes = [vp, C.c_size_t, c_dp]
     L.pfgpu_fs_last_indices.argtypes = [vp, c_u32p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.pfgpu_fs_last_neff.argtypes = [vp, c_dp]
+    L.pfgpu_fs_last_gate.argtypes = [vp, C.POINTER(C.c_int)]
     L.pfgpu_fs_count.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.pfgpu_fs_sync.argtypes = [vp]
     L.pfgpu_nccl_unique_id.argtypes = [vp]
@@ -389,6 +392,47 @@ class FastSlam1:
 
     create_particles = classmethod(lambda cls, n, m, **kw: cls(n, m, **kw))
 
+    @classmethod
+    def create_sharded_local(cls, n_particles_global, n_landmarks, devices, config=None, seed=42):
+        """All ranks of the sharded engine inside this process (pfgpu_fs_create_sharded_local): one FastSlam1 per entry of
+        `devices` (entries may repeat).  Drive them with step_all()."""
+        L = load_library()
+        config = config or FsConfig()
+        cc = config._c()
+        world = len(devices)
+        devs = (C.c_int * world)(*devices)
+        hs = (C.c_void_p * world)()
+        _check(L, L.pfgpu_fs_create_sharded_local(C.byref(cc), n_particles_global, n_landmarks, seed, devs, world, hs))
+        out = []
+        for r in range(world):
+            g = cls.__new__(cls)
+            g.L, g.config, g.h = L, config, C.c_void_p(hs[r])
+            nl, ng, m = C.c_size_t(), C.c_size_t(), C.c_size_t()
+            _check(L, L.pfgpu_fs_count(g.h, C.byref(nl), C.byref(ng), C.byref(m)))
+            g.n_local, g.n_global, g.m = nl.value, ng.value, m.value
+            out.append(g)
+        return out
+
+    @staticmethod
+    def step_all(ranks, u, z):
+        """one fastslam_update on every in-process rank: enqueue everywhere first, then synchronise; returns did_resample"""
+        for g in ranks:
+            g.fastslam_update(u, z, want_flag=False)
+        for g in ranks:
+            g.sync()
+        return ranks[0].did_resample()
+
+    def did_resample(self):
+        """whether the last step resampled (synchronises)"""
+        return self.last_gate()
+
+    def last_gate(self):
+        idx = C.c_size_t()
+        _check(self.L, self.L.pfgpu_fs_best(self.h, C.byref(idx), None))      # synchronises the stream
+        g = C.c_int()
+        _check(self.L, self.L.pfgpu_fs_last_gate(self.h, C.byref(g)))
+        return bool(g.value)
+
     def close(self):
         if getattr(self, "h", None) and self.h.value:
             self.L.pfgpu_fs_destroy(self.h)
@@ -465,7 +509,7 @@ class FastSlam1:
         return s
 
     def shard_mode(self):
-        """0 = one GPU, 1 = sharded over NCCL collectives, 2 = sharded over peer memory (NVLink)."""
+        """0 = one GPU, 2 = sharded over peer memory (NVLink)."""
         m = C.c_int()
         _check(self.L, self.L.pfgpu_fs_shard_mode(self.h, C.byref(m)))
         return m.value

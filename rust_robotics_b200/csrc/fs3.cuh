@@ -405,10 +405,13 @@ __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const do
     __syncthreads();
     const int D = sh.D;
     if (!sh.fail) {
-        if ((unsigned)tid < nt) {
-            const int c = sh.tD[tid], o0 = sh.tDoff[tid];
-            const size_t g0 = ((size_t)slot * FS3_MAX_TILES + tid) * FS3_ENT_TILE;
-            for (int e = 0; e < c; ++e) { sh.eP[o0 + e] = sh.tPoff[tid] + __ldcg(d.entP + g0 + e); sh.eV[o0 + e] = __ldcg(d.entV + g0 + e); sh.eL[o0 + e] = __ldcg(d.entL + g0 + e); }
+        for (unsigned x = tid; x < nt * FS3_ENT_TILE; x += NT) {       // one (tile, entry) pair per thread and trip: the loads overlap
+            const unsigned tb = x / FS3_ENT_TILE; const int e = (int)(x % FS3_ENT_TILE);
+            if (e < sh.tD[tb]) {
+                const size_t g = ((size_t)slot * FS3_MAX_TILES + tb) * FS3_ENT_TILE + e;
+                const int o = sh.tDoff[tb] + e;
+                sh.eP[o] = sh.tPoff[tb] + __ldcg(d.entP + g); sh.eV[o] = __ldcg(d.entV + g); sh.eL[o] = __ldcg(d.entL + g);
+            }
         }
         __syncthreads();
         if (tid == 0) {                                       // the serial part: one integer add + one FP add per dirty value
@@ -489,7 +492,7 @@ __device__ __forceinline__ unsigned fs3_warp_search(const double* c, unsigned n,
         const int cnt = __popc(mask);
         const unsigned nlo = cnt ? lo + (unsigned)cnt * step : lo;
         const unsigned long long nh = (unsigned long long)lo + (unsigned long long)(cnt + 1) * step - 1ull;
-        hi = nh < hi ? (unsigned)nh : hi;
+        if (cnt < 32 && nh < hi) hi = (unsigned)nh;           // lane cnt probed c[nh] >= r (with cnt == 32 nobody probed nh)
         lo = nlo;
     }
     {

@@ -66,7 +66,8 @@ static int fs_create_impl(const pfgpu_fs_config* cfg, size_t n, size_t n_global,
     {
         const char* env = getenv("PFGPU_POST_NT");
         h->post_nt = (env && atoi(env) == 512) ? 512 : 256;
-        const unsigned want = (unsigned)std::min<int>(128, h->ctx.num_sms);
+        unsigned want = (unsigned)std::min<int>(128, h->ctx.num_sms);
+        { const char* ew = getenv("PFGPU_POST_TILES"); if (ew && atoi(ew) >= 1 && atoi(ew) <= (int)want) want = (unsigned)atoi(ew); }   // tests: several values per thread at small n
         unsigned K = (unsigned)((n_global + (size_t)want * h->post_nt - 1) / ((size_t)want * h->post_nt));
         if (K == 0) K = 1;
         h->post_K = K;
@@ -129,7 +130,7 @@ static int fs_create_impl(const pfgpu_fs_config* cfg, size_t n, size_t n_global,
     }
     { const char* e5 = getenv("PFGPU_PDL"); h->pdl = !(e5 && e5[0] == '0'); }
     { const char* e3 = getenv("PFGPU_EKF_VARIANT"); if (e3 && e3[0] >= '0' && e3[0] <= '3') h->ekf_variant = e3[0] - '0'; }
-    if (world > 1) {
+    if (world > 1 && uid) {
         ncclUniqueId id;
         memcpy(&id, uid, sizeof(id));
         ncclResult_t nr = ncclCommInitRank(&h->comm, world, id, rank);
@@ -177,12 +178,40 @@ extern "C" int pfgpu_fs_create_sharded(const pfgpu_fs_config* cfg, size_t n_glob
     size_t nl = n_global / (size_t)world;
     return fs_create_impl(cfg, nl, n_global, (size_t)rank * nl, m, seed, device, uid, rank, world, out);
 }
+// All ranks in ONE process (one host thread drives them, no NCCL): peers are plain device pointers (same device) or
+// peer-access pointers (different devices).
+extern "C" int pfgpu_fs_create_sharded_local(const pfgpu_fs_config* cfg, size_t n_global, size_t m, uint64_t seed, const int* devices,
+                                             int world, pfgpu_fs** out) {
+    if (!out || !devices || world < 1 || world > FS3_MAXG || n_global == 0 || n_global % (size_t)world != 0) return PFGPU_ERR_INVALID;
+    for (int r = 0; r < world; ++r) out[r] = nullptr;
+    const size_t nl = n_global / (size_t)world;
+    static const char dummy_uid = 0;
+    for (int r = 0; r < world; ++r) {
+        int rc = fs_create_impl(cfg, nl, n_global, (size_t)r * nl, m, seed, devices[r], world > 1 ? nullptr : &dummy_uid, r, world, &out[r]);
+        if (rc) { for (int q = 0; q < r; ++q) { pfgpu_fs_destroy(out[q]); out[q] = nullptr; } return rc; }
+    }
+    for (int a = 0; a < world; ++a)
+        for (int b = 0; b < world; ++b) {
+            if (devices[a] != devices[b]) {
+                cudaSetDevice(devices[a]);
+                cudaError_t e = cudaDeviceEnablePeerAccess(devices[b], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                    snprintf(g_pfgpu_err, sizeof(g_pfgpu_err), "no peer access from device %d to device %d", devices[a], devices[b]);
+                    for (int q = 0; q < world; ++q) { pfgpu_fs_destroy(out[q]); out[q] = nullptr; }
+                    return PFGPU_ERR_UNSUPPORTED;
+                }
+                cudaGetLastError();
+            }
+            out[a]->d.peer[b] = out[b]->arena;
+        }
+    return PFGPU_OK;
+}
 extern "C" void pfgpu_fs_destroy(pfgpu_fs* h) {
     if (!h) return;
     cudaSetDevice(h->ctx.device);
     if (h->ctx.stream) cudaStreamSynchronize(h->ctx.stream);
     Fs3Dev& d = h->d;
-    for (int g = 0; g < h->world; ++g) if (g != h->rank && h->peer_ptr[g]) cudaIpcCloseMemHandle(h->peer_ptr[g]);
+    for (int g = 0; g < h->world; ++g) if (g != h->rank && h->peer_ptr[g]) cudaIpcCloseMemHandle(h->peer_ptr[g]);   // (local mode: none were opened)
     cudaFree(h->arena);
     cudaFree(d.st); cudaFree(d.lmst); cudaFree(d.w); cudaFree(d.wn_all); cudaFree(d.cum_all); cudaFree(d.rcomb_all); cudaFree(d.idx);
     cudaFree(d.tileP); cudaFree(d.tileD); cudaFree(d.tileQ); cudaFree(d.entP); cudaFree(d.entV); cudaFree(d.entL);
@@ -394,6 +423,13 @@ extern "C" int pfgpu_fs_last_neff(pfgpu_fs* h, double* neff) {
     PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
     *neff = h->h_rec->neff;
     return 0;
+}
+extern "C" int pfgpu_fs_last_gate(pfgpu_fs* h, int* did) {
+    if (!h || !did) return PFGPU_ERR_INVALID;
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+    *did = h->steps ? h->h_rec->gate : 0;
+    return fs_check_err(h);
 }
 extern "C" int pfgpu_fs_stats(pfgpu_fs* h, pfgpu_stats* s) {
     if (!h || !s) return PFGPU_ERR_INVALID;

@@ -287,7 +287,8 @@ def test_fastslam_trajectory_bit_exact(oracle, n, side, steps):
         if did:
             resamples += 1
             idx = g.last_indices()
-            assert np.array_equal(idx, o.last_indices()), f"step {t}: indices"
+            oi = o.last_indices()
+            assert np.array_equal(idx, oi), f"step {t}: indices differ at {np.flatnonzero(idx != oi)[:8]} ({int((idx != oi).sum())} slots): {idx[idx != oi][:8]} vs {oi[idx != oi][:8]}"
             assert np.all(np.diff(idx.astype(np.int64)) >= 0)          # systematic resampling is monotone
         if n <= 4096 or t == steps - 1:
             _fs_compare(g, o, f"step {t}")
@@ -295,6 +296,28 @@ def test_fastslam_trajectory_bit_exact(oracle, n, side, steps):
         assert bi == o.best()
     assert resamples > 0, "scenario never resampled"
     assert g.stats().serial_fallbacks == 0
+
+
+@pytest.mark.parametrize("tiles,n,nt", [(2, 4096, 256), (3, 5000, 256), (1, 2048, 512), (5, 1 << 14, 512)])
+def test_fastslam_post_kernel_shapes_bit_exact(oracle, tiles, n, nt, monkeypatch):
+    """the fused post kernel with several values per thread and few tiles (the shape large particle counts get), at sizes
+    the oracle checks in seconds"""
+    monkeypatch.setenv("PFGPU_POST_TILES", str(tiles))
+    monkeypatch.setenv("PFGPU_POST_NT", str(nt))
+    sc = scenarios.FastSlamScenario(6, (25.0, 25.0, 0.0), (1.0, 0.025), 16)
+    g = rr.FastSlam1(n, sc.m, rr.FsConfig(nth=n / 1.5), seed=3)
+    o = OracleFS(oracle, n, sc.m, seed=3, nth=n / 1.5)
+    g.seed_map(sc.start, sc.landmarks); o.seed_map(sc.start, sc.landmarks)
+    resamples = 0
+    for t in range(16):
+        did = g.fastslam_update(sc.control, sc.obs[t])
+        assert did == bool(o.step(sc.control, sc.obs[t])), f"step {t}"
+        if did:
+            resamples += 1
+            idx, oi = g.last_indices(), o.last_indices()
+            assert np.array_equal(idx, oi), f"step {t}: {int((idx != oi).sum())} indices differ, first at {np.flatnonzero(idx != oi)[:4]}"
+    _fs_compare(g, o, "end")
+    assert resamples > 0 and g.stats().serial_fallbacks == 0
 
 
 def test_fastslam_reference_constants_and_fresh_particles(oracle):
@@ -408,3 +431,75 @@ def test_fastslam_full_size_matches_oracle(oracle):
     for t in range(3):
         assert g.fastslam_update(sc.control, sc.obs[t]) == bool(o.step(sc.control, sc.obs[t]))
     _fs_compare(g, o, "full size")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the SHARDED engine on one GPU: all ranks inside this process, on the same device (pfgpu_fs_create_sharded_local).  Every
+# cross-rank path runs — weights pushed into every rank's copy, arrive / done flags, ancestors and ancestry rows read from
+# another rank's arena, lazy import of a remote map at the next EKF update — and every rank's shard must equal the oracle's
+# slice bit for bit.  (tests/test_gpu_multi.py runs the same engine with one process per GPU when several GPUs exist.)
+# ---------------------------------------------------------------------------------------------------------------------
+def _shard_compare(ranks, o, what):
+    op, ol = o.state()
+    for r, g in enumerate(ranks):
+        lo, hi = r * g.n_local, (r + 1) * g.n_local
+        gp, gl = g.state()
+        assert np.array_equal(gp, op[lo:hi]), f"{what}: rank {r} pose/weight rows {np.flatnonzero((gp != op[lo:hi]).any(axis=1))[:5]}"
+        assert np.array_equal(gl, ol[lo:hi]), f"{what}: rank {r} landmarks differ for particles {np.flatnonzero((gl != ol[lo:hi]).any(axis=(1, 2)))[:5]}"
+
+
+@pytest.mark.parametrize("world,n,side,steps,fast", [(2, 1024, 6, 60, True), (4, 4096, 6, 40, True), (2, 1 << 14, 8, 12, False), (8, 4096, 5, 30, True)])
+def test_fastslam_sharded_in_process_bit_exact(oracle, world, n, side, steps, fast):
+    if fast:   # landmarks leave and re-enter the view: remote references survive several resamples
+        sc = scenarios.FastSlamScenario(side, (10.0 * side / 2 - 5.0, 10.0 * side / 2 - 15.0, 0.0), (8.0, 0.8), steps, max_range=12.0)
+    else:
+        sc = scenarios.FastSlamScenario(side, (10.0 * side / 2 - 5.0, 10.0 * side / 2 - 5.0, 0.0), (1.0, 0.025), steps)
+    ranks = rr.FastSlam1.create_sharded_local(n, sc.m, [0] * world, rr.FsConfig(nth=n / 1.5), seed=9)
+    o = OracleFS(oracle, n, sc.m, seed=9, nth=n / 1.5)
+    for g in ranks:
+        g.seed_map(sc.start, sc.landmarks)
+    o.seed_map(sc.start, sc.landmarks)
+    assert all(g.shard_mode() == 2 for g in ranks)
+    resamples = 0
+    for t in range(steps):
+        did = rr.FastSlam1.step_all(ranks, sc.control, sc.obs[t])
+        assert did == bool(o.step(sc.control, sc.obs[t])), f"step {t}: gate"
+        assert all(g.last_gate() == did for g in ranks)
+        if did:
+            resamples += 1
+            idx = np.concatenate([g.last_indices() for g in ranks])
+            assert np.array_equal(idx, o.last_indices()), f"step {t}: indices"
+        for g in ranks:
+            assert g.get_best_particle()[0] == o.best(), f"step {t}: best particle"
+        if t % 9 == 0:
+            _shard_compare(ranks, o, f"step {t}")
+    _shard_compare(ranks, o, "end")
+    assert resamples > 2
+    assert all(g.stats().serial_fallbacks == 0 for g in ranks)
+
+
+def test_fastslam_sharded_in_process_edge_cases(oracle):
+    """duplicate landmark ids, empty list, all-zero weights (every slot descends from the last particle of the last rank),
+    fresh landmarks — sharded over 2 in-process ranks"""
+    n, m = 2048, 4
+    lm_xy = np.array([[5.0, 0.0], [0.0, 5.0], [5.0, 5.0], [-5.0, 2.0]])
+    ranks = rr.FastSlam1.create_sharded_local(n, m, [0, 0], rr.FsConfig(nth=n / 1.5), seed=11)
+    o = OracleFS(oracle, n, m, seed=11, nth=n / 1.5)
+    for g in ranks:
+        g.seed_map([0.0, 0.0, 0.0], lm_xy)
+    o.seed_map([0.0, 0.0, 0.0], lm_xy)
+    z = [(5.1, 0.02, 0), (5.0, 1.55, 1), (4.9, -0.01, 0)]
+    assert rr.FastSlam1.step_all(ranks, [1.0, 0.1], z) == bool(o.step([1.0, 0.1], z)); _shard_compare(ranks, o, "duplicate ids")
+    assert rr.FastSlam1.step_all(ranks, [1.0, 0.1], []) == bool(o.step([1.0, 0.1], [])); _shard_compare(ranks, o, "empty obs")
+    for g in ranks:
+        p, l = g.state(); p[:, 0] = 0.0; g.set_state(p, l)
+    op, ol = o.state(); op[:, 0] = 0.0; o.set_state(op, ol)
+    assert rr.FastSlam1.step_all(ranks, [1.0, 0.1], z[:2]) is True and o.step([1.0, 0.1], z[:2]) == 1
+    assert all(np.all(g.last_indices() == n - 1) for g in ranks); _shard_compare(ranks, o, "zero weights")
+    for g in ranks:
+        p, l = g.state(); l[:, 2, :] = [0.0, 0.0, 1000.0, 0.0, 0.0, 1000.0]; g.set_state(p, l)
+    op, ol = o.state(); ol[:, 2, :] = [0.0, 0.0, 1000.0, 0.0, 0.0, 1000.0]; o.set_state(op, ol)
+    z2 = [(7.0, 0.8, 2), (5.0, 0.1, 0)]
+    for _ in range(6):
+        assert rr.FastSlam1.step_all(ranks, [1.0, 0.0], z2) == bool(o.step([1.0, 0.0], z2))
+    _shard_compare(ranks, o, "mixed fresh")

@@ -316,20 +316,15 @@ def run_ours(args, rank, world, local_rank):
         out = (C.c_ulonglong * 32)()
         g.L.pfgpu_fs_post_trace(g.h, out)
         nl = max(out[31], 1)
-        names = ["init+sync", "S tilesum", "sync", "S classify", "sync", "S chain", "norm+Q/S2 tilesums", "sync", "Q approx", "Q exact (border)",
-                 "S2 classify+sync+chain", "cum/comb tilesum", "sync", "cum/comb classify", "sync", "chains+emit"]
-        if world > 1 and g.shard_mode() == 2:
-            nr = max(int(g.stats().resamples), 1)
-            sys.stderr.write("fs_post_mg_kernel (us per launch, CTA 0): load+S tilesum+barrier=%.2f classify+barrier=%.2f chain S+Q/S2 tilesums+barrier=%.2f | "
-                             "per RESAMPLE: S2 classify..cum/comb classify (3 barriers)=%.2f chains+emit+CDF push=%.2f\n" %
-                             (out[0] / nl / 1e3, out[1] / nl / 1e3, out[2] / nl / 1e3, out[3] / nr / 1e3, out[4] / nr / 1e3))
-            sys.stderr.write("resample-step stages (us per resample, kernel start to next kernel start): post=%.1f search+pose=%.1f plan=%.1f "
-                             "(unused)=%.1f import+compose=%.1f flip(wait)=%.1f   [%d resamples traced]\n" %
-                             tuple([out[8 + k] / nr / 1e3 for k in range(6)] + [nr]))
-        sys.stderr.write("fs_post_kernel phase times (us per launch, CTA 0): " +
-                         ", ".join(f"{nm}={out[k] / nl / 1e3:.2f}" for k, nm in enumerate(names)) + f"  launches={out[31]}\n")
-        sys.stderr.write("  S chain detail (us): segscan=%.2f staging=%.2f walk=%.2f verify+final=%.2f  mean dirty=%.1f\n" %
-                         (out[16] / nl / 1e3, out[17] / nl / 1e3, out[18] / nl / 1e3, out[19] / nl / 1e3, out[22] / nl))
+        nr = max(int(g.stats().resamples), 1)
+        us = lambda k, den: out[k] / den / 1e3
+        sys.stderr.write("fs3_post_kernel (us, CTA 0; per launch): load+offsets=%.2f  S sum=%.2f [classify+publish %.2f | barrier %.2f | chain %.2f]  "
+                         "normalise+gate=%.2f   launches=%d\n" % (us(0, nl), us(1, nl), us(8, nl), us(9, nl), us(10, nl), us(2, nl), nl))
+        sys.stderr.write("   per RESAMPLE (%d): S2 sum=%.2f  CDF scan=%.2f [classify+publish %.2f | barrier %.2f | chain %.2f | emit %.2f]  comb+barrier=%.2f  "
+                         "search+clone=%.2f\n" % (nr, us(3, nr), us(4, nr), us(12, nr), us(13, nr), us(14, nr), us(15, nr), us(5, nr), us(6, nr)))
+        nc = max(out[19], 1)
+        sys.stderr.write("fs3_ekf_kernel CTA timeline (SM cycles, mean over %d CTAs): loads+predict+barrier=%.0f  EKF+stores=%.0f  epilogue=%.0f\n" %
+                         (nc, out[16] / nc, out[17] / nc, out[18] / nc))
     if rank == 0:
         peak, peak_src = load_peaks()
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9

@@ -39,15 +39,14 @@
 #include "../../include/fs_ekf_math.h"
 
 #define FS3_MAXG 8
-#define FS3_MAX_OBS 32            // observations per EKF launch (one warp each)
+#define FS3_MAX_OBS 31            // observations per EKF launch (one warp each, plus the helper warp)
 #define FS3_MAX_TILES 160
-#define FS3_ENT_TILE 32           // dirty values itemised per tile (more: that sum takes the serial walk)
-#define FS3_ENT_CAP 1024          // ... per sum
+#define FS3_ENT_CAP 512           // dirty values itemised per sum (more: that sum takes the serial walk)
 #define FS3_SLOTS 5               // S, Q (border only), S2, cdf, comb (n not a power of two)
 #define FS3_SPIN_LIMIT (1u << 27)
 
 struct Fs3Obs { double d, angle; int lm_id; int pad; };
-struct Fs3ObsParam { Fs3Obs o[FS3_MAX_OBS]; };
+struct Fs3ObsParam { Fs3Obs o[32]; };
 
 struct Fs3State {                 // device-resident; written by the last CTA of a launch, read by the next launch
     int cur, rcur;                // live pose buffer / live rows buffer
@@ -69,6 +68,8 @@ struct Fs3Rec {                   // mapped pinned host memory: what a caller re
 struct Fs3Dev {
     unsigned n, n_glob, off, m, ld;           // local / global particles, first global slot, landmarks, column stride
     int G, rank;
+    int wait_inline;                          // 1: kernels spin on the peers' flags themselves; 0: the host launches fs3_wait_kernel
+                                              // in front of them (ranks sharing one GPU must not hold SMs while they wait)
     unsigned npart;                           // partial sums per rank (= ld / 64)
     Fs3State* st;
     int* lmst;                                // [m]
@@ -82,8 +83,11 @@ struct Fs3Dev {
     double* cum_all;                          // [n_glob] exact CDF
     double* rcomb_all;                        // [n_glob] exact comb (only when n_glob is not a power of two)
     unsigned* idx;                            // [ld] global ancestor of local slot t at the last resample
-    unsigned long long* tileP; int* tileD; double* tileQ;      // [FS3_SLOTS][FS3_MAX_TILES] tile aggregates
-    unsigned long long* entP; double* entV; int* entL;         // [FS3_SLOTS][FS3_MAX_TILES][FS3_ENT_TILE]
+    unsigned long long* tileP; double* tileQ;                  // [FS3_SLOTS][FS3_MAX_TILES] clean-increment sum per tile; [tiles] sum w_raw^2
+    unsigned* entCnt;                                          // [FS3_SLOTS] dirty values appended so far (any order)
+    unsigned* entKey; unsigned* entTile; unsigned long long* entP; double* entV; int* entL;   // [FS3_SLOTS][FS3_ENT_CAP]
+    unsigned* bar;                                             // [8] grid-barrier arrival counters of the running post kernel
+    unsigned short* rowlist; int* rowinfo;                     // live ancestry rows ([m]), [0] their count, [1] new row id or -1
     double* tileBw; unsigned* tileBi;         // [FS3_MAX_TILES] best (weight, global slot) per tile
     int* flagsg;                              // [FS3_SLOTS] "bad value seen" per sum (reset by the post kernel's last CTA)
     Fs3Rec* rec;
@@ -115,198 +119,294 @@ __device__ __forceinline__ void fs3_signal_peers(const Fs3Dev& d, int which, uns
 }
 
 // =====================================================================================================================
-// EKF kernel
+// EKF kernel: persistent, software-pipelined
 // =====================================================================================================================
+// One CTA per SM walks groups of 64 particles (two per lane).  Warps 0..k-1 each own one observation: per group they take the
+// group's landmark columns out of a cp.async landing buffer (issued one group ahead, so the HBM latency of the next group
+// hides behind the ~600 FP64 instructions of this one), run update_landmark for their two pairs, store the columns and
+// publish the two likelihood factors.  Warp k is the helper: it runs predict_particle one group AHEAD (Philox, Box-Muller,
+// sincos: a ~2 us dependent chain that would otherwise sit in front of every group) and the weight products of the group
+// BEHIND.  Hand-offs go through four double-buffered named barriers (pose full/empty, likelihoods full/empty).
 __device__ __noinline__ double fs3_update_slow(FsLm* L, double px, double py, double pyaw, double z0, double z1, double r00, double r11) {
     int wrote;
     return fs_update_landmark(L, px, py, pyaw, z0, z1, r00, r11, &wrote);   // 1.0 whenever the weight is left alone
 }
+__device__ __forceinline__ void nb_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void nb_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void cp_async16(void* smem, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+enum { FS3_B_POSE_FULL = 1, FS3_B_POSE_EMPTY = 3, FS3_B_LIK_FULL = 5, FS3_B_LIK_EMPTY = 7 };
 
-// flags: bit 0 = first launch of the step (predict; weights start from Particle::weight), bit 1 = last launch of the step
-template <int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB)
+// flags: bit 0 = first launch of the step (predict; weights start from Particle::weight)
+// dynamic shared memory: pose [2][3][64] | lik [2][k][64] | landing [2][k][6][64]   (doubles)
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
 fs3_ekf_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsParam po, double u0, double u1, double dt,
                double sq0, double sq1, double r00, double r11, uint64_t seed, uint32_t call, int k_obs, int flags, unsigned step) {
     pf_grid_dep_sync();
-    extern __shared__ double s_dyn[];
-    double* s_pose = s_dyn;                     // [3][64]
-    double* s_lik = s_dyn + 192;                // [k_obs][64]
-    __shared__ int s_last;
+    extern __shared__ __align__(16) double s_dyn[];
+    double* s_pose = s_dyn;                                         // [2][3][64]
+    double* s_lik = s_dyn + 384;                                    // [2][k][64]
+    double* s_land = s_lik + (size_t)2 * k_obs * 64;                // [2][k][6][64]
     const int lane = threadIdx.x & 31, wj = threadIdx.x >> 5;
-    const unsigned i0 = blockIdx.x * 64u + 2u * (unsigned)lane;     // local slots i0, i0 + 1 (inside the padded stride)
+    const int nsync = 32 * (k_obs + 1);
     Fs3State* st = d.st;
-    if (d.G > 1) {                              // peers' rows / poses / maps are stable once their previous post kernel is over
+    if (d.G > 1 && d.wait_inline) {             // peers' rows / poses / maps are stable once their previous post kernel is over
         if (threadIdx.x == 0) fs3_wait_peers(d, 1, step);
         __syncthreads();
     }
     const int cur = st->cur, rcur = st->rcur, par = (int)(step & 1u);
     const size_t ld = d.ld;
-    // ---- landmark loads first (they do not depend on the pose) ----
-    FsLm L[2];
-    Fs3Obs ob; ob.d = 0.0; ob.angle = 0.0; ob.lm_id = 0; ob.pad = 0;
-    bool ident = true; int buf = 0; size_t lbase = 0;
-    if (k_obs > 0) {
-        ob = po.o[wj];
-        const int s = d.lmst[ob.lm_id];
-        ident = (s >> 1) == 0; buf = s & 1;
-        lbase = (size_t)ob.lm_id * 6 * ld;
+    const unsigned ngroups = d.ld / 64;
+    if (wj == k_obs) {
+        // =============================== helper warp: predict ahead, weights behind ===============================
+        double2 Wp = make_double2(0.0, 0.0);                              // weights of the previous trip's group
+        unsigned gprev = 0;
+        for (unsigned it = 0, g = blockIdx.x; ; g += gridDim.x, ++it) {
+            const bool have = g < ngroups;
+            const int sg = (int)(it & 1u);
+            double2 Wn = make_double2(0.0, 0.0);
+            if (have) {
+                const unsigned i0 = g * 64u + 2u * (unsigned)lane;
+                const double* wsrc = (flags & 1) ? d.w : d.wraw[par] + d.off;
+                Wn = *reinterpret_cast<const double2*>(wsrc + i0);                  // needed one trip later
+                double2 X = *reinterpret_cast<const double2*>(d.px[cur] + i0), Y = *reinterpret_cast<const double2*>(d.py[cur] + i0);
+                double2 A = *reinterpret_cast<const double2*>(d.pyaw[cur] + i0);
+                if (flags & 1) {       // predict_particle + motion_model fs1.rs:70-77,123-137, in place
+                    double xs[2] = { X.x, X.y }, ys[2] = { Y.x, Y.y }, as[2] = { A.x, A.y };
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        double z0, z1;
+                        pfc_normal_pair(pfc_rng_block(seed, PFC_STREAM_FS_PREDICT, call, (uint64_t)d.off + i0 + q), &z0, &z1);
+                        const double un0 = u0 + z0 * sq0;                      // fs1.rs:129
+                        const double un1 = u1 + z1 * sq1;                      // fs1.rs:130
+                        double sn, cs;
+                        pfc_sincos(as[q], &sn, &cs);
+                        xs[q] = xs[q] + un0 * dt * cs;                         // motion_model fs1.rs:73-75
+                        ys[q] = ys[q] + un0 * dt * sn;
+                        as[q] = fs_normalize_angle(as[q] + un1 * dt);
+                    }
+                    X = make_double2(xs[0], xs[1]); Y = make_double2(ys[0], ys[1]); A = make_double2(as[0], as[1]);
+                    *reinterpret_cast<double2*>(d.px[cur] + i0) = X; *reinterpret_cast<double2*>(d.py[cur] + i0) = Y;
+                    *reinterpret_cast<double2*>(d.pyaw[cur] + i0) = A;
+                }
+                if (k_obs > 0) {
+                    if (it >= 2) nb_sync(FS3_B_POSE_EMPTY + sg, nsync);          // the EKF warps have read what this stage held
+                    double* sp = s_pose + sg * 192;
+                    *reinterpret_cast<double2*>(sp + 2 * lane) = X; *reinterpret_cast<double2*>(sp + 64 + 2 * lane) = Y;
+                    *reinterpret_cast<double2*>(sp + 128 + 2 * lane) = A;
+                    __threadfence_block();
+                    nb_arrive(FS3_B_POSE_FULL + sg, nsync);
+                }
+            }
+            // weights of the group one trip behind (of this trip's group when there are no observations):
+            // w = (((w * l_0) * l_1) ...) in observation order (fs1.rs:181 inside the loops fs1.rs:250-256)
+            if (k_obs > 0 ? it >= 1 : have) {
+                const unsigned ge = k_obs > 0 ? gprev : g;
+                const unsigned i0 = ge * 64u + 2u * (unsigned)lane;
+                double w0 = k_obs > 0 ? Wp.x : Wn.x, w1 = k_obs > 0 ? Wp.y : Wn.y;
+                if (k_obs > 0) {
+                    const int se = (int)((it - 1u) & 1u);
+                    nb_sync(FS3_B_LIK_FULL + se, nsync);
+                    const double* sl = s_lik + (size_t)se * k_obs * 64;
+                    for (int j = 0; j < k_obs; ++j) {
+                        const double2 l = *reinterpret_cast<const double2*>(sl + j * 64 + 2 * lane);
+                        w0 = w0 * l.x; w1 = w1 * l.y;
+                    }
+                    nb_arrive(FS3_B_LIK_EMPTY + se, nsync);
+                }
+                const bool v0 = i0 < d.n, v1 = i0 + 1 < d.n;
+                if (!v0) w0 = 0.0;
+                if (!v1) w1 = 0.0;
+                const double psum = warp_sum(w0 + w1);                           // honest (tree-order) sum: steers x3_classify only
+                for (int gg = 0; gg < d.G; ++gg) {
+                    double* wr = (d.G > 1 ? reinterpret_cast<double*>(d.peer[gg] + d.o_wraw[par]) : d.wraw[par]) + d.off;
+                    if (v1) *reinterpret_cast<double2*>(wr + i0) = make_double2(w0, w1);
+                    else if (v0) wr[i0] = w0;
+                    if (lane == 0) {
+                        double* pp = d.G > 1 ? reinterpret_cast<double*>(d.peer[gg] + d.o_part[par]) : d.part[par];
+                        pp[(size_t)d.rank * d.npart + ge] = psum;
+                    }
+                }
+            }
+            if (!have) break;
+            Wp = Wn; gprev = g;
+        }
+        return;
+    }
+    // =============================== EKF warps: one observation each ===============================
+    const Fs3Obs ob = po.o[wj];
+    const int sl = d.lmst[ob.lm_id];
+    const bool ident = (sl >> 1) == 0;
+    const int buf = sl & 1;
+    const size_t lbase = (size_t)ob.lm_id * 6 * ld;
+    const double* lm_own = d.lm[buf] + lbase;
+    double* lm_dst = d.lm[ident ? buf : (buf ^ 1)] + lbase;           // own columns; the other buffer when read through a row
+    const unsigned* row = ident ? nullptr : d.rows[rcur] + (size_t)((sl >> 1) - 1) * ld;
+    // issue the landing copies of group g into stage sg (each lane copies exactly the 12 doubles it will consume)
+    auto issue = [&](unsigned g, int sg, uint2 ref) {
+        double* land = s_land + ((size_t)sg * k_obs + wj) * 384 + 2 * lane;
+        const unsigned i0 = g * 64u + 2u * (unsigned)lane;
         if (ident) {
-            const double* p = d.lm[buf] + lbase + i0;
-            const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + ld);
-            const double2 c = *reinterpret_cast<const double2*>(p + 2 * ld), e = *reinterpret_cast<const double2*>(p + 3 * ld);
-            const double2 f = *reinterpret_cast<const double2*>(p + 4 * ld), g = *reinterpret_cast<const double2*>(p + 5 * ld);
-            L[0].x = a.x; L[1].x = a.y; L[0].y = b.x; L[1].y = b.y; L[0].c00 = c.x; L[1].c00 = c.y;
-            L[0].c01 = e.x; L[1].c01 = e.y; L[0].c10 = f.x; L[1].c10 = f.y; L[0].c11 = g.x; L[1].c11 = g.y;
-        } else {                                // lazy clone: read the ancestors' copies through the landmark's row
-            const uint2 ref = *reinterpret_cast<const uint2*>(d.rows[rcur] + (size_t)((s >> 1) - 1) * ld + i0);
+#pragma unroll
+            for (int f = 0; f < 6; ++f) cp_async16(land + f * 64, lm_own + f * ld + i0);
+        } else {                                  // lazy clone: the ancestors' copies, through the landmark's row
             const unsigned rr[2] = { ref.x, ref.y };
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                const double* base = d.G > 1 ? reinterpret_cast<const double*>(d.peer[rr[q] >> 28] + d.o_lm[buf]) : d.lm[buf];
-                const double* p = base + lbase + (rr[q] & 0x0FFFFFFFu);
-                L[q].x = p[0]; L[q].y = p[ld]; L[q].c00 = p[2 * ld]; L[q].c01 = p[3 * ld]; L[q].c10 = p[4 * ld]; L[q].c11 = p[5 * ld];
-            }
-        }
-    }
-    // ---- predict_particle + motion_model fs1.rs:70-77,123-137: warp 0, in place, shared with the other warps ----
-    if (wj == 0) {
-        double2 X = *reinterpret_cast<const double2*>(d.px[cur] + i0), Y = *reinterpret_cast<const double2*>(d.py[cur] + i0);
-        double2 A = *reinterpret_cast<const double2*>(d.pyaw[cur] + i0);
-        if (flags & 1) {
-            double xs[2] = { X.x, X.y }, ys[2] = { Y.x, Y.y }, as[2] = { A.x, A.y };
+                const double* base = d.G > 1 ? reinterpret_cast<const double*>(d.peer[rr[q] >> 28] + d.o_lm[buf]) + lbase : lm_own;
+                const double* p = base + (rr[q] & 0x0FFFFFFFu);
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                double z0, z1;
-                pfc_normal_pair(pfc_rng_block(seed, PFC_STREAM_FS_PREDICT, call, (uint64_t)d.off + i0 + q), &z0, &z1);
-                const double un0 = u0 + z0 * sq0;                      // fs1.rs:129
-                const double un1 = u1 + z1 * sq1;                      // fs1.rs:130
-                double s, c;
-                pfc_sincos(as[q], &s, &c);
-                xs[q] = xs[q] + un0 * dt * c;                          // motion_model fs1.rs:73-75
-                ys[q] = ys[q] + un0 * dt * s;
-                as[q] = fs_normalize_angle(as[q] + un1 * dt);
+                for (int f = 0; f < 6; ++f) cp_async8(land + f * 64 + q, p + f * ld);
             }
-            X = make_double2(xs[0], xs[1]); Y = make_double2(ys[0], ys[1]); A = make_double2(as[0], as[1]);
-            *reinterpret_cast<double2*>(d.px[cur] + i0) = X; *reinterpret_cast<double2*>(d.py[cur] + i0) = Y;
-            *reinterpret_cast<double2*>(d.pyaw[cur] + i0) = A;
         }
-        *reinterpret_cast<double2*>(s_pose + 2 * lane) = X; *reinterpret_cast<double2*>(s_pose + 64 + 2 * lane) = Y;
-        *reinterpret_cast<double2*>(s_pose + 128 + 2 * lane) = A;
+        cp_async_commit();
+    };
+    unsigned g = blockIdx.x;
+    if (g >= ngroups) return;
+    uint2 ref_next = make_uint2(0u, 0u);
+    {
+        uint2 r0 = make_uint2(0u, 0u);
+        if (!ident) r0 = *reinterpret_cast<const uint2*>(row + g * 64u + 2u * (unsigned)lane);
+        issue(g, 0, r0);
+        if (!ident && g + gridDim.x < ngroups) ref_next = *reinterpret_cast<const uint2*>(row + (g + gridDim.x) * 64u + 2u * (unsigned)lane);
     }
-    __syncthreads();
-    if (k_obs > 0) {
-        const double2 X = *reinterpret_cast<const double2*>(s_pose + 2 * lane), Y = *reinterpret_cast<const double2*>(s_pose + 64 + 2 * lane);
-        const double2 A = *reinterpret_cast<const double2*>(s_pose + 128 + 2 * lane);
-        const double px[2] = { X.x, X.y }, py[2] = { Y.x, Y.y }, pyaw[2] = { A.x, A.y };
+    for (unsigned it = 0; g < ngroups; g += gridDim.x, ++it) {
+        const int sg = (int)(it & 1u);
+        const unsigned i0 = g * 64u + 2u * (unsigned)lane;
+        // [A] this group's landmark columns out of the landing buffer
+        cp_async_wait_all();
+        FsLm L[2];
+        {
+            const double* land = s_land + ((size_t)sg * k_obs + wj) * 384 + 2 * lane;
+            const double2 a = *reinterpret_cast<const double2*>(land), b = *reinterpret_cast<const double2*>(land + 64);
+            const double2 c = *reinterpret_cast<const double2*>(land + 128), e = *reinterpret_cast<const double2*>(land + 192);
+            const double2 f = *reinterpret_cast<const double2*>(land + 256), h = *reinterpret_cast<const double2*>(land + 320);
+            L[0].x = a.x; L[1].x = a.y; L[0].y = b.x; L[1].y = b.y; L[0].c00 = c.x; L[1].c00 = c.y;
+            L[0].c01 = e.x; L[1].c01 = e.y; L[0].c10 = f.x; L[1].c10 = f.y; L[0].c11 = h.x; L[1].c11 = h.y;
+        }
+        // [B] next group's copies (its row entries were loaded one trip ago), and the row entries of the group after it
+        const unsigned gn = g + gridDim.x;
+        if (gn < ngroups) {
+            issue(gn, sg ^ 1, ref_next);
+            if (!ident && gn + gridDim.x < ngroups) ref_next = *reinterpret_cast<const uint2*>(row + (gn + gridDim.x) * 64u + 2u * (unsigned)lane);
+        }
+        // [C] the predicted pose of this group
+        nb_sync(FS3_B_POSE_FULL + sg, nsync);
+        double px[2], py[2], pyaw[2];
+        {
+            const double* sp = s_pose + sg * 192;
+            const double2 X = *reinterpret_cast<const double2*>(sp + 2 * lane), Y = *reinterpret_cast<const double2*>(sp + 64 + 2 * lane);
+            const double2 A = *reinterpret_cast<const double2*>(sp + 128 + 2 * lane);
+            px[0] = X.x; px[1] = X.y; py[0] = Y.x; py[1] = Y.y; pyaw[0] = A.x; pyaw[1] = A.y;
+        }
+        nb_arrive(FS3_B_POSE_EMPTY + sg, nsync);
+        // [D] update_landmark for the two pairs
         double lik[2] = { 1.0, 1.0 };
         int ok[2];
         fs_update_landmark_fastw<2>(L, px, py, pyaw, ob.d, ob.angle, r00, r11, lik, ok);
 #pragma unroll
         for (int q = 0; q < 2; ++q)
             if (!ok[q] && i0 + q < d.n) lik[q] = fs3_update_slow(&L[q], px[q], py[q], pyaw[q], ob.d, ob.angle, r00, r11);
-        double* o = d.lm[ident ? buf : (buf ^ 1)] + lbase + i0;       // own columns; the other buffer when read through a row
+        double* o = lm_dst + i0;
         *reinterpret_cast<double2*>(o) = make_double2(L[0].x, L[1].x);
         *reinterpret_cast<double2*>(o + ld) = make_double2(L[0].y, L[1].y);
         *reinterpret_cast<double2*>(o + 2 * ld) = make_double2(L[0].c00, L[1].c00);
         *reinterpret_cast<double2*>(o + 3 * ld) = make_double2(L[0].c01, L[1].c01);
         *reinterpret_cast<double2*>(o + 4 * ld) = make_double2(L[0].c10, L[1].c10);
         *reinterpret_cast<double2*>(o + 5 * ld) = make_double2(L[0].c11, L[1].c11);
-        *reinterpret_cast<double2*>(s_lik + wj * 64 + 2 * lane) = make_double2(lik[0], lik[1]);
+        // [E] likelihood factors to the helper
+        if (it >= 2) nb_sync(FS3_B_LIK_EMPTY + sg, nsync);
+        *reinterpret_cast<double2*>(s_lik + ((size_t)sg * k_obs + wj) * 64 + 2 * lane) = make_double2(lik[0], lik[1]);
+        __threadfence_block();
+        nb_arrive(FS3_B_LIK_FULL + sg, nsync);
     }
-    __syncthreads();
-    // ---- weights: w = (((w * l_0) * l_1) ...) in observation order (fs1.rs:181 inside the loops fs1.rs:250-256) ----
-    if (wj == 0) {
-        const double* wsrc = (flags & 1) ? d.w : d.wraw[par] + d.off;
-        const double2 W = *reinterpret_cast<const double2*>(wsrc + i0);
-        double w0 = W.x, w1 = W.y;
-        for (int j = 0; j < k_obs; ++j) {
-            const double2 l = *reinterpret_cast<const double2*>(s_lik + j * 64 + 2 * lane);
-            w0 = w0 * l.x; w1 = w1 * l.y;
-        }
-        const bool v0 = i0 < d.n, v1 = i0 + 1 < d.n;
-        if (!v0) w0 = 0.0;
-        if (!v1) w1 = 0.0;
-        const double psum = warp_sum(w0 + w1);                           // honest (tree-order) sum: steers x3_classify only
-        for (int g = 0; g < d.G; ++g) {
-            double* wr = (d.G > 1 ? reinterpret_cast<double*>(d.peer[g] + d.o_wraw[par]) : d.wraw[par]) + d.off;
-            if (v1) *reinterpret_cast<double2*>(wr + i0) = make_double2(w0, w1);
-            else if (v0) wr[i0] = w0;
-            if (lane == 0) {
-                double* pp = d.G > 1 ? reinterpret_cast<double*>(d.peer[g] + d.o_part[par]) : d.part[par];
-                pp[(size_t)d.rank * d.npart + blockIdx.x] = psum;
-            }
-        }
-    }
-    // ---- completion: the last CTA does the lazy-clone bookkeeping and tells the peers ----
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (d.G > 1) __threadfence_system(); else __threadfence();
-        s_last = (atomicAdd(&st->ekf_done, 1u) + 1u == gridDim.x) ? 1 : 0;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    for (int j = threadIdx.x; j < k_obs; j += blockDim.x) {               // updated landmarks: own columns of the other buffer
+}
+
+// lazy-clone bookkeeping after an EKF launch: the landmarks it updated through a row now live in own columns of the other
+// buffer.  (Its own tiny launch between the pieces of a split observation list; the post kernel does it for the last piece.)
+__device__ __forceinline__ void fs3_mark_updated(const Fs3Dev& d, const Fs3ObsParam& po, int k_obs) {
+    for (int j = threadIdx.x; j < k_obs; j += blockDim.x) {
         const int l = po.o[j].lm_id, s = d.lmst[l];
         if (s >> 1) d.lmst[l] = (s & 1) ^ 1;
     }
-    if (threadIdx.x == 0) st->ekf_done = 0;
-    if ((flags & 2) && d.G > 1) fs3_signal_peers(d, 0, step + 1u);
+}
+// one-warp launches that stand in for the kernels' own waits / signals when several ranks share a GPU (wait_inline == 0)
+__global__ void fs3_wait_kernel(const __grid_constant__ Fs3Dev d, int which, unsigned target) {
+    pf_grid_dep_sync();
+    if (threadIdx.x == 0) fs3_wait_peers(d, which, target);
+}
+__global__ void fs3_signal_kernel(const __grid_constant__ Fs3Dev d, int which, unsigned value) {
+    pf_grid_dep_sync();
+    fs3_signal_peers(d, which, value);
+}
+__global__ void fs3_mark_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsParam po, int k_obs) {
+    pf_grid_dep_sync();
+    fs3_mark_updated(d, po, k_obs);
 }
 
 // =====================================================================================================================
 // post kernel
 // =====================================================================================================================
+// Written for LATENCY: it moves ~1 MB, so what it costs is instruction fetch (every instruction runs once per warp), waits
+// at barriers and dependent memory round trips.  Hence: one small out-of-line routine (fs3_xsum) serves every exact sum; four
+// block barriers and one grid barrier per sum; the chain over the dirty values is evaluated by warp 0 with warp primitives
+// while the other warps sleep at a block barrier; grid barriers are per-round arrival counters (no generation juggling).
 template <int NT>
 struct Fs3Sh {
-    double sd[NT / 32]; unsigned long long su[NT / 32]; int si[NT / 32];
-    unsigned long long tP[FS3_MAX_TILES], tPoff[FS3_MAX_TILES];
-    int tD[FS3_MAX_TILES], tDoff[FS3_MAX_TILES];
-    unsigned long long eP[FS3_ENT_CAP]; double eV[FS3_ENT_CAP]; int eL[FS3_ENT_CAP];
-    double bef[FS3_ENT_CAP], aft[FS3_ENT_CAP];
+    double wd[2][NT / 32]; unsigned long long wu[2][NT / 32]; int wi[2][NT / 32];   // warp totals (double-buffered by round)
+    double red[2][NT / 32];
+    unsigned long long tPoff[FS3_MAX_TILES];                  // clean-increment sum in front of every tile
+    unsigned ukey[FS3_ENT_CAP], skey[FS3_ENT_CAP];            // dirty values: global index (unsorted / sorted)
+    unsigned long long sP[FS3_ENT_CAP]; double sV[FS3_ENT_CAP]; int sL[FS3_ENT_CAP];
+    double bef[FS3_ENT_CAP], aft[FS3_ENT_CAP];                // exact sum in front of / right after each dirty value
     double total, tbase, bcast;
     unsigned long long Ptot;
     int D, fail, last;
-    unsigned rowbits[32]; unsigned short rowlist[1024]; int nrows, newrow;
+    x3_comb_table comb;
 };
 
-__device__ __forceinline__ void fs3_grid_sync(Fs3State* st, unsigned nblocks) {
+#define FS3_TRACE(k) do { if (d.trace && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); d.trace[k] += t__ - t_prev; t_prev = t__; } } while (0)
+
+// grid barrier `round` of this launch: every CTA arrives once per round; the counters are zeroed by the launch's last CTA
+__device__ __forceinline__ void fs3_bar_arrive(const Fs3Dev& d, int round) {        // thread 0, after a block barrier
+    __threadfence();
+    atomicAdd(d.bar + round, 1u);
+}
+__device__ __forceinline__ void fs3_bar_wait(const Fs3Dev& d, int round, unsigned nblocks) {   // one thread
+    unsigned spins = 0;
+    while (*reinterpret_cast<volatile unsigned*>(d.bar + round) < nblocks) { if (++spins > FS3_SPIN_LIMIT) { d.st->err = 1; break; } __nanosleep(20); }
+    __threadfence();
+}
+template <int NT>
+__device__ __forceinline__ void fs3_grid_sync(const Fs3Dev& d, int round, unsigned nblocks) {
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned gen = ld_acquire_gpu(&st->bar_gen);
-        __threadfence();
-        if (atomicAdd(&st->bar_count, 1u) + 1u == nblocks) {
-            st->bar_count = 0;
-            __threadfence();
-            atomicAdd(&st->bar_gen, 1u);
-        } else {
-            unsigned spins = 0;
-            while (ld_acquire_gpu(&st->bar_gen) == gen) { if (++spins > FS3_SPIN_LIMIT) { st->err = 1; break; } }
-        }
-        __threadfence();
-    }
+    if (threadIdx.x == 0) { fs3_bar_arrive(d, round); fs3_bar_wait(d, round, nblocks); }
     __syncthreads();
 }
 
-// exclusive prefix over the block's threads (thread order) of a double; *tot = block total (tree order, same in every CTA)
+// exclusive prefix over the block's threads (thread order) of a double, ONE block barrier (sm: this round's scratch)
 template <int NT>
-__device__ __forceinline__ double fs3_scan_d(double x, double* tot, double* sm) {
+__device__ __forceinline__ double fs3_scan_d(double x, double* sm) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double inc = x;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const double y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = y + inc; }
     double ex = __shfl_up_sync(0xffffffffu, inc, 1);
     if (lane == 0) ex = 0.0;
-    __syncthreads();
     if (lane == 31) sm[wid] = inc;
     __syncthreads();
-    double woff = 0.0, t = 0.0;
-#pragma unroll
-    for (int w = 0; w < NT / 32; ++w) { const double s = sm[w]; if (w < wid) woff += s; t += s; }
-    *tot = t;
+    double woff = 0.0;
+    for (int w = 0; w < wid; ++w) woff += sm[w];
     return woff + ex;
 }
-// the same for a (u64 increment sum, int count) pair
+// the same for a (u64 increment sum, int count) pair; also returns the block totals
 template <int NT>
 __device__ __forceinline__ void fs3_scan_ui(unsigned long long p, int c, unsigned long long* pex, int* cex, unsigned long long* ptot, int* ctot,
                                             unsigned long long* smu, int* smi) {
@@ -317,25 +417,22 @@ __device__ __forceinline__ void fs3_scan_ui(unsigned long long p, int c, unsigne
         const unsigned long long y = __shfl_up_sync(0xffffffffu, ip, o); const int z = __shfl_up_sync(0xffffffffu, ic, o);
         if (lane >= o) { ip += y; ic += z; }
     }
-    __syncthreads();
     if (lane == 31) { smu[wid] = ip; smi[wid] = ic; }
     __syncthreads();
     unsigned long long wp = 0, tp = 0; int wc = 0, tc = 0;
-#pragma unroll
     for (int w = 0; w < NT / 32; ++w) { const unsigned long long a = smu[w]; const int b = smi[w]; if (w < wid) { wp += a; wc += b; } tp += a; tc += b; }
     *pex = wp + ip - p; *cex = wc + ic - c; *ptot = tp; *ctot = tc;
 }
+// block sums of two doubles at once (tree order, identical in every CTA; valid in all threads); ONE block barrier
 template <int NT>
-__device__ __forceinline__ double fs3_block_sum(double x, double* sm) {    // tree order, identical in every CTA; valid in all threads
+__device__ __forceinline__ void fs3_block_sum2(double& x, double& y, double* smx, double* smy) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    x = warp_sum(x);
+    x = warp_sum(x); y = warp_sum(y);
+    if (lane == 0) { smx[wid] = x; smy[wid] = y; }
     __syncthreads();
-    if (lane == 0) sm[wid] = x;
-    __syncthreads();
-    double t = 0.0;
-#pragma unroll
-    for (int w = 0; w < NT / 32; ++w) t += sm[w];
-    return t;
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < NT / 32; ++w) { a += smx[w]; b += smy[w]; }
+    x = a; y = b;
 }
 
 // value i of the sum `slot`, recomputed from global memory (serial walks only)
@@ -347,26 +444,45 @@ __device__ __forceinline__ double fs3_value(const Fs3Dev& d, int slot, size_t i,
     if (slot == 3) return S2 > 0.0 ? w / S2 : w;
     return i == 0 ? r0 : inv;
 }
+// exact by construction: one thread walks all values in order (bad values, too many dirty ones, failed certificate)
+template <int NT>
+__device__ __noinline__ void fs3_serial_walk(const Fs3Dev& d, Fs3Sh<NT>& sh, unsigned K, int slot, double* out, int par, double S2, double r0, double inv) {
+    if (threadIdx.x == 0) {
+        const size_t T = (size_t)NT * K, lo = (size_t)blockIdx.x * T;
+        double s = 0.0;
+        sh.tbase = 0.0;
+        for (size_t i = 0; i < d.n_glob; ++i) { if (i == lo) sh.tbase = s; s = s + fs3_value(d, slot, i, par, S2, r0, inv); }
+        if (lo >= d.n_glob) sh.tbase = s;
+        sh.total = s;
+        if (blockIdx.x == 0) d.st->serial_walks += 1;
+        if (out) {
+            double c = sh.tbase;
+            for (size_t i = lo; i < lo + T && i < d.n_glob; ++i) { c = c + fs3_value(d, slot, i, par, S2, r0, inv); out[i] = c; }
+        }
+    }
+    __syncthreads();
+}
 
 // One exact sequential sum over the n_glob values held tile-wise in shared memory (thread t owns values t*K .. t*K+K-1 of its
 // tile, stored at vals[k*NT + t]).  toff = approximate sum of everything in front of this tile.  Returns the exact total
 // (identical in every CTA); with out != nullptr also stores the exact inclusive prefix of every value to out[global index].
-// Contains ONE grid barrier.
+// Contains ONE grid barrier (`round`).
 template <int NT>
-__device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const double* vals, unsigned K, unsigned nt, double toff, int slot,
+__device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const double* vals, unsigned K, unsigned nt, double toff, int slot, int round,
                                         unsigned m32, double* out, int par, double S2, double r0, double inv, double extraQ) {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, pp = round & 1;
     const unsigned b = blockIdx.x;
     const size_t T = (size_t)NT * K;
-    Fs3State* st = d.st;
+    unsigned long long t_prev = 0;
+    const int tb0 = slot == 0 ? 8 : (slot == 3 ? 12 : 24);   // trace slots (PFGPU_POST_TRACE): S -> 8..11, CDF -> 12..15
+    if (d.trace && b == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_prev));
     // ---- approximate prefixes, classification, tile aggregate ----
     double ts = 0.0; bool bad = false;
     for (unsigned k = 0; k < K; ++k) { const double v = vals[k * NT + tid]; ts += v; if (!(v >= 0.0) || !(v <= 1.7976931348623157e308)) bad = true; }
-    double btot;
-    const double excl = fs3_scan_d<NT>(ts, &btot, sh.sd);
+    const double a_first = toff + fs3_scan_d<NT>(ts, sh.wd[pp]);
     unsigned long long P = 0; int nd = 0;
     {
-        double a = toff + excl;
+        double a = a_first;
         for (unsigned k = 0; k < K; ++k) {
             const double v = vals[k * NT + tid], a1 = a + v;
             unsigned long long inc; int lvl;
@@ -375,109 +491,114 @@ __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const do
         }
     }
     unsigned long long Pex, Ptile; int dex, ndtile;
-    fs3_scan_ui<NT>(P, nd, &Pex, &dex, &Ptile, &ndtile, sh.su, sh.si);
-    const size_t sb = (size_t)slot * FS3_MAX_TILES + b;
-    if (nd > 0 && ndtile <= FS3_ENT_TILE) {                 // rare: itemise this thread's dirty values
-        double a = toff + excl; unsigned long long Pr = Pex; int e = dex;
+    fs3_scan_ui<NT>(P, nd, &Pex, &dex, &Ptile, &ndtile, sh.wu[pp], sh.wi[pp]);
+    if (nd > 0) {                                              // rare: itemise this thread's dirty values (any order; sorted by the chain)
+        const unsigned e0 = atomicAdd(d.entCnt + slot, (unsigned)nd);
+        double a = a_first; unsigned long long Pr = Pex; unsigned e = e0;
         for (unsigned k = 0; k < K; ++k) {
             const double v = vals[k * NT + tid], a1 = a + v;
             unsigned long long inc; int lvl;
-            if (x3_classify(v, a, a1, m32, &inc, &lvl)) { const size_t o = sb * FS3_ENT_TILE + e; d.entP[o] = Pr; d.entV[o] = v; d.entL[o] = lvl; e++; }
-            else Pr += inc;
+            if (x3_classify(v, a, a1, m32, &inc, &lvl)) {
+                if (e < FS3_ENT_CAP) {
+                    const size_t o = (size_t)slot * FS3_ENT_CAP + e;
+                    d.entKey[o] = (unsigned)((size_t)b * T + (size_t)tid * K + k); d.entTile[o] = b; d.entP[o] = Pr; d.entV[o] = v; d.entL[o] = lvl;
+                }
+                e++;
+            } else Pr += inc;
             a = a1;
         }
     }
     if (bad) d.flagsg[slot] = 1;
-    if (tid == 0) { d.tileP[sb] = Ptile; d.tileD[sb] = ndtile <= FS3_ENT_TILE ? ndtile : -1; if (slot == 0) d.tileQ[b] = extraQ; }
-    fs3_grid_sync(st, nt);
-    // ---- chain: every CTA evaluates it (tens of entries) ----
-    if (tid == 0) { sh.fail = __ldcg(d.flagsg + slot); }
+    if (tid == 0) { d.tileP[(size_t)slot * FS3_MAX_TILES + b] = Ptile; if (slot == 0) d.tileQ[b] = extraQ; }
+    FS3_TRACE(tb0);
     __syncthreads();
-    {
-        unsigned long long tp = 0; int td = 0;
-        if ((unsigned)tid < nt) { tp = __ldcg(d.tileP + (size_t)slot * FS3_MAX_TILES + tid); td = __ldcg(d.tileD + (size_t)slot * FS3_MAX_TILES + tid); }
-        if (td < 0) { sh.fail = 1; td = 0; }
-        unsigned long long pex, ptot; int cex, ctot;
-        fs3_scan_ui<NT>(tp, td, &pex, &cex, &ptot, &ctot, sh.su, sh.si);
-        if ((unsigned)tid < nt) { sh.tPoff[tid] = pex; sh.tDoff[tid] = cex; sh.tD[tid] = td; }
-        if (tid == 0) { sh.Ptot = ptot; sh.D = ctot; if (ctot > FS3_ENT_CAP) sh.fail = 1; }
-    }
-    __syncthreads();
-    const int D = sh.D;
-    if (!sh.fail) {
-        for (unsigned x = tid; x < nt * FS3_ENT_TILE; x += NT) {       // one (tile, entry) pair per thread and trip: the loads overlap
-            const unsigned tb = x / FS3_ENT_TILE; const int e = (int)(x % FS3_ENT_TILE);
-            if (e < sh.tD[tb]) {
-                const size_t g = ((size_t)slot * FS3_MAX_TILES + tb) * FS3_ENT_TILE + e;
-                const int o = sh.tDoff[tb] + e;
-                sh.eP[o] = sh.tPoff[tb] + __ldcg(d.entP + g); sh.eV[o] = __ldcg(d.entV + g); sh.eL[o] = __ldcg(d.entL + g);
-            }
+    // ---- grid barrier + chain: warp 0 only; the other warps wait at the block barrier below ----
+    if (tid < 32) {
+        if (tid == 0) { fs3_bar_arrive(d, round); fs3_bar_wait(d, round, nt); }
+        __syncwarp();
+        FS3_TRACE(tb0 + 1);
+        // clean-increment sum in front of every tile (lane owns `per` consecutive tiles)
+        const unsigned per = (nt + 31u) / 32u, t0 = (unsigned)lane * per;
+        unsigned long long loc[(FS3_MAX_TILES + 31) / 32], lsum = 0;
+#pragma unroll
+        for (unsigned i = 0; i < (FS3_MAX_TILES + 31) / 32; ++i) {
+            loc[i] = (i < per && t0 + i < nt) ? __ldcg(d.tileP + (size_t)slot * FS3_MAX_TILES + t0 + i) : 0ull;
+            lsum += loc[i];
         }
-        __syncthreads();
-        if (tid == 0) {                                       // the serial part: one integer add + one FP add per dirty value
+        const unsigned cnt = __ldcg(d.entCnt + slot);
+        int fail = __ldcg(d.flagsg + slot) | (cnt > FS3_ENT_CAP ? 1 : 0);
+        unsigned long long inc = lsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+        const unsigned long long Ptot = __shfl_sync(0xffffffffu, inc, 31);
+        unsigned long long run = inc - lsum;
+#pragma unroll
+        for (unsigned i = 0; i < (FS3_MAX_TILES + 31) / 32; ++i) { if (i < per && t0 + i < nt) sh.tPoff[t0 + i] = run; run += loc[i]; }
+        const int D = fail ? 0 : (int)cnt;
+        const size_t eb = (size_t)slot * FS3_ENT_CAP;
+        for (int e = lane; e < D; e += 32) sh.ukey[e] = __ldcg(d.entKey + eb + e);
+        __syncwarp();
+        for (int e = lane; e < D; e += 32) {                   // rank = position in index order (keys are distinct)
+            const unsigned key = sh.ukey[e];
+            int rank = 0;
+            for (int j = 0; j < D; ++j) rank += sh.ukey[j] < key ? 1 : 0;
+            sh.skey[rank] = key; sh.sP[rank] = sh.tPoff[__ldcg(d.entTile + eb + e)] + __ldcg(d.entP + eb + e);
+            sh.sV[rank] = __ldcg(d.entV + eb + e); sh.sL[rank] = __ldcg(d.entL + eb + e);
+        }
+        __syncwarp();
+        double total = 0.0;
+        if (lane == 0) {                                       // the serial part: one integer add + one FP add per dirty value
             double s = 0.0; unsigned long long prev = 0;
             for (int o = 0; o < D; ++o) {
-                const unsigned long long p = sh.eP[o];
+                const unsigned long long p = sh.sP[o];
                 sh.bef[o] = s;
-                s = pfc_u2d(pfc_d2u(s) + (p - prev)) + sh.eV[o];
+                s = pfc_u2d(pfc_d2u(s) + (p - prev)) + sh.sV[o];
                 sh.aft[o] = s; prev = p;
             }
             int ok = 1;
-            sh.total = x3_apply(s, sh.Ptot - prev, -1, &ok);
-            if (!ok) sh.fail = 1;
-            if (b == 0) st->dirty_last = D;
+            total = x3_apply(s, Ptot - prev, -1, &ok);
+            if (!ok) fail = 1;
         }
-        __syncthreads();
-        for (int o = tid; o < D; o += NT) {                   // certificates of the clean runs, in parallel
-            const unsigned long long dp = sh.eP[o] - (o ? sh.eP[o - 1] : 0ull);
+        __syncwarp();
+        for (int o = lane; o < D; o += 32) {                   // certificates of the clean runs, in parallel
+            const unsigned long long dp = sh.sP[o] - (o ? sh.sP[o - 1] : 0ull);
             int ok = 1;
-            (void)x3_apply(sh.bef[o], dp, sh.eL[o], &ok);
-            if (!ok) sh.fail = 1;
+            (void)x3_apply(sh.bef[o], dp, sh.sL[o], &ok);
+            if (!ok) fail = 1;
         }
-        __syncthreads();
+        fail = __any_sync(0xffffffffu, fail);
+        if (lane == 0) { sh.total = total; sh.Ptot = Ptot; sh.D = D; sh.fail = fail; if (b == 0) d.st->dirty_last = (int)cnt; }
     }
-    if (sh.fail) {                                            // exact by construction: one thread walks all values in order
-        if (tid == 0) {
-            double s = 0.0;
-            const size_t lo = (size_t)b * T;
-            for (size_t i = 0; i < d.n_glob; ++i) { if (i == lo) sh.tbase = s; s = s + fs3_value(d, slot, i, par, S2, r0, inv); }
-            if (lo >= d.n_glob) sh.tbase = s;
-            sh.total = s;
-            if (b == 0) { st->serial_walks += 1; }
-            if (out) {
-                double c = sh.tbase;
-                for (size_t i = lo; i < lo + T && i < d.n_glob; ++i) { c = c + fs3_value(d, slot, i, par, S2, r0, inv); out[i] = c; }
-            }
-        }
-        __syncthreads();
-        return sh.total;
-    }
+    __syncthreads();
+    FS3_TRACE(tb0 + 2);
+    if (sh.fail) { fs3_serial_walk<NT>(d, sh, K, slot, out, par, S2, r0, inv); return sh.total; }
     if (out) {                                                // exact inclusive prefix of every value of this tile
-        int ko = sh.tDoff[b] + dex;
-        double base = ko ? sh.aft[ko - 1] : 0.0;
-        unsigned long long Pb = ko ? sh.eP[ko - 1] : 0ull, Pc = sh.tPoff[b] + Pex;
-        double a = toff + excl;
-        int ok = 1;
+        const int D = sh.D;
         const size_t g0 = (size_t)b * T + (size_t)tid * K;
+        int ko = 0;                                            // dirty values in front of this thread's first value
+        { int lo = 0, hi = D; while (lo < hi) { const int mid = (lo + hi) >> 1; if ((size_t)sh.skey[mid] < g0) lo = mid + 1; else hi = mid; } ko = lo; }
+        double base = ko ? sh.aft[ko - 1] : 0.0;
+        unsigned long long Pb = ko ? sh.sP[ko - 1] : 0ull, Pc = sh.tPoff[b] + Pex;
+        double a = a_first;
+        int ok = 1;
         for (unsigned k = 0; k < K; ++k) {
             const double v = vals[k * NT + tid], a1 = a + v;
             unsigned long long inc; int lvl; double c;
-            if (x3_classify(v, a, a1, m32, &inc, &lvl)) { base = sh.aft[ko]; Pb = sh.eP[ko]; ko++; c = base; }
+            if (x3_classify(v, a, a1, m32, &inc, &lvl)) { base = sh.aft[ko]; Pb = sh.sP[ko]; ko++; c = base; }
             else { Pc += inc; c = x3_apply(base, Pc - Pb, inc ? lvl : -1, &ok); }
             if (g0 + k < d.n_glob) out[g0 + k] = c;
             a = a1;
         }
-        if (!ok) atomicAdd(&st->cert_fail, 1);
+        if (!ok) atomicAdd(&d.st->cert_fail, 1);
+        FS3_TRACE(tb0 + 3);
     }
     return sh.total;
 }
 
-#define FS3_TRACE(k) do { if (d.trace && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); d.trace[k] += t__ - t_prev; t_prev = t__; } } while (0)
-
 // lower bound of r in the exact CDF, clamped: "while r > cum_sum[j+1] && j < n-1 { j += 1 }" (fs1.rs:224-226) with r and j both
 // non-decreasing over the slots, i.e. the first j with c_j >= r.  Searched inside [lo, hi) (c_{lo-1} < r guaranteed by the caller).
 __device__ __forceinline__ unsigned fs3_lower_bound(const double* c, unsigned lo, unsigned hi, double r) {
-    while (lo < hi) { const unsigned mid = lo + ((hi - lo) >> 1); if (c[mid] < r) lo = mid + 1; else hi = mid; }
+    while (lo < hi) { const unsigned mid = lo + ((hi - lo) >> 1); if (__ldcg(c + mid) < r) lo = mid + 1; else hi = mid; }
     return lo;
 }
 // warp-cooperative 32-way search of one r over [0, n): returns the lower bound (all lanes)
@@ -487,27 +608,23 @@ __device__ __forceinline__ unsigned fs3_warp_search(const double* c, unsigned n,
     while (hi - lo > 32) {
         const unsigned step = (hi - lo + 32) / 33;            // probes lo + (lane+1)*step - 1
         const unsigned long long pi = (unsigned long long)lo + (unsigned long long)(lane + 1) * step - 1ull;
-        const bool below = pi < hi ? (c[pi] < r) : false;     // monotone: a prefix of lanes is "below"
-        const unsigned mask = __ballot_sync(0xffffffffu, below);
-        const int cnt = __popc(mask);
-        const unsigned nlo = cnt ? lo + (unsigned)cnt * step : lo;
+        const bool below = pi < hi ? (__ldcg(c + pi) < r) : false;     // monotone: a prefix of lanes is "below"
+        const int cnt = __popc(__ballot_sync(0xffffffffu, below));
         const unsigned long long nh = (unsigned long long)lo + (unsigned long long)(cnt + 1) * step - 1ull;
         if (cnt < 32 && nh < hi) hi = (unsigned)nh;           // lane cnt probed c[nh] >= r (with cnt == 32 nobody probed nh)
-        lo = nlo;
+        if (cnt) lo += (unsigned)cnt * step;
     }
-    {
-        const unsigned pi = lo + (unsigned)lane;
-        const bool below = pi < hi ? (c[pi] < r) : false;
-        lo += (unsigned)__popc(__ballot_sync(0xffffffffu, below));
-    }
-    return lo;
+    const unsigned pi = lo + (unsigned)lane;
+    const bool below = pi < hi ? (__ldcg(c + pi) < r) : false;
+    return lo + (unsigned)__popc(__ballot_sync(0xffffffffu, below));
 }
 
 template <int NT>
 __global__ void __launch_bounds__(NT, 1)
-fs3_post_kernel(const __grid_constant__ Fs3Dev d, double nth, uint64_t seed, unsigned step, unsigned K, unsigned m32, int log2n) {
+fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsParam po, int k_last, double nth, uint64_t seed, unsigned step,
+                unsigned K, unsigned m32, int log2n) {
     pf_grid_dep_sync();
-    extern __shared__ double vals[];                          // [K][NT]
+    extern __shared__ __align__(16) double vals[];            // [K][NT]
     __shared__ Fs3Sh<NT> sh;
     Fs3State* st = d.st;
     const int tid = threadIdx.x;
@@ -516,30 +633,53 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, double nth, uint64_t seed, uns
     const int par = (int)(step & 1u);
     unsigned long long t_prev = 0;
     if (d.trace && b == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_prev));
-    if (d.G > 1) {                                            // every rank's weights of this step are in my copy
-        if (tid == 0) fs3_wait_peers(d, 0, step + 1u);
+    if (d.G > 1) {      // my EKF launch is complete: its pushes are in every peer's copy.  Say so, then wait for the others'.
+        if (b == 0) fs3_signal_peers(d, 0, step + 1u);
+        if (d.wait_inline) {
+            if (tid == 0) fs3_wait_peers(d, 0, step + 1u);
+            __syncthreads();
+        }
+    }
+    if (b == 0) {
+        // lazy-clone bookkeeping of the EKF launch that just ran, then the rows a resample would have to compose: one bit per
+        // row some landmark still reads through; the identity landmarks would get ONE new row (the first free id: with an
+        // identity landmark at most m - 1 rows are live).  Other CTAs read the list only after >= 3 grid barriers.
+        fs3_mark_updated(d, po, k_last);
+        __shared__ unsigned s_bits[32];
+        if (tid < 32) s_bits[tid] = 0u;
         __syncthreads();
+        int any_ident = 0;
+        for (unsigned l = tid; l < d.m; l += NT) { const int s = d.lmst[l]; if (s >> 1) atomicOr(&s_bits[((s >> 1) - 1) >> 5], 1u << (((s >> 1) - 1) & 31)); else any_ident = 1; }
+        any_ident = __syncthreads_or(any_ident);
+        if (tid < 32) {
+            const unsigned bits = s_bits[tid];
+            const int cnt = __popc(bits);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += y; }
+            int pos = incl - cnt;
+            for (unsigned x = bits; x; x &= x - 1) d.rowlist[pos++] = (unsigned short)(tid * 32 + __ffs(x) - 1);
+            const unsigned fr = ~bits;
+            const unsigned has = __ballot_sync(0xffffffffu, fr != 0u);
+            if (tid == 31) d.rowinfo[0] = incl;
+            if (tid == 0) d.rowinfo[1] = -1;
+            __syncwarp();
+            if (any_ident && tid == __ffs(has) - 1) d.rowinfo[1] = tid * 32 + __ffs(fr) - 1;
+        }
     }
     // ---- load this tile's weights; approximate sum of everything in front of the tile from the 64-particle partials ----
     const size_t g0 = (size_t)b * T + (size_t)tid * K;
     double q = 0.0;
     for (unsigned k = 0; k < K; ++k) { const double v = g0 + k < ng ? __ldcg(d.wraw[par] + g0 + k) : 0.0; vals[k * NT + tid] = v; q += v * v; }
-    double toff;
+    double toff = 0.0;
     {
-        // partials are indexed rank * npart + cta; global slot i belongs to partial (i / n) * npart + (i % n) / 64
-        const size_t first = (size_t)b * T;                   // a multiple of 64 (and of n when it crosses ranks: n % T or T % n == 0 is NOT required)
-        double acc = 0.0;
-        const size_t np_total = (size_t)d.G * d.npart;
-        for (size_t p = tid; p < np_total; p += NT) {
-            const size_t slot0 = (p / d.npart) * (size_t)d.n + (p % d.npart) * 64;      // first global slot of partial p
-            if (slot0 < first) acc += __ldcg(d.part[par] + p);
-        }
-        toff = fs3_block_sum<NT>(acc, sh.sd);
+        const unsigned pfirst = (unsigned)(((size_t)b * T) / 64);      // partial p covers global slots [64 p, 64 p + 64)
+        for (unsigned p = tid; p < pfirst; p += NT) toff += __ldcg(d.part[par] + p);
     }
-    const double qtile = fs3_block_sum<NT>(q, sh.sd);
+    fs3_block_sum2<NT>(toff, q, sh.red[0], sh.red[1]);
     FS3_TRACE(0);
     // ---------------- S = sum w_raw (normalize_weights fs1.rs:196-203) ----------------
-    const double S = fs3_xsum<NT>(d, sh, vals, K, nt, toff, 0, m32, nullptr, par, 0.0, 0.0, 0.0, qtile);
+    const double S = fs3_xsum<NT>(d, sh, vals, K, nt, toff, 0, 0, m32, nullptr, par, 0.0, 0.0, 0.0, q);
     FS3_TRACE(1);
     // w = w_raw / S; best particle of the tile (LAST maximum, fs1.rs:269-274)
     double bw = -1.0; unsigned bi = 0;
@@ -554,34 +694,27 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, double nth, uint64_t seed, uns
             if (v >= bw) { bw = v; bi = (unsigned)i; }
         }
     }
-    {   // block arg-max with "last wins among equals"
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ow = __shfl_xor_sync(0xffffffffu, bw, o); const unsigned oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ow > bw || (ow == bw && oi > bi)) { bw = ow; bi = oi; }
-        }
-        __syncthreads();
-        if ((tid & 31) == 0) { sh.sd[tid >> 5] = bw; sh.si[tid >> 5] = (int)bi; }
-        __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < NT / 32; ++w) { const double ow = sh.sd[w]; const unsigned oi = (unsigned)sh.si[w]; if (ow > bw || (ow == bw && oi > bi)) { bw = ow; bi = oi; } }
-            d.tileBw[b] = bw; d.tileBi[b] = bi;
-        }
+    for (int o = 16; o > 0; o >>= 1) {      // arg-max with "last wins among equals"
+        const double ow = __shfl_xor_sync(0xffffffffu, bw, o); const unsigned oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ow > bw || (ow == bw && oi > bi)) { bw = ow; bi = oi; }
     }
+    if ((tid & 31) == 0) { sh.red[0][tid >> 5] = bw; sh.wi[0][tid >> 5] = (int)bi; }
     // ---------------- gate: neff = 1 / sum w^2 < NTH (compute_neff fs1.rs:186-193, fs1.rs:262-263) ----------------
     // Only the DECISION feeds back into the state.  Q is first taken from the tree-order sums of w_raw^2 published with the
     // aggregates of S: sum (w_raw_i / S)^2 differs from the reference's sequential sum of fl(w_raw_i / S)^2 by at most
     // (n + 64) 2^-51 relatively; only when neff lands that close to NTH is the exact sequential sum walked.
-    double Q;
-    {
-        const double qs = (unsigned)tid < nt ? __ldcg(d.tileQ + tid) : 0.0;
-        Q = fs3_block_sum<NT>(qs, sh.sd);
-        if (S > 0.0) Q = (Q / S) / S;
+    double Q = (unsigned)tid < nt ? __ldcg(d.tileQ + tid) : 0.0, dummy = 0.0;
+    fs3_block_sum2<NT>(Q, dummy, sh.red[1], sh.wd[1]);         // (also orders the arg-max partials above)
+    if (tid == 0) {
+        for (int w = 1; w < NT / 32; ++w) { const double ow = sh.red[0][w]; const unsigned oi = (unsigned)sh.wi[0][w]; if (ow > bw || (ow == bw && oi > bi)) { bw = ow; bi = oi; } }
+        d.tileBw[b] = bw; d.tileBi[b] = bi;
     }
+    if (S > 0.0) Q = (Q / S) / S;
     double neff = Q > 0.0 ? 1.0 / Q : 0.0;
     const double slack = 16.0 * (double)(ng + 64) * 2.220446049250313e-16;
     if (!(fabs(neff - nth) > slack * fmax(fabs(nth), fabs(neff)))) {     // rare; the same decision in every CTA
-        fs3_grid_sync(st, nt);                                 // wn_all is complete
+        fs3_grid_sync<NT>(d, 6, nt);                           // wn_all is complete
         if (tid == 0) {
             double s = 0.0;
             for (size_t i = 0; i < ng; ++i) { const double w = __ldcg(d.wn_all + i); s = s + w * w; }
@@ -599,12 +732,12 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, double nth, uint64_t seed, uns
     if (gate) {
         // ---------------- resample() re-normalises first (fs1.rs:207) ----------------
         const double toff2 = S > 0.0 ? toff / S : toff;
-        S2 = fs3_xsum<NT>(d, sh, vals, K, nt, toff2, 2, m32, nullptr, par, 0.0, 0.0, 0.0, 0.0);
+        S2 = fs3_xsum<NT>(d, sh, vals, K, nt, toff2, 2, 1, m32, nullptr, par, 0.0, 0.0, 0.0, 0.0);
         FS3_TRACE(3);
         if (S2 > 0.0) for (unsigned k = 0; k < K; ++k) vals[k * NT + tid] = vals[k * NT + tid] / S2;
         // ---------------- cum_sum fs1.rs:213-216 ----------------
         const double toff3 = S2 > 0.0 ? toff2 / S2 : toff2;
-        (void)fs3_xsum<NT>(d, sh, vals, K, nt, toff3, 3, m32, d.cum_all, par, S2, 0.0, 0.0, 0.0);
+        (void)fs3_xsum<NT>(d, sh, vals, K, nt, toff3, 3, 2, m32, d.cum_all, par, S2, 0.0, 0.0, 0.0);
         FS3_TRACE(4);
         // ---------------- the comb r, r + 1/n, ... accumulated sequentially (fs1.rs:219-230) ----------------
         {
@@ -615,35 +748,15 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, double nth, uint64_t seed, uns
             for (unsigned k = 0; k < K; ++k) { const size_t i = g0 + k; vals[k * NT + tid] = i < ng ? (i == 0 ? r0 : inv) : 0.0; }
             const double toff4 = b == 0 ? 0.0 : r0 + ((double)((size_t)b * T) - 1.0) * inv;
             __syncthreads();
-            (void)fs3_xsum<NT>(d, sh, vals, K, nt, toff4, 4, m32, d.rcomb_all, par, S2, r0, inv, 0.0);
+            (void)fs3_xsum<NT>(d, sh, vals, K, nt, toff4, 4, 3, m32, d.rcomb_all, par, S2, r0, inv, 0.0);
+        } else if (tid == 0) {
+            x3_comb_build(&sh.comb, r0, inv, (double)ng, ng);  // closed form: one segment per binade
         }
-        fs3_grid_sync(st, nt);                                 // the whole CDF (and comb) is visible
+        fs3_grid_sync<NT>(d, 4, nt);                           // the whole CDF (and comb) is visible
         FS3_TRACE(5);
         // ---------------- index walk, pose clone, lazy map clone for this CTA's share of the local slots ----------------
-        // live rows: one bit per row some landmark still reads through; identity landmarks get ONE new row
-        if (tid < 32) sh.rowbits[tid] = 0u;
-        if (tid == 0) sh.newrow = -1;
-        __syncthreads();
-        int any_ident = 0;
-        for (unsigned l = tid; l < d.m; l += NT) { const int s = d.lmst[l]; if (s >> 1) atomicOr(&sh.rowbits[((s >> 1) - 1) >> 5], 1u << (((s >> 1) - 1) & 31)); else any_ident = 1; }
-        any_ident = __syncthreads_or(any_ident);
-        if (tid < 32) {
-            const unsigned bits = sh.rowbits[tid];
-            int cnt = __popc(bits), incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += y; }
-            int pos = incl - cnt;
-            for (unsigned x = bits; x; x &= x - 1) sh.rowlist[pos++] = (unsigned short)(tid * 32 + __ffs(x) - 1);
-            if (tid == 31) sh.nrows = incl;
-            // first free row id (m >= 1 rows exist; with an identity landmark at most m - 1 rows are live)
-            const unsigned fr = ~bits;
-            const unsigned has = __ballot_sync(0xffffffffu, fr != 0u);
-            if (any_ident && tid == __ffs(has) - 1) sh.newrow = tid * 32 + __ffs(fr) - 1;
-        }
-        __syncthreads();
-        const int nrows = sh.nrows, newrow = sh.newrow;
+        const int nrows = d.rowinfo[0], newrow = d.rowinfo[1];
         const int cur = st->cur, rcur = st->rcur;
-        const double ninv = (double)ng;
         const unsigned per = (d.n + nt - 1) / nt;              // local slots per CTA
         const unsigned t_lo = b * per, t_hi = min(d.n, t_lo + per);
         const double* cdf = d.cum_all;
@@ -652,11 +765,10 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, double nth, uint64_t seed, uns
             const size_t tg = (size_t)d.off + t;
             const bool valid = t < t_hi;
             double r = 0.0;
-            if (valid) r = log2n >= 0 ? x3_comb_pow2(r0, inv, ninv, tg) : d.rcomb_all[tg];
+            if (valid) r = log2n >= 0 ? x3_comb_eval(&sh.comb, inv, tg) : __ldcg(d.rcomb_all + tg);
             // the warp's first and last slot bracket every lane's answer
             const double r_first = __shfl_sync(0xffffffffu, r, 0);
-            const int lastlane = min(31, (int)(t_hi - 1 - tb));
-            const double r_last = __shfl_sync(0xffffffffu, r, lastlane);
+            const double r_last = __shfl_sync(0xffffffffu, r, min(31, (int)(t_hi - 1 - tb)));
             const unsigned jlo = fs3_warp_search(cdf, (unsigned)ng, r_first);
             const unsigned jhi = fs3_warp_search(cdf, (unsigned)ng, r_last);
             if (!valid) continue;
@@ -671,7 +783,7 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, double nth, uint64_t seed, uns
             d.w[t] = inv;                                                                // fs1.rs:228
             const unsigned* srows = d.G > 1 ? reinterpret_cast<const unsigned*>(d.peer[jr] + d.o_rows[rcur]) : d.rows[rcur];
             unsigned* drows = d.rows[rcur ^ 1];
-            for (int x = 0; x < nrows; ++x) { const size_t ro = (size_t)sh.rowlist[x] * d.ld; drows[ro + t] = srows[ro + jc]; }
+            for (int x = 0; x < nrows; ++x) { const size_t ro = (size_t)d.rowlist[x] * d.ld; drows[ro + t] = srows[ro + jc]; }
             if (newrow >= 0) drows[(size_t)newrow * d.ld + t] = fs3_ref(jr, jc);
         }
         FS3_TRACE(6);
@@ -683,10 +795,11 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, double nth, uint64_t seed, uns
     if (!sh.last) return;
     __threadfence();
     if (gate) {
-        const int newrow = sh.newrow;
+        const int newrow = d.rowinfo[1];
         for (unsigned l = tid; l < d.m; l += NT) { const int s = d.lmst[l]; if ((s >> 1) == 0) d.lmst[l] = (s & 1) | ((newrow + 1) << 1); }
     }
-    if (tid < FS3_SLOTS) d.flagsg[tid] = 0;
+    if (tid < FS3_SLOTS) { d.flagsg[tid] = 0; d.entCnt[tid] = 0u; }
+    if (tid < 8) d.bar[tid] = 0u;
     if (tid < 32) {
         // best particle: the last maximum over the tiles (no resample) / the last slot (after a resample every weight is 1/n)
         double bw2 = -1.0; unsigned bi2 = 0;
@@ -699,7 +812,7 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, double nth, uint64_t seed, uns
         unsigned src = bi2;                                    // slot whose pose (in the buffer live BEFORE the flip) is reported
         if (gate) {
             bi2 = (unsigned)ng - 1; bw2 = inv;
-            const double rl = log2n >= 0 ? x3_comb_pow2(r0, inv, (double)ng, ng - 1) : d.rcomb_all[ng - 1];
+            const double rl = log2n >= 0 ? x3_comb_eval(&sh.comb, inv, ng - 1) : __ldcg(d.rcomb_all + ng - 1);
             src = fs3_warp_search(d.cum_all, (unsigned)ng, rl);
             if (src >= ng) src = (unsigned)ng - 1;
         }

@@ -19,7 +19,7 @@ struct pfgpu_fs {
     Fs3Rec* h_rec = nullptr;          // pinned + mapped
     double* stage = nullptr; size_t stage_bytes = 0;   // device staging buffer for upload / download / seed_map
     bool pdl = true;
-    int ekf_variant = -1;             // -1: pick by the number of observations
+    bool ekf_attr[2] = { false, false };
     int post_nt = 256; unsigned post_K = 1, post_tiles = 1, m32 = 0; int log2n = -1; size_t post_smem = 0;
 };
 
@@ -59,7 +59,7 @@ static int fs_create_impl(const pfgpu_fs_config* cfg, size_t n, size_t n_global,
     Fs3Dev& d = h->d;
     const size_t ld = (n + 63) / 64 * 64, mm = m ? m : 1;
     d.n = (unsigned)n; d.n_glob = (unsigned)n_global; d.off = (unsigned)offset; d.m = (unsigned)m; d.ld = (unsigned)ld;
-    d.G = world; d.rank = rank; d.npart = (unsigned)(ld / 64);
+    d.G = world; d.rank = rank; d.npart = (unsigned)(ld / 64); d.wait_inline = 1;
     auto fail = [&](int code) { pfgpu_fs_destroy(h); return code; };
 #define FS_TRY(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { snprintf(g_pfgpu_err, sizeof(g_pfgpu_err), "%s -> %s", #x, cudaGetErrorString(e__)); return fail(PFGPU_ERR_CUDA); } } while (0)
     // post kernel shape: <= 128 tiles (one CTA each, co-resident), NT threads x K values
@@ -116,11 +116,16 @@ static int fs_create_impl(const pfgpu_fs_config* cfg, size_t n, size_t n_global,
         FS_TRY(cudaMalloc(&d.cum_all, (n_global + 64) * sizeof(double)));
         if (h->log2n < 0) FS_TRY(cudaMalloc(&d.rcomb_all, (n_global + 64) * sizeof(double)));
         FS_TRY(cudaMalloc(&d.idx, ld * sizeof(unsigned))); FS_TRY(cudaMemset(d.idx, 0, ld * sizeof(unsigned)));
-        const size_t nsl = (size_t)FS3_SLOTS * FS3_MAX_TILES;
-        FS_TRY(cudaMalloc(&d.tileP, nsl * sizeof(unsigned long long))); FS_TRY(cudaMalloc(&d.tileD, nsl * sizeof(int)));
+        const size_t nsl = (size_t)FS3_SLOTS * FS3_MAX_TILES, nen = (size_t)FS3_SLOTS * FS3_ENT_CAP;
+        FS_TRY(cudaMalloc(&d.tileP, nsl * sizeof(unsigned long long)));
         FS_TRY(cudaMalloc(&d.tileQ, FS3_MAX_TILES * sizeof(double)));
-        FS_TRY(cudaMalloc(&d.entP, nsl * FS3_ENT_TILE * sizeof(unsigned long long))); FS_TRY(cudaMalloc(&d.entV, nsl * FS3_ENT_TILE * sizeof(double)));
-        FS_TRY(cudaMalloc(&d.entL, nsl * FS3_ENT_TILE * sizeof(int)));
+        FS_TRY(cudaMalloc(&d.entCnt, 8 * sizeof(unsigned))); FS_TRY(cudaMemset(d.entCnt, 0, 8 * sizeof(unsigned)));
+        FS_TRY(cudaMalloc(&d.entKey, nen * sizeof(unsigned))); FS_TRY(cudaMalloc(&d.entTile, nen * sizeof(unsigned)));
+        FS_TRY(cudaMalloc(&d.entP, nen * sizeof(unsigned long long))); FS_TRY(cudaMalloc(&d.entV, nen * sizeof(double)));
+        FS_TRY(cudaMalloc(&d.entL, nen * sizeof(int)));
+        FS_TRY(cudaMalloc(&d.bar, 8 * sizeof(unsigned))); FS_TRY(cudaMemset(d.bar, 0, 8 * sizeof(unsigned)));
+        FS_TRY(cudaMalloc(&d.rowlist, 1024 * sizeof(unsigned short))); FS_TRY(cudaMalloc(&d.rowinfo, 2 * sizeof(int)));
+        FS_TRY(cudaMemset(d.rowinfo, 0, 2 * sizeof(int)));
         FS_TRY(cudaMalloc(&d.tileBw, FS3_MAX_TILES * sizeof(double))); FS_TRY(cudaMalloc(&d.tileBi, FS3_MAX_TILES * sizeof(unsigned)));
         FS_TRY(cudaMalloc(&d.flagsg, 8 * sizeof(int))); FS_TRY(cudaMemset(d.flagsg, 0, 8 * sizeof(int)));
         FS_TRY(cudaHostAlloc(&h->h_rec, sizeof(Fs3Rec), cudaHostAllocMapped));
@@ -129,7 +134,6 @@ static int fs_create_impl(const pfgpu_fs_config* cfg, size_t n, size_t n_global,
         if (getenv("PFGPU_POST_TRACE")) { FS_TRY(cudaMalloc(&d.trace, 32 * sizeof(unsigned long long))); FS_TRY(cudaMemset(d.trace, 0, 32 * sizeof(unsigned long long))); }
     }
     { const char* e5 = getenv("PFGPU_PDL"); h->pdl = !(e5 && e5[0] == '0'); }
-    { const char* e3 = getenv("PFGPU_EKF_VARIANT"); if (e3 && e3[0] >= '0' && e3[0] <= '3') h->ekf_variant = e3[0] - '0'; }
     if (world > 1 && uid) {
         ncclUniqueId id;
         memcpy(&id, uid, sizeof(id));
@@ -203,6 +207,7 @@ extern "C" int pfgpu_fs_create_sharded_local(const pfgpu_fs_config* cfg, size_t 
                 cudaGetLastError();
             }
             out[a]->d.peer[b] = out[b]->arena;
+            if (a != b && devices[a] == devices[b]) out[a]->d.wait_inline = 0;     // ranks sharing a GPU must not hold SMs while they wait
         }
     return PFGPU_OK;
 }
@@ -214,7 +219,8 @@ extern "C" void pfgpu_fs_destroy(pfgpu_fs* h) {
     for (int g = 0; g < h->world; ++g) if (g != h->rank && h->peer_ptr[g]) cudaIpcCloseMemHandle(h->peer_ptr[g]);   // (local mode: none were opened)
     cudaFree(h->arena);
     cudaFree(d.st); cudaFree(d.lmst); cudaFree(d.w); cudaFree(d.wn_all); cudaFree(d.cum_all); cudaFree(d.rcomb_all); cudaFree(d.idx);
-    cudaFree(d.tileP); cudaFree(d.tileD); cudaFree(d.tileQ); cudaFree(d.entP); cudaFree(d.entV); cudaFree(d.entL);
+    cudaFree(d.tileP); cudaFree(d.tileQ); cudaFree(d.entCnt); cudaFree(d.entKey); cudaFree(d.entTile); cudaFree(d.entP); cudaFree(d.entV); cudaFree(d.entL);
+    cudaFree(d.bar); cudaFree(d.rowlist); cudaFree(d.rowinfo);
     cudaFree(d.tileBw); cudaFree(d.tileBi); cudaFree(d.flagsg); cudaFree(d.trace); cudaFree(h->stage);
     if (h->h_rec) cudaFreeHost(h->h_rec);
     if (h->comm) ncclCommDestroy(h->comm);
@@ -313,12 +319,20 @@ extern "C" int pfgpu_fs_seed_map(pfgpu_fs* h, const double pose3[3], const doubl
     return 0;
 }
 
-template <int MAXT, int MINB>
+template <int MAXT>
 static int fs3_launch_ekf(pfgpu_fs* h, const Fs3ObsParam& po, const double u[2], int kk, int flags) {
     const Fs3Dev& d = h->d;
-    const unsigned threads = 32u * (unsigned)(kk > 0 ? kk : 1);
-    const size_t smem = (192 + (size_t)(kk > 0 ? kk : 1) * 64) * sizeof(double);
-    PF_LAUNCH_PDL(h->ctx, h->pdl, (fs3_ekf_kernel<MAXT, MINB>), d.ld / 64, threads, smem, d, po, u[0], u[1], h->cfg.dt, sqrt(h->cfg.q00), sqrt(h->cfg.q11),
+    const unsigned threads = 32u * (unsigned)(kk + 1);
+    const size_t smem = (384 + (size_t)2 * kk * 64 + (size_t)2 * kk * 384) * sizeof(double);
+    const unsigned groups = d.ld / 64;
+    // persistent: one CTA per SM walks the 64-particle groups; without observations the launch is predict-only and latency
+    // bound, so every group gets its own (one-warp) CTA
+    const unsigned grid = kk > 0 ? std::min<unsigned>(groups, (unsigned)h->ctx.num_sms) : groups;
+    if (!h->ekf_attr[MAXT == 512 ? 0 : 1]) {
+        PF_CUDA(cudaFuncSetAttribute(fs3_ekf_kernel<MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((384 + (size_t)2 * (MAXT / 32 - 1) * 448) * sizeof(double))));
+        h->ekf_attr[MAXT == 512 ? 0 : 1] = true;
+    }
+    PF_LAUNCH_PDL(h->ctx, h->pdl, (fs3_ekf_kernel<MAXT>), grid, threads, smem, d, po, u[0], u[1], h->cfg.dt, sqrt(h->cfg.q00), sqrt(h->cfg.q11),
                   h->cfg.r00, h->cfg.r11, h->seed, (uint32_t)h->n_step, kk, flags, (unsigned)h->n_step);
     return 0;
 }
@@ -332,9 +346,9 @@ extern "C" int pfgpu_fs_step(pfgpu_fs* h, const double u[2], const pfgpu_fs_obs*
         if (z[j].lm_id >= d.m) return PFGPU_ERR_INVALID;             // the reference would panic on the Vec index (fs1.rs:141)
     }
     PF_CUDA(cudaSetDevice(h->ctx.device));
-    // One EKF launch runs one warp per observation and does the lazy-clone bookkeeping per launch, so a launch must not see
-    // the same lm_id twice and holds at most FS3_MAX_OBS observations: the list is cut before every repeated id / every 32
-    // entries and the pieces run as consecutive launches (same per-particle order as fs1.rs:250-256).
+    // One EKF launch runs one warp per observation and the lazy-clone bookkeeping is per launch, so a launch must not see the
+    // same lm_id twice and holds at most FS3_MAX_OBS observations: the list is cut before every repeated id / every
+    // FS3_MAX_OBS entries and the pieces run as consecutive launches (same per-particle order as fs1.rs:250-256).
     std::vector<size_t> cuts;
     cuts.push_back(0);
     {
@@ -350,29 +364,30 @@ extern "C" int pfgpu_fs_step(pfgpu_fs* h, const double u[2], const pfgpu_fs_obs*
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->timer.on) { PF_CUDA(cudaEventCreate(&e0)); PF_CUDA(cudaEventCreate(&e1)); PF_CUDA(cudaEventRecord(e0, h->ctx.stream)); }
     const size_t nseg = cuts.size() - 1;
+    Fs3ObsParam po;
+    int k_last = 0;
+    const bool host_waits = d.G > 1 && !d.wait_inline;
+    if (host_waits) PF_LAUNCH(h->ctx, fs3_wait_kernel, 1, 32, 0, d, 1, (unsigned)h->n_step);            // peers' previous post kernels are over
     for (size_t seg = 0; seg < nseg; ++seg) {
         const size_t j0 = cuts[seg], kk = cuts[seg + 1] - cuts[seg];
-        const int flags = (seg == 0 ? 1 : 0) | (seg + 1 == nseg ? 2 : 0);
-        Fs3ObsParam po;
+        const int flags = seg == 0 ? 1 : 0;
         memset(&po, 0, sizeof(po));
         for (size_t j = 0; j < kk; ++j) { po.o[j].d = z[j0 + j].d; po.o[j].angle = z[j0 + j].angle; po.o[j].lm_id = (int)z[j0 + j].lm_id; }
-        int var = h->ekf_variant;
-        if (var < 0) var = kk <= 8 ? 2 : (kk <= 16 ? 1 : 0);
-        if (var == 2 && kk > 8) var = 1;
-        if (var == 1 && kk > 16) var = 0;
-        int rc;
-        if (var == 2)      rc = fs3_launch_ekf<256, 3>(h, po, u, (int)kk, flags);
-        else if (var == 1) rc = fs3_launch_ekf<512, 1>(h, po, u, (int)kk, flags);
-        else if (var == 3) rc = fs3_launch_ekf<1024, 1>(h, po, u, (int)kk, flags);
-        else               rc = fs3_launch_ekf<1024, 1>(h, po, u, (int)kk, flags);
+        int rc = kk <= 15 ? fs3_launch_ekf<512>(h, po, u, (int)kk, flags) : fs3_launch_ekf<1024>(h, po, u, (int)kk, flags);
         if (rc) return rc;
+        if (seg + 1 < nseg) PF_LAUNCH_PDL(h->ctx, h->pdl, fs3_mark_kernel, 1, 64, 0, d, po, (int)kk);    // the last piece: the post kernel does it
+        k_last = (int)kk;
     }
     if (h->timer.on) { PF_CUDA(cudaEventRecord(e1, h->ctx.stream)); h->timer.pending.push_back({e0, e1}); }
+    if (host_waits) {      // the post kernel signals "my weights are pushed" itself; the wait for the others' is its own launch here
+        PF_LAUNCH(h->ctx, fs3_signal_kernel, 1, 32, 0, d, 0, (unsigned)h->n_step + 1u);
+        PF_LAUNCH(h->ctx, fs3_wait_kernel, 1, 32, 0, d, 0, (unsigned)h->n_step + 1u);
+    }
     // normalise, N_eff gate and (when it opens) the whole resample: one launch
     if (h->post_nt == 512)
-        PF_LAUNCH_PDL(h->ctx, h->pdl, fs3_post_kernel<512>, h->post_tiles, 512, h->post_smem, d, h->cfg.nth, h->seed, (unsigned)h->n_step, h->post_K, h->m32, h->log2n);
+        PF_LAUNCH_PDL(h->ctx, h->pdl, fs3_post_kernel<512>, h->post_tiles, 512, h->post_smem, d, po, k_last, h->cfg.nth, h->seed, (unsigned)h->n_step, h->post_K, h->m32, h->log2n);
     else
-        PF_LAUNCH_PDL(h->ctx, h->pdl, fs3_post_kernel<256>, h->post_tiles, 256, h->post_smem, d, h->cfg.nth, h->seed, (unsigned)h->n_step, h->post_K, h->m32, h->log2n);
+        PF_LAUNCH_PDL(h->ctx, h->pdl, fs3_post_kernel<256>, h->post_tiles, 256, h->post_smem, d, po, k_last, h->cfg.nth, h->seed, (unsigned)h->n_step, h->post_K, h->m32, h->log2n);
     h->n_step++;
     h->steps++;
     if (did) {     // the gate lives on the device; only a caller who asks pays a sync

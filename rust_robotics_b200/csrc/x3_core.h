@@ -80,4 +80,29 @@ PFC_HD double x3_comb_pow2(double r0, double inv, double ninv /* = 2^p */, unsig
     return v;
 }
 
+/* The same comb as a table: segment k covers slots [T_k, T_{k+1}) on which r_t = V_k + (t - T_k) * inv EXACTLY (no rounding
+ * inside a binade); V_{k+1} is the one rounded addition that enters the next binade.  At most p + 3 segments for n = 2^p. */
+#define X3_COMB_SEGS 72
+typedef struct { int n; unsigned long long T[X3_COMB_SEGS + 1]; double V[X3_COMB_SEGS]; } x3_comb_table;
+PFC_HD void x3_comb_build(x3_comb_table* tb, double r0, double inv, double ninv, unsigned long long n) {
+    unsigned long long t = 0; double v = r0; int k = 0;
+    while (t < n && k < X3_COMB_SEGS) {
+        tb->T[k] = t; tb->V[k] = v; k++;
+        const int e = (int)(pfc_d2u(v) >> 52);
+        const double top = e >= 2046 ? v : pfc_u2d((uint64_t)(e + 1) << 52);
+        double j = ceil((top - v) * ninv);
+        if (!(j >= 1.0)) j = 1.0;
+        if (j >= 1.8e19 || t + (unsigned long long)j >= n) { t = n; break; }
+        v = v + (j - 1.0) * inv;
+        v = v + inv;
+        t += (unsigned long long)j;
+    }
+    tb->n = k; tb->T[k] = n;
+}
+PFC_HD double x3_comb_eval(const x3_comb_table* tb, double inv, unsigned long long t) {
+    int k = 0;
+    while (k + 1 < tb->n && tb->T[k + 1] <= t) ++k;
+    return tb->V[k] + (double)(t - tb->T[k]) * inv;
+}
+
 #endif

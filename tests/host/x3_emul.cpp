@@ -99,10 +99,16 @@ extern "C" long long x3_emul_comb(double u01, int p, size_t stride) {
     const double r0 = u01 * (inv - 0.0) + 0.0;
     long long bad = 0;
     double r = r0;
+    x3_comb_table tb;
+    x3_comb_build(&tb, r0, inv, ninv, n);
     for (size_t t = 0; t < n; ++t) {
         if (t % stride == 0 || t + 3 > n) {
             double c = x3_comb_pow2(r0, inv, ninv, t);
             if (std::memcmp(&c, &r, 8) != 0) bad++;
+        }
+        {
+            double c2 = x3_comb_eval(&tb, inv, t);
+            if (std::memcmp(&c2, &r, 8) != 0) bad++;
         }
         r = r + inv;
     }

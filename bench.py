@@ -1,14 +1,19 @@
 #!/usr/bin/env python3
-"""bench.py — particle-steps/s of the FastSLAM 1.0 hot path (BASELINE.json config 3: 65 536 particles x 256 landmarks).
+"""bench.py — particle-steps/s of the FastSLAM 1.0 hot path.
 
     python bench.py --gpus N --steps K --warmup W            # our arm (one JSON line on rank 0)
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port) on the host cores
 
-A "step" = one fastslam_update (fs1.rs:237-266) over all particles with that step's observation list (~12 of 256
-landmarks in range).  Timing: CUDA events on the engine's own stream around every step, L2 flushed (256 MiB memset)
-before each step so no step runs out of a warm cache; `value` = particles x K / sum of step times.  Inputs (particle
-state, maps) are resident in HBM; the per-step control + observation list (~300 B) rides in the launch parameters.
-`e2e` repeats the K steps through the public API with host buffers and a host read-back of the result every step.
+Primary line (`value`, `e2e`, `roofline`): BASELINE.json config 3 — 65 536 particles x 256 landmarks PER GPU (weak scaling:
+global = 65 536 x N), ~12.7 of 256 landmarks observed per step, nth = particles / 1.5.  A "step" = one fastslam_update
+(fs1.rs:237-266) over all particles.  Timing: CUDA events on the engine's own stream around every step, L2 flushed (256 MiB
+memset + 256 MiB clean read) before each step so no step runs out of a warm cache; `value` = particles x K / sum of step
+times (max over ranks).  Inputs (particle state, maps) are resident in HBM; the per-step control + observation list (~300 B)
+rides in the launch parameters.  `e2e` repeats K steps through the public API with host buffers, one host synchronisation
+and a host read-back of the step's result record (best particle, gate, N_eff) every step.
+Second key `c4_strong`: BASELINE config 4 — 2^20 particles x 1024 landmarks sharded over the N GPUs (strong scaling; at
+N = 1 the whole 103 GB of landmark state lives on the one GPU), same timing rules, fewer steps.  `--config c4` makes it the
+primary line instead.
 """
 import argparse
 import json
@@ -46,7 +51,7 @@ class ClockSampler:
     def __init__(self, index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                        "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -132,24 +137,31 @@ def cpu_run(sc, n, steps, warmup, threads, t0_step=0):
 
 def pick_threads(sc, n):
     """the thread count that serves the CPU arm best on this box (all logical CPUs is often NOT it: shared hosts,
-    cgroup quotas, tiny per-thread work); probed with 3-step runs"""
+    cgroup quotas, tiny per-thread work); probed with 3-step runs.  Returns (best, seconds per step, {threads: steps/s})."""
     ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     cands = sorted({c for c in (1, 4, 8, 16, 32, 64, ncpu) if c <= ncpu})
-    best, best_dt = 1, None
+    best, best_dt, table = 1, None, {}
     for c in cands:
         dt, _ = cpu_run(sc, n, 3, 1, c)
+        table[c] = round(n * 3 / dt, 1)
         if best_dt is None or dt < best_dt:
             best, best_dt = c, dt
-    return best, best_dt / 3
+    return best, best_dt / 3, table
 
 
 def cpu_baseline(sc, budget_s, max_steps):
-    """bounded sample of the same workload: same map, same observation stream, fewer particles / steps"""
+    """bounded sample of the same workload: same map, same observation stream, fewer particles / steps.  Reported both the
+    way the reference runs (ONE thread: the Rust loops are serial) and with the thread count that serves this box best."""
     n = 32768
-    threads, per_step = pick_threads(sc, n)
+    threads, per_step, table = pick_threads(sc, n)
     steps = int(max(4, min(max_steps, len(sc.obs) - 4, budget_s / max(per_step, 1e-6))))
     dt, res = cpu_run(sc, n, steps, 2, threads)
+    n1 = 4096
+    steps1 = int(max(3, min(40, len(sc.obs) - 4)))
+    dt1, _ = cpu_run(sc, n1, steps1, 1, 1)
     return {"value": n * steps / dt, "unit": "particle-steps/s", "cores": threads, "kind": "port",
+            "one_thread": {"value": n1 * steps1 / dt1, "unit": "particle-steps/s", "sample": f"{n1} particles, {steps1} steps, {dt1:.1f} s"},
+            "threads_probe_particle_steps_per_s": table,
             "sample": f"oracle port (C, glibc libm, OpenMP x{threads}) of fs1.rs on {n} of {N_PARTICLES} particles x {sc.m} landmarks, "
                       f"{steps} steps of the same observation stream, {res} resamples, {dt:.1f} s"}
 
@@ -160,7 +172,7 @@ def run_reference(args, rank):
     sc = make_scenario(args.warmup + args.steps + 8)
     # size the per-step sample so the whole run stays within ~2 minutes
     n = 2048
-    threads, per_step = pick_threads(sc, n)
+    threads, per_step, _ = pick_threads(sc, n)
     per_ps = per_step / n
     budget = 90.0
     n_fit = budget / (per_ps * (args.steps + args.warmup))
@@ -172,7 +184,7 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(sc, args.gpus),
+            "config": workload_config(CONFIGS["c3"], sc, args.gpus, N_PARTICLES * args.gpus, sc.obs[args.warmup:args.warmup + args.steps], res, args.steps),
             "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": threads, "kind": "port",
                              "sample": f"oracle port of fs1.rs (C, glibc libm, OpenMP x{threads}); each step = {n} of "
                                        f"{N_PARTICLES} particles x {sc.m} landmarks, {res} resamples in {args.steps} steps"},
@@ -195,68 +207,59 @@ def load_traffic():
         return {"traffic": None}
 
 
-def workload_config(sc, n_gpus):
-    return {"workload": "FastSLAM 1.0 (fs1.rs fastslam_update), BASELINE config 3", "particles_per_gpu": N_PARTICLES,
-            "particles": N_PARTICLES * n_gpus, "landmarks": sc.m, "mean_obs_per_step": round(sc.mean_k(), 2),
+CONFIGS = {
+    "c3": dict(name="FastSLAM 1.0 (fs1.rs fastslam_update), BASELINE config 3", particles_per_gpu=N_PARTICLES, particles_total=None,
+               scenario="c3_scenario", scaling="weak"),
+    "c4": dict(name="FastSLAM 1.0 (fs1.rs fastslam_update), BASELINE config 4", particles_per_gpu=None, particles_total=1 << 20,
+               scenario="c4_scenario", scaling="strong"),
+}
+
+
+def workload_config(cfg, sc, n_gpus, n_global, obs_timed, resamples, K):
+    return {"workload": cfg["name"], "particles": n_global, "particles_per_gpu": n_global // n_gpus, "landmarks": sc.m,
+            "mean_obs_per_step": round(sum(len(z) for z in obs_timed) / max(len(obs_timed), 1), 2),
+            "resample_fraction": round(resamples / max(K, 1), 3),
             "nth": {"default": "particles/1.5", "literal": "66.67 (fs1.rs:21; never resamples at this particle count)",
                     "every": "particles + 1 (stress variant: resample every step)"}[NTH_MODE],
             "start": "initialised map (cov 10 I), poses at truth", "seed": 42,
-            "parallelism": f"particle shards x{n_gpus}", "l2": "flushed (256 MiB memset) before every timed step"}
+            "parallelism": f"particle shards x{n_gpus}" + ("" if n_gpus == 1 else ", peer memory (NVLink loads / stores inside the kernels; no NCCL call, no host sync per step)"),
+            "l2": "flushed (256 MiB memset + clean read) before every timed step"}
 
 
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args, rank, world, local_rank):
-    import rust_robotics_b200 as rr
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist_mod
-        dist = dist_mod
-        dist.init_process_group("gloo", init_method="env://")     # control plane only; the data path uses NCCL inside libpfgpu
-    K, W = args.steps, args.warmup
+def make_engine(rr, grp, cfg_key, rank, world, local_rank):
+    from rust_robotics_b200 import dist as rdist, scenarios
+    cfg = CONFIGS[cfg_key]
+    n_global = cfg["particles_total"] or cfg["particles_per_gpu"] * world
+    return cfg, n_global, scenarios, rdist
+
+
+def measure(rr, grp, cfg_key, K, W, rank, world, local_rank, with_e2e, sampler_cb=None):
+    """one configuration: warm-up, K flushed + event-timed steps, K un-flushed steps, (optionally) K end-to-end steps"""
+    from rust_robotics_b200 import dist as rdist, scenarios
+    cfg = CONFIGS[cfg_key]
+    n_global = cfg["particles_total"] or cfg["particles_per_gpu"] * world
     total = W + 3 * K + 4
-    sc = make_scenario(total)
+    sc = getattr(scenarios, cfg["scenario"])(steps=total)
     arrs = obs_arrays(rr, sc)
-    n_global = N_PARTICLES * world
-    cfg = rr.FsConfig(nth=nth_value(n_global))
+    fcfg = rr.FsConfig(nth=nth_value(n_global))
     if world > 1:
-        import numpy as np
-        import torch
-        uid = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            import ctypes as C
-            buf = C.create_string_buffer(128)
-            rc = rr.load_library().pfgpu_nccl_unique_id(buf)
-            if rc != 0:
-                raise SystemExit(f"pfgpu_nccl_unique_id failed: {rc}")
-            uid = torch.tensor(list(buf.raw), dtype=torch.uint8)
-        dist.broadcast(uid, 0)
-        g = rr.FastSlam1(n_global, sc.m, cfg, seed=42, device=local_rank, shard=(bytes(uid.tolist()), rank, world))
+        uid = rdist.broadcast_unique_id(grp, rdist.nccl_unique_id)
+        g = rr.FastSlam1(n_global, sc.m, fcfg, seed=42, device=local_rank, shard=(uid, rank, world))
     else:
-        g = rr.FastSlam1(N_PARTICLES, sc.m, cfg, seed=42, device=local_rank)
+        g = rr.FastSlam1(n_global, sc.m, fcfg, seed=42, device=local_rank)
     g.seed_map(sc.start, sc.landmarks)
 
     def barrier():
         g.sync()
-        if dist is not None:
-            dist.barrier()
-
-    def maxr(x):
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        grp.barrier()
 
     step = 0
     for _ in range(W):                                   # warm-up (untimed)
         g.fastslam_update(sc.control, sc.obs[step], want_flag=False, obs_array=arrs[step]); step += 1
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-
     # ---- timed region 1: K steps, L2 flushed before each, one event pair per step ----
     st0 = g.stats()
     g.time_main_kernel(True)
@@ -266,10 +269,6 @@ def run_ours(args, rank, world, local_rank):
     for t in range(K):
         if flush_mode != "none":
             g.flush_l2()
-        if flush_mode == "flush_sync":
-            g.sync()
-        if dist is not None and os.environ.get("BENCH_STEP_BARRIER", "0") == "1":
-            barrier()            # optional: ranks enter the timed step together (costs a host round trip per step)
         g.mark(2 * t)
         g.fastslam_update(sc.control, sc.obs[step], want_flag=False, obs_array=arrs[step]); step += 1
         g.mark(2 * t + 1)
@@ -282,35 +281,36 @@ def run_ours(args, rank, world, local_rank):
             sorted(range(K), key=lambda i: -step_ms[i])[:8]))
     st1 = g.stats()
     g.time_main_kernel(False)
-    t_flushed = maxr(sum(step_ms) * 1e-3)
+    t_flushed = grp.max(sum(step_ms) * 1e-3)
     launches = st1.kernel_launches - st0.kernel_launches
     resamples = st1.resamples - st0.resamples
     kernel_ms = st1.main_kernel_ms_sum / max(st1.main_kernel_count, 1)
-    alg_bytes = sum(N_PARTICLES * (BYTES_POSE_WEIGHT + BYTES_PER_OBS * len(sc.obs[first + t])) for t in range(K)) / K
-
-    # ---- timed region 2: the same K steps' successors back to back, no flush (steady state, informational) ----
+    obs_timed = sc.obs[first:first + K]
+    n_local = n_global // world
+    alg_bytes = sum(n_local * (BYTES_POSE_WEIGHT + BYTES_PER_OBS * len(z)) for z in obs_timed) / K
+    # ---- timed region 2: the next K steps back to back, no flush (steady state, informational) ----
     barrier()
     g.mark(8000)
     for t in range(K):
         g.fastslam_update(sc.control, sc.obs[step], want_flag=False, obs_array=arrs[step]); step += 1
     g.mark(8001)
     barrier()
-    t_noflush = maxr(g.elapsed_ms(8000, 8001) * 1e-3)
-
-    # ---- end to end: public API, host buffers in, result read back to the host every step ----
-    barrier()
-    t0 = time.perf_counter()
-    h2d = d2h = 0
-    for t in range(K):
-        z = sc.obs[step]
-        did = g.fastslam_update(sc.control, z, want_flag=True); step += 1          # builds the C array from host data, syncs
-        idx, pose = g.get_best_particle()                                          # D2H of the step's result
-        h2d += 16 + 24 * len(z)
-        d2h += 4 + 4 + 8 * 3 + 16 * min(296, N_PARTICLES // 256)      # gate, cur, pose of the best, per-block argmax partials
-    barrier()
-    t_e2e = maxr(time.perf_counter() - t0)
-    clocks = sampler.stop() if sampler else None
-
+    t_noflush = grp.max(g.elapsed_ms(8000, 8001) * 1e-3)
+    # ---- end to end: public API, host buffers in, the step's result record read back to the host every step ----
+    e2e = None
+    if with_e2e:
+        barrier()
+        t0 = time.perf_counter()
+        h2d = d2h = 0
+        for t in range(K):
+            z = sc.obs[step]
+            did = g.fastslam_update(sc.control, z, want_flag=True); step += 1          # builds the C array from host data, synchronises
+            idx, pose = g.get_best_particle()                                          # the record: best particle + pose, gate, N_eff
+            h2d += 16 + 24 * len(z)
+            d2h += 64
+        barrier()
+        t_e2e = grp.max(time.perf_counter() - t0)
+        e2e = {"value": n_global * K / t_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K}
     if rank == 0 and os.environ.get("PFGPU_POST_TRACE"):
         import ctypes as C
         out = (C.c_ulonglong * 32)()
@@ -322,36 +322,54 @@ def run_ours(args, rank, world, local_rank):
                          "normalise+gate=%.2f   launches=%d\n" % (us(0, nl), us(1, nl), us(8, nl), us(9, nl), us(10, nl), us(2, nl), nl))
         sys.stderr.write("   per RESAMPLE (%d): S2 sum=%.2f  CDF scan=%.2f [classify+publish %.2f | barrier %.2f | chain %.2f | emit %.2f]  comb+barrier=%.2f  "
                          "search+clone=%.2f\n" % (nr, us(3, nr), us(4, nr), us(12, nr), us(13, nr), us(14, nr), us(15, nr), us(5, nr), us(6, nr)))
-        nc = max(out[19], 1)
-        sys.stderr.write("fs3_ekf_kernel CTA timeline (SM cycles, mean over %d CTAs): loads+predict+barrier=%.0f  EKF+stores=%.0f  epilogue=%.0f\n" %
-                         (nc, out[16] / nc, out[17] / nc, out[18] / nc))
+    res = {"cfg": cfg, "sc": sc, "n_global": n_global, "t_flushed": t_flushed, "t_noflush": t_noflush, "launches": int(launches),
+           "resamples": int(resamples), "kernel_ms": kernel_ms, "alg_bytes": alg_bytes, "obs_timed": obs_timed, "e2e": e2e,
+           "serial_fallbacks": int(st1.serial_fallbacks), "K": K}
+    g.close()
+    return res
+
+
+def run_ours(args, rank, world, local_rank):
+    import rust_robotics_b200 as rr
+    from rust_robotics_b200 import dist as rdist
+    grp = rdist.TcpGroup()
+    K, W = args.steps, args.warmup
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    primary = measure(rr, grp, args.config, K, W, rank, world, local_rank, True)
+    second_key = "c4" if args.config == "c3" else "c3"
+    second = None
+    if not args.no_second:
+        K2 = max(10, min(K, 50 if second_key == "c4" else K))
+        second = measure(rr, grp, second_key, K2, max(3, min(W, 5 if second_key == "c4" else W)), rank, world, local_rank, False)
+    clocks = sampler.stop() if sampler else None
     if rank == 0:
         peak, peak_src = load_peaks()
-        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-        cpu = cpu_baseline(sc, 12.0, 400) if (world == 1 and not args.no_cpu_baseline) else None
-        line = {"metric": "particle-steps/sec", "value": n_global * K / t_flushed, "unit": "particle-steps/s",
-                "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_flushed / K * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": dict(workload_config(sc, world), resamples_in_timed_steps=int(resamples),
-                               **({"imported_particles_rank0": int(st1.imported_particles - st0.imported_particles),
-                                   "guest_compactions_rank0": int(st1.compactions - st0.compactions),
-                                   "exchange": {1: "NCCL collectives + host-planned send/recv", 2: "peer memory (NVLink stores/atomics/loads "
-                                                "inside the kernels; no NCCL call, no host sync per step)"}.get(g.shard_mode(), "?")}
-                                  if world > 1 else {})),
-                "value_steady_state_no_flush": n_global * K / t_noflush,
-                "e2e": {"value": n_global * K / t_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d / K,
-                        "d2h_bytes_per_step": d2h / K},
-                "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "kernel": "fs_predict_kernel + fs_ekf_kernel (predict + per-observation EKF, fs1.rs:245-256)", "achieved": achieved,
-                             "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, **load_traffic(),
-                             "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": kernel_ms},
-                "clocks": clocks, "serial_fallbacks": int(st1.serial_fallbacks)}
+        r = primary
+        achieved = r["alg_bytes"] / (r["kernel_ms"] * 1e-3) / 1e9
+        cpu = cpu_baseline(r["sc"], 12.0, 400) if (world == 1 and not args.no_cpu_baseline and args.config == "c3") else None
+        line = {"metric": "particle-steps/sec", "value": r["n_global"] * K / r["t_flushed"], "unit": "particle-steps/s",
+                "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": r["t_flushed"] / K * 1e3, "higher_is_better": True,
+                "scaling": r["cfg"]["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(r["cfg"], r["sc"], world, r["n_global"], r["obs_timed"], r["resamples"], K),
+                "value_steady_state_no_flush": r["n_global"] * K / r["t_noflush"],
+                "e2e": r["e2e"], "gpu_launches": r["launches"],
+                "roofline": {"bound": "hbm", "kernel": "fs3_ekf_kernel (predict + per-observation EKF + weight products, fs1.rs:245-256)",
+                             "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, **load_traffic(),
+                             "algorithmic_bytes_per_launch": r["alg_bytes"], "avg_launch_ms": r["kernel_ms"],
+                             "note": "per GPU; algorithmic bytes = particles x (64 + 96 x observations of the step), SURVEY.md 8(d)"},
+                "clocks": clocks, "serial_fallbacks": r["serial_fallbacks"]}
+        if second:
+            q = second
+            line[{"c4": "c4_strong", "c3": "c3_weak"}[second_key]] = {
+                "value": q["n_global"] * q["K"] / q["t_flushed"], "unit": "particle-steps/s", "steps": q["K"], "ms_per_step": q["t_flushed"] / q["K"] * 1e3,
+                "scaling": q["cfg"]["scaling"], "value_steady_state_no_flush": q["n_global"] * q["K"] / q["t_noflush"],
+                "ekf_launch_ms": q["kernel_ms"], "ekf_roofline_frac": q["alg_bytes"] / (q["kernel_ms"] * 1e-3) / 1e9 / peak,
+                "config": workload_config(q["cfg"], q["sc"], world, q["n_global"], q["obs_timed"], q["resamples"], q["K"])}
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    grp.barrier()
+    grp.close()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -440,6 +458,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs)")
     ap.add_argument("--workload", default="fastslam", choices=["fastslam", "mcl", "pf"],
                     help="fastslam = BASELINE config 3 (default, the headline); mcl = config 2; pf = one point of the config-5 sweep")
+    ap.add_argument("--config", default="c3", choices=["c3", "c4"], help="fastslam workload: which BASELINE config is the primary line (the other one is reported under a second key)")
+    ap.add_argument("--no-second", action="store_true", help="skip the second configuration")
     ap.add_argument("--nth", default="default", choices=["default", "literal", "every"],
                     help="fastslam workload: resample threshold — particles/1.5 (default), the reference's literal 66.67, or every step")
     ap.add_argument("--particles", type=int, default=1 << 20, help="mcl / pf workloads only")

@@ -137,6 +137,11 @@ int  pfgpu_fs_download(pfgpu_fs*, double* pose_w, double* lm, size_t n);
 int  pfgpu_fs_seed_map(pfgpu_fs*, const double pose3[3], const double* landmarks_xy, size_t m, double sigma, double cov0);
 /* fastslam_update fs1.rs:237-266.  did_resample (nullable): non-NULL synchronises. */
 int  pfgpu_fs_step(pfgpu_fs*, const double u[2], const pfgpu_fs_obs* z, size_t k, int* did_resample);
+/* get_observations fs1.rs:277-299, the simulator next to the filter, on the device: landmarks within cfg.max_range of x_true
+ * (x, y, yaw), in landmark order; range / bearing noise N(0,1) * sqrt(R) from Philox stream PFC_STREAM_OBS keyed by (seed of the
+ * handle, call, landmark id).  out has room for n_landmarks tuples; *k receives their number. */
+int  pfgpu_fs_get_observations(pfgpu_fs*, const double x_true[3], const double* landmarks_xy, size_t n_landmarks, uint32_t call,
+                               pfgpu_fs_obs* out, size_t* k);
 /* get_best_particle fs1.rs:269-274 (last maximum wins); pose_w4 = (weight, x, y, yaw) */
 int  pfgpu_fs_best(pfgpu_fs*, size_t* index_global, double pose_w4[4]);
 /* landmarks of one particle (what render_gif_slam.rs:183-191 reads): lm6 = m x 6 */

@@ -59,7 +59,7 @@ EXPORTS = [
     "pfgpu_pf_neff", "pfgpu_pf_set_range_noise", "pfgpu_pf_last_indices", "pfgpu_pf_sync",
     "pfgpu_fs_default_config", "pfgpu_fs_create", "pfgpu_fs_create_sharded", "pfgpu_fs_create_sharded_local", "pfgpu_fs_destroy",
     "pfgpu_fs_upload", "pfgpu_fs_download", "pfgpu_fs_seed_map", "pfgpu_fs_step", "pfgpu_fs_best", "pfgpu_fs_particle_landmarks",
-    "pfgpu_fs_last_indices", "pfgpu_fs_last_neff", "pfgpu_fs_last_gate", "pfgpu_fs_count", "pfgpu_fs_sync",
+    "pfgpu_fs_get_observations", "pfgpu_fs_last_indices", "pfgpu_fs_last_neff", "pfgpu_fs_last_gate", "pfgpu_fs_count", "pfgpu_fs_sync",
     "pfgpu_nccl_unique_id", "pfgpu_pf_stats", "pfgpu_fs_stats", "pfgpu_pf_time_main_kernel",
     "pfgpu_fs_time_main_kernel", "pfgpu_pf_mark", "pfgpu_pf_elapsed_ms", "pfgpu_fs_mark", "pfgpu_fs_elapsed_ms",
     "pfgpu_pf_flush_l2", "pfgpu_fs_flush_l2", "pfgpu_fs_post_trace", "pfgpu_fs_shard_mode",
@@ -119,6 +119,7 @@ def load_library():
     L.pfgpu_fs_last_indices.argtypes = [vp, c_u32p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.pfgpu_fs_last_neff.argtypes = [vp, c_dp]
     L.pfgpu_fs_last_gate.argtypes = [vp, C.POINTER(C.c_int)]
+    L.pfgpu_fs_get_observations.argtypes = [vp, c_dp, c_dp, C.c_size_t, C.c_uint32, C.POINTER(_FsObs), C.POINTER(C.c_size_t)]
     L.pfgpu_fs_count.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.pfgpu_fs_sync.argtypes = [vp]
     L.pfgpu_nccl_unique_id.argtypes = [vp]
@@ -461,6 +462,15 @@ class FastSlam1:
         return bool(did.value) if want_flag else None
 
     step = fastslam_update
+
+    def get_observations(self, x_true, landmarks_xy, call):
+        """fs1.rs:277-299 on the device (Philox stream OBS keyed by the handle's seed, `call` and the landmark id)"""
+        xt, lm = _f64(x_true), _f64(landmarks_xy)
+        n = lm.size // 2
+        out = (_FsObs * max(n, 1))()
+        k = C.c_size_t()
+        _check(self.L, self.L.pfgpu_fs_get_observations(self.h, _dp(xt), _dp(lm), n, call, out, C.byref(k)))
+        return [(out[i].d, out[i].angle, int(out[i].lm_id)) for i in range(k.value)]
 
     def get_best_particle(self):
         idx = C.c_size_t()

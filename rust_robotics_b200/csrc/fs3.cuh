@@ -141,21 +141,28 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* g) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-enum { FS3_B_POSE_FULL = 1, FS3_B_POSE_EMPTY = 3, FS3_B_LIK_FULL = 5, FS3_B_LIK_EMPTY = 7 };
+// named barriers: 4 per hand-off stage (stage = trip % number of helper warps)
+__device__ __forceinline__ int fs3_bid(int stage, int which) { return 1 + 4 * stage + which; }   // which: 0 pose full, 1 pose empty, 2 lik full, 3 lik empty
+__device__ __noinline__ void fs3_normal_pair(uint64_t seed, uint32_t call, uint64_t index, double* z0, double* z1) {
+    pfc_normal_pair(pfc_rng_block(seed, PFC_STREAM_FS_PREDICT, call, index), z0, z1);
+}
+__device__ __noinline__ void fs3_sincos(double x, double* s, double* c) { pfc_sincos(x, s, c); }
 
 // flags: bit 0 = first launch of the step (predict; weights start from Particle::weight)
-// dynamic shared memory: pose [2][3][64] | lik [2][k][64] | landing [2][k][6][64]   (doubles)
+// blockDim = 32 * (k_obs + nh), nh >= 1 helper warps.  Dynamic shared memory (doubles):
+//   pose [nh][3][64] | lik [nh][k][64] | landing [2][k][6][64]
 template <int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 fs3_ekf_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsParam po, double u0, double u1, double dt,
                double sq0, double sq1, double r00, double r11, uint64_t seed, uint32_t call, int k_obs, int flags, unsigned step) {
     pf_grid_dep_sync();
     extern __shared__ __align__(16) double s_dyn[];
-    double* s_pose = s_dyn;                                         // [2][3][64]
-    double* s_lik = s_dyn + 384;                                    // [2][k][64]
-    double* s_land = s_lik + (size_t)2 * k_obs * 64;                // [2][k][6][64]
     const int lane = threadIdx.x & 31, wj = threadIdx.x >> 5;
-    const int nsync = 32 * (k_obs + 1);
+    const int nh = (int)(blockDim.x >> 5) - k_obs;
+    double* s_pose = s_dyn;                                         // [nh][3][64]
+    double* s_lik = s_dyn + (size_t)nh * 192;                       // [nh][k][64]
+    double* s_land = s_lik + (size_t)nh * k_obs * 64;               // [2][k][6][64]
+    const int nsync = 32 * (k_obs + 1);                             // one helper + the EKF warps meet at every hand-off
     Fs3State* st = d.st;
     if (d.G > 1 && d.wait_inline) {             // peers' rows / poses / maps are stable once their previous post kernel is over
         if (threadIdx.x == 0) fs3_wait_peers(d, 1, step);
@@ -164,67 +171,72 @@ fs3_ekf_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsP
     const int cur = st->cur, rcur = st->rcur, par = (int)(step & 1u);
     const size_t ld = d.ld;
     const unsigned ngroups = d.ld / 64;
-    if (wj == k_obs) {
-        // =============================== helper warp: predict ahead, weights behind ===============================
-        double2 Wp = make_double2(0.0, 0.0);                              // weights of the previous trip's group
+    if (wj >= k_obs) {
+        // ========== helper warp h: predict for trips h, h + nh, ... (ahead), weight products of the same trips (behind) ==========
+        const int h = wj - k_obs;
+        double2 Wp = make_double2(0.0, 0.0);                              // weights of this helper's previous trip
         unsigned gprev = 0;
-        for (unsigned it = 0, g = blockIdx.x; ; g += gridDim.x, ++it) {
+        bool first = true;
+        for (unsigned g = blockIdx.x + (unsigned)h * gridDim.x; ; g += (unsigned)nh * gridDim.x) {
             const bool have = g < ngroups;
-            const int sg = (int)(it & 1u);
             double2 Wn = make_double2(0.0, 0.0);
             if (have) {
                 const unsigned i0 = g * 64u + 2u * (unsigned)lane;
                 const double* wsrc = (flags & 1) ? d.w : d.wraw[par] + d.off;
                 Wn = *reinterpret_cast<const double2*>(wsrc + i0);                  // needed one trip later
-                double2 X = *reinterpret_cast<const double2*>(d.px[cur] + i0), Y = *reinterpret_cast<const double2*>(d.py[cur] + i0);
-                double2 A = *reinterpret_cast<const double2*>(d.pyaw[cur] + i0);
+                const double2 X = *reinterpret_cast<const double2*>(d.px[cur] + i0), Y = *reinterpret_cast<const double2*>(d.py[cur] + i0);
+                const double2 A = *reinterpret_cast<const double2*>(d.pyaw[cur] + i0);
+                double xs[2] = { X.x, X.y }, ys[2] = { Y.x, Y.y }, as[2] = { A.x, A.y };
                 if (flags & 1) {       // predict_particle + motion_model fs1.rs:70-77,123-137, in place
-                    double xs[2] = { X.x, X.y }, ys[2] = { Y.x, Y.y }, as[2] = { A.x, A.y };
-#pragma unroll
+#pragma unroll 1
                     for (int q = 0; q < 2; ++q) {
                         double z0, z1;
-                        pfc_normal_pair(pfc_rng_block(seed, PFC_STREAM_FS_PREDICT, call, (uint64_t)d.off + i0 + q), &z0, &z1);
+                        fs3_normal_pair(seed, call, (uint64_t)d.off + i0 + q, &z0, &z1);
+                        const double xq = q ? xs[1] : xs[0], yq = q ? ys[1] : ys[0], aq = q ? as[1] : as[0];
                         const double un0 = u0 + z0 * sq0;                      // fs1.rs:129
                         const double un1 = u1 + z1 * sq1;                      // fs1.rs:130
                         double sn, cs;
-                        pfc_sincos(as[q], &sn, &cs);
-                        xs[q] = xs[q] + un0 * dt * cs;                         // motion_model fs1.rs:73-75
-                        ys[q] = ys[q] + un0 * dt * sn;
-                        as[q] = fs_normalize_angle(as[q] + un1 * dt);
+                        fs3_sincos(aq, &sn, &cs);
+                        const double nx = xq + un0 * dt * cs;                  // motion_model fs1.rs:73-75
+                        const double ny = yq + un0 * dt * sn;
+                        const double na = fs_normalize_angle(aq + un1 * dt);
+                        if (q) { xs[1] = nx; ys[1] = ny; as[1] = na; } else { xs[0] = nx; ys[0] = ny; as[0] = na; }
                     }
-                    X = make_double2(xs[0], xs[1]); Y = make_double2(ys[0], ys[1]); A = make_double2(as[0], as[1]);
-                    *reinterpret_cast<double2*>(d.px[cur] + i0) = X; *reinterpret_cast<double2*>(d.py[cur] + i0) = Y;
-                    *reinterpret_cast<double2*>(d.pyaw[cur] + i0) = A;
+                    *reinterpret_cast<double2*>(d.px[cur] + i0) = make_double2(xs[0], xs[1]);
+                    *reinterpret_cast<double2*>(d.py[cur] + i0) = make_double2(ys[0], ys[1]);
+                    *reinterpret_cast<double2*>(d.pyaw[cur] + i0) = make_double2(as[0], as[1]);
                 }
                 if (k_obs > 0) {
-                    if (it >= 2) nb_sync(FS3_B_POSE_EMPTY + sg, nsync);          // the EKF warps have read what this stage held
-                    double* sp = s_pose + sg * 192;
-                    *reinterpret_cast<double2*>(sp + 2 * lane) = X; *reinterpret_cast<double2*>(sp + 64 + 2 * lane) = Y;
-                    *reinterpret_cast<double2*>(sp + 128 + 2 * lane) = A;
+                    if (!first) nb_sync(fs3_bid(h, 1), nsync);                   // the EKF warps have read what this stage held
+                    double* sp = s_pose + h * 192;
+                    *reinterpret_cast<double2*>(sp + 2 * lane) = make_double2(xs[0], xs[1]);
+                    *reinterpret_cast<double2*>(sp + 64 + 2 * lane) = make_double2(ys[0], ys[1]);
+                    *reinterpret_cast<double2*>(sp + 128 + 2 * lane) = make_double2(as[0], as[1]);
                     __threadfence_block();
-                    nb_arrive(FS3_B_POSE_FULL + sg, nsync);
+                    nb_arrive(fs3_bid(h, 0), nsync);
                 }
             }
-            // weights of the group one trip behind (of this trip's group when there are no observations):
+            // weights of this helper's previous trip (of this trip when there are no observations):
             // w = (((w * l_0) * l_1) ...) in observation order (fs1.rs:181 inside the loops fs1.rs:250-256)
-            if (k_obs > 0 ? it >= 1 : have) {
+            if (k_obs > 0 ? !first : have) {
                 const unsigned ge = k_obs > 0 ? gprev : g;
                 const unsigned i0 = ge * 64u + 2u * (unsigned)lane;
                 double w0 = k_obs > 0 ? Wp.x : Wn.x, w1 = k_obs > 0 ? Wp.y : Wn.y;
                 if (k_obs > 0) {
-                    const int se = (int)((it - 1u) & 1u);
-                    nb_sync(FS3_B_LIK_FULL + se, nsync);
-                    const double* sl = s_lik + (size_t)se * k_obs * 64;
+                    nb_sync(fs3_bid(h, 2), nsync);
+                    const double* sl = s_lik + (size_t)h * k_obs * 64;
+#pragma unroll 1
                     for (int j = 0; j < k_obs; ++j) {
                         const double2 l = *reinterpret_cast<const double2*>(sl + j * 64 + 2 * lane);
                         w0 = w0 * l.x; w1 = w1 * l.y;
                     }
-                    nb_arrive(FS3_B_LIK_EMPTY + se, nsync);
+                    nb_arrive(fs3_bid(h, 3), nsync);
                 }
                 const bool v0 = i0 < d.n, v1 = i0 + 1 < d.n;
                 if (!v0) w0 = 0.0;
                 if (!v1) w1 = 0.0;
                 const double psum = warp_sum(w0 + w1);                           // honest (tree-order) sum: steers x3_classify only
+#pragma unroll 1
                 for (int gg = 0; gg < d.G; ++gg) {
                     double* wr = (d.G > 1 ? reinterpret_cast<double*>(d.peer[gg] + d.o_wraw[par]) : d.wraw[par]) + d.off;
                     if (v1) *reinterpret_cast<double2*>(wr + i0) = make_double2(w0, w1);
@@ -236,7 +248,7 @@ fs3_ekf_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsP
                 }
             }
             if (!have) break;
-            Wp = Wn; gprev = g;
+            Wp = Wn; gprev = g; first = false;
         }
         return;
     }
@@ -249,64 +261,62 @@ fs3_ekf_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsP
     const double* lm_own = d.lm[buf] + lbase;
     double* lm_dst = d.lm[ident ? buf : (buf ^ 1)] + lbase;           // own columns; the other buffer when read through a row
     const unsigned* row = ident ? nullptr : d.rows[rcur] + (size_t)((sl >> 1) - 1) * ld;
-    // issue the landing copies of group g into stage sg (each lane copies exactly the 12 doubles it will consume)
-    auto issue = [&](unsigned g, int sg, uint2 ref) {
-        double* land = s_land + ((size_t)sg * k_obs + wj) * 384 + 2 * lane;
-        const unsigned i0 = g * 64u + 2u * (unsigned)lane;
-        if (ident) {
-#pragma unroll
-            for (int f = 0; f < 6; ++f) cp_async16(land + f * 64, lm_own + f * ld + i0);
-        } else {                                  // lazy clone: the ancestors' copies, through the landmark's row
-            const unsigned rr[2] = { ref.x, ref.y };
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const double* base = d.G > 1 ? reinterpret_cast<const double*>(d.peer[rr[q] >> 28] + d.o_lm[buf]) + lbase : lm_own;
-                const double* p = base + (rr[q] & 0x0FFFFFFFu);
-#pragma unroll
-                for (int f = 0; f < 6; ++f) cp_async8(land + f * 64 + q, p + f * ld);
-            }
-        }
-        cp_async_commit();
-    };
     unsigned g = blockIdx.x;
     if (g >= ngroups) return;
-    uint2 ref_next = make_uint2(0u, 0u);
-    {
-        uint2 r0 = make_uint2(0u, 0u);
-        if (!ident) r0 = *reinterpret_cast<const uint2*>(row + g * 64u + 2u * (unsigned)lane);
-        issue(g, 0, r0);
-        if (!ident && g + gridDim.x < ngroups) ref_next = *reinterpret_cast<const uint2*>(row + (g + gridDim.x) * 64u + 2u * (unsigned)lane);
+    uint2 ref_cur = make_uint2(0u, 0u), ref_next = make_uint2(0u, 0u);
+    if (!ident) {
+        ref_cur = *reinterpret_cast<const uint2*>(row + g * 64u + 2u * (unsigned)lane);
+        if (g + gridDim.x < ngroups) ref_next = *reinterpret_cast<const uint2*>(row + (g + gridDim.x) * 64u + 2u * (unsigned)lane);
     }
-    for (unsigned it = 0; g < ngroups; g += gridDim.x, ++it) {
-        const int sg = (int)(it & 1u);
-        const unsigned i0 = g * 64u + 2u * (unsigned)lane;
-        // [A] this group's landmark columns out of the landing buffer
-        cp_async_wait_all();
+    // trip -1 .. last: at the top of trip `it` the landing copies of trip it are in flight; the body issues those of trip it + 1
+    int stage = 0;
+    for (int it = -1; ; ++it) {
+        const unsigned gi = it < 0 ? g : g + gridDim.x;            // group whose copies are issued in this pass
+        const bool issue_ok = gi < ngroups;
         FsLm L[2];
-        {
-            const double* land = s_land + ((size_t)sg * k_obs + wj) * 384 + 2 * lane;
+        if (it >= 0) {
+            // [A] this group's landmark columns out of the landing buffer
+            cp_async_wait_all();
+            const double* land = s_land + ((size_t)(it & 1) * k_obs + wj) * 384 + 2 * lane;
             const double2 a = *reinterpret_cast<const double2*>(land), b = *reinterpret_cast<const double2*>(land + 64);
             const double2 c = *reinterpret_cast<const double2*>(land + 128), e = *reinterpret_cast<const double2*>(land + 192);
-            const double2 f = *reinterpret_cast<const double2*>(land + 256), h = *reinterpret_cast<const double2*>(land + 320);
+            const double2 f = *reinterpret_cast<const double2*>(land + 256), hh = *reinterpret_cast<const double2*>(land + 320);
             L[0].x = a.x; L[1].x = a.y; L[0].y = b.x; L[1].y = b.y; L[0].c00 = c.x; L[1].c00 = c.y;
-            L[0].c01 = e.x; L[1].c01 = e.y; L[0].c10 = f.x; L[1].c10 = f.y; L[0].c11 = h.x; L[1].c11 = h.y;
+            L[0].c01 = e.x; L[1].c01 = e.y; L[0].c10 = f.x; L[1].c10 = f.y; L[0].c11 = hh.x; L[1].c11 = hh.y;
         }
-        // [B] next group's copies (its row entries were loaded one trip ago), and the row entries of the group after it
-        const unsigned gn = g + gridDim.x;
-        if (gn < ngroups) {
-            issue(gn, sg ^ 1, ref_next);
-            if (!ident && gn + gridDim.x < ngroups) ref_next = *reinterpret_cast<const uint2*>(row + (gn + gridDim.x) * 64u + 2u * (unsigned)lane);
+        // [B] issue the landing copies of the next group (each lane copies exactly the 12 doubles it will consume)
+        if (issue_ok) {
+            double* land = s_land + ((size_t)((it + 1) & 1) * k_obs + wj) * 384 + 2 * lane;
+            const unsigned i0n = gi * 64u + 2u * (unsigned)lane;
+            if (ident) {
+#pragma unroll
+                for (int f = 0; f < 6; ++f) cp_async16(land + f * 64, lm_own + f * ld + i0n);
+            } else {                                  // lazy clone: the ancestors' copies, through the landmark's row
+                const uint2 ref = it < 0 ? ref_cur : ref_next;
+                const unsigned rr[2] = { ref.x, ref.y };
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const double* base = d.G > 1 ? reinterpret_cast<const double*>(d.peer[rr[q] >> 28] + d.o_lm[buf]) + lbase : lm_own;
+                    const double* p = base + (rr[q] & 0x0FFFFFFFu);
+#pragma unroll
+                    for (int f = 0; f < 6; ++f) cp_async8(land + f * 64 + q, p + f * ld);
+                }
+                if (it >= 0 && gi + gridDim.x < ngroups) ref_next = *reinterpret_cast<const uint2*>(row + (gi + gridDim.x) * 64u + 2u * (unsigned)lane);
+            }
+            cp_async_commit();
         }
+        if (it < 0) continue;
+        const unsigned i0 = g * 64u + 2u * (unsigned)lane;
         // [C] the predicted pose of this group
-        nb_sync(FS3_B_POSE_FULL + sg, nsync);
+        nb_sync(fs3_bid(stage, 0), nsync);
         double px[2], py[2], pyaw[2];
         {
-            const double* sp = s_pose + sg * 192;
+            const double* sp = s_pose + stage * 192;
             const double2 X = *reinterpret_cast<const double2*>(sp + 2 * lane), Y = *reinterpret_cast<const double2*>(sp + 64 + 2 * lane);
             const double2 A = *reinterpret_cast<const double2*>(sp + 128 + 2 * lane);
             px[0] = X.x; px[1] = X.y; py[0] = Y.x; py[1] = Y.y; pyaw[0] = A.x; pyaw[1] = A.y;
         }
-        nb_arrive(FS3_B_POSE_EMPTY + sg, nsync);
+        nb_arrive(fs3_bid(stage, 1), nsync);
         // [D] update_landmark for the two pairs
         double lik[2] = { 1.0, 1.0 };
         int ok[2];
@@ -322,10 +332,13 @@ fs3_ekf_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsP
         *reinterpret_cast<double2*>(o + 4 * ld) = make_double2(L[0].c10, L[1].c10);
         *reinterpret_cast<double2*>(o + 5 * ld) = make_double2(L[0].c11, L[1].c11);
         // [E] likelihood factors to the helper
-        if (it >= 2) nb_sync(FS3_B_LIK_EMPTY + sg, nsync);
-        *reinterpret_cast<double2*>(s_lik + ((size_t)sg * k_obs + wj) * 64 + 2 * lane) = make_double2(lik[0], lik[1]);
+        if (it >= nh) nb_sync(fs3_bid(stage, 3), nsync);
+        *reinterpret_cast<double2*>(s_lik + ((size_t)stage * k_obs + wj) * 64 + 2 * lane) = make_double2(lik[0], lik[1]);
         __threadfence_block();
-        nb_arrive(FS3_B_LIK_FULL + sg, nsync);
+        nb_arrive(fs3_bid(stage, 2), nsync);
+        g += gridDim.x;
+        if (g >= ngroups) break;
+        stage = stage + 1 == nh ? 0 : stage + 1;
     }
 }
 
@@ -381,6 +394,7 @@ __device__ __forceinline__ void fs3_bar_arrive(const Fs3Dev& d, int round) {    
 }
 __device__ __forceinline__ void fs3_bar_wait(const Fs3Dev& d, int round, unsigned nblocks) {   // one thread
     unsigned spins = 0;
+#pragma unroll 1
     while (*reinterpret_cast<volatile unsigned*>(d.bar + round) < nblocks) { if (++spins > FS3_SPIN_LIMIT) { d.st->err = 1; break; } __nanosleep(20); }
     __threadfence();
 }
@@ -396,13 +410,14 @@ template <int NT>
 __device__ __forceinline__ double fs3_scan_d(double x, double* sm) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double inc = x;
-#pragma unroll
+#pragma unroll 1
     for (int o = 1; o < 32; o <<= 1) { const double y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = y + inc; }
     double ex = __shfl_up_sync(0xffffffffu, inc, 1);
     if (lane == 0) ex = 0.0;
     if (lane == 31) sm[wid] = inc;
     __syncthreads();
     double woff = 0.0;
+#pragma unroll 1
     for (int w = 0; w < wid; ++w) woff += sm[w];
     return woff + ex;
 }
@@ -412,7 +427,7 @@ __device__ __forceinline__ void fs3_scan_ui(unsigned long long p, int c, unsigne
                                             unsigned long long* smu, int* smi) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     unsigned long long ip = p; int ic = c;
-#pragma unroll
+#pragma unroll 1
     for (int o = 1; o < 32; o <<= 1) {
         const unsigned long long y = __shfl_up_sync(0xffffffffu, ip, o); const int z = __shfl_up_sync(0xffffffffu, ic, o);
         if (lane >= o) { ip += y; ic += z; }
@@ -420,28 +435,36 @@ __device__ __forceinline__ void fs3_scan_ui(unsigned long long p, int c, unsigne
     if (lane == 31) { smu[wid] = ip; smi[wid] = ic; }
     __syncthreads();
     unsigned long long wp = 0, tp = 0; int wc = 0, tc = 0;
+#pragma unroll 1
     for (int w = 0; w < NT / 32; ++w) { const unsigned long long a = smu[w]; const int b = smi[w]; if (w < wid) { wp += a; wc += b; } tp += a; tc += b; }
     *pex = wp + ip - p; *cex = wc + ic - c; *ptot = tp; *ctot = tc;
+}
+__device__ __forceinline__ double fs3_warp_sum(double v) {
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
 }
 // block sums of two doubles at once (tree order, identical in every CTA; valid in all threads); ONE block barrier
 template <int NT>
 __device__ __forceinline__ void fs3_block_sum2(double& x, double& y, double* smx, double* smy) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    x = warp_sum(x); y = warp_sum(y);
+    x = fs3_warp_sum(x); y = fs3_warp_sum(y);
     if (lane == 0) { smx[wid] = x; smy[wid] = y; }
     __syncthreads();
     double a = 0.0, b = 0.0;
+#pragma unroll 1
     for (int w = 0; w < NT / 32; ++w) { a += smx[w]; b += smy[w]; }
     x = a; y = b;
 }
 
+__device__ __noinline__ double fs3_div(double a, double b) { return a / b; }      // one copy of the IEEE division sequence
 // value i of the sum `slot`, recomputed from global memory (serial walks only)
 __device__ __forceinline__ double fs3_value(const Fs3Dev& d, int slot, size_t i, int par, double S2, double r0, double inv) {
     if (slot == 0) return __ldcg(d.wraw[par] + i);
     const double w = slot == 4 ? 0.0 : __ldcg(d.wn_all + i);
     if (slot == 1) return w * w;
     if (slot == 2) return w;
-    if (slot == 3) return S2 > 0.0 ? w / S2 : w;
+    if (slot == 3) return S2 > 0.0 ? fs3_div(w, S2) : w;
     return i == 0 ? r0 : inv;
 }
 // exact by construction: one thread walks all values in order (bad values, too many dirty ones, failed certificate)
@@ -451,18 +474,23 @@ __device__ __noinline__ void fs3_serial_walk(const Fs3Dev& d, Fs3Sh<NT>& sh, uns
         const size_t T = (size_t)NT * K, lo = (size_t)blockIdx.x * T;
         double s = 0.0;
         sh.tbase = 0.0;
+#pragma unroll 1
         for (size_t i = 0; i < d.n_glob; ++i) { if (i == lo) sh.tbase = s; s = s + fs3_value(d, slot, i, par, S2, r0, inv); }
         if (lo >= d.n_glob) sh.tbase = s;
         sh.total = s;
         if (blockIdx.x == 0) d.st->serial_walks += 1;
         if (out) {
             double c = sh.tbase;
+#pragma unroll 1
             for (size_t i = lo; i < lo + T && i < d.n_glob; ++i) { c = c + fs3_value(d, slot, i, par, S2, r0, inv); out[i] = c; }
         }
     }
     __syncthreads();
 }
 
+__device__ __noinline__ int fs3_classify(double v, double a0, double a1, unsigned m32, unsigned long long* inc, int* lvl) {
+    return x3_classify(v, a0, a1, m32, inc, lvl);            // one copy of the code for the three passes of fs3_xsum
+}
 // One exact sequential sum over the n_glob values held tile-wise in shared memory (thread t owns values t*K .. t*K+K-1 of its
 // tile, stored at vals[k*NT + t]).  toff = approximate sum of everything in front of this tile.  Returns the exact total
 // (identical in every CTA); with out != nullptr also stores the exact inclusive prefix of every value to out[global index].
@@ -478,15 +506,17 @@ __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const do
     if (d.trace && b == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_prev));
     // ---- approximate prefixes, classification, tile aggregate ----
     double ts = 0.0; bool bad = false;
+#pragma unroll 1
     for (unsigned k = 0; k < K; ++k) { const double v = vals[k * NT + tid]; ts += v; if (!(v >= 0.0) || !(v <= 1.7976931348623157e308)) bad = true; }
     const double a_first = toff + fs3_scan_d<NT>(ts, sh.wd[pp]);
     unsigned long long P = 0; int nd = 0;
     {
         double a = a_first;
-        for (unsigned k = 0; k < K; ++k) {
+    #pragma unroll 1
+    for (unsigned k = 0; k < K; ++k) {
             const double v = vals[k * NT + tid], a1 = a + v;
             unsigned long long inc; int lvl;
-            if (x3_classify(v, a, a1, m32, &inc, &lvl)) nd++; else P += inc;
+            if (fs3_classify(v, a, a1, m32, &inc, &lvl)) nd++; else P += inc;
             a = a1;
         }
     }
@@ -495,10 +525,11 @@ __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const do
     if (nd > 0) {                                              // rare: itemise this thread's dirty values (any order; sorted by the chain)
         const unsigned e0 = atomicAdd(d.entCnt + slot, (unsigned)nd);
         double a = a_first; unsigned long long Pr = Pex; unsigned e = e0;
-        for (unsigned k = 0; k < K; ++k) {
+    #pragma unroll 1
+    for (unsigned k = 0; k < K; ++k) {
             const double v = vals[k * NT + tid], a1 = a + v;
             unsigned long long inc; int lvl;
-            if (x3_classify(v, a, a1, m32, &inc, &lvl)) {
+            if (fs3_classify(v, a, a1, m32, &inc, &lvl)) {
                 if (e < FS3_ENT_CAP) {
                     const size_t o = (size_t)slot * FS3_ENT_CAP + e;
                     d.entKey[o] = (unsigned)((size_t)b * T + (size_t)tid * K + k); d.entTile[o] = b; d.entP[o] = Pr; d.entV[o] = v; d.entL[o] = lvl;
@@ -519,28 +550,28 @@ __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const do
         FS3_TRACE(tb0 + 1);
         // clean-increment sum in front of every tile (lane owns `per` consecutive tiles)
         const unsigned per = (nt + 31u) / 32u, t0 = (unsigned)lane * per;
-        unsigned long long loc[(FS3_MAX_TILES + 31) / 32], lsum = 0;
-#pragma unroll
-        for (unsigned i = 0; i < (FS3_MAX_TILES + 31) / 32; ++i) {
-            loc[i] = (i < per && t0 + i < nt) ? __ldcg(d.tileP + (size_t)slot * FS3_MAX_TILES + t0 + i) : 0ull;
-            lsum += loc[i];
-        }
+        unsigned long long lsum = 0;
+#pragma unroll 1
+        for (unsigned i = 0; i < per; ++i) if (t0 + i < nt) lsum += __ldcg(d.tileP + (size_t)slot * FS3_MAX_TILES + t0 + i);
         const unsigned cnt = __ldcg(d.entCnt + slot);
         int fail = __ldcg(d.flagsg + slot) | (cnt > FS3_ENT_CAP ? 1 : 0);
         unsigned long long inc = lsum;
-#pragma unroll
+#pragma unroll 1
         for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
         const unsigned long long Ptot = __shfl_sync(0xffffffffu, inc, 31);
         unsigned long long run = inc - lsum;
-#pragma unroll
-        for (unsigned i = 0; i < (FS3_MAX_TILES + 31) / 32; ++i) { if (i < per && t0 + i < nt) sh.tPoff[t0 + i] = run; run += loc[i]; }
+#pragma unroll 1
+        for (unsigned i = 0; i < per; ++i) if (t0 + i < nt) { sh.tPoff[t0 + i] = run; run += __ldcg(d.tileP + (size_t)slot * FS3_MAX_TILES + t0 + i); }
         const int D = fail ? 0 : (int)cnt;
         const size_t eb = (size_t)slot * FS3_ENT_CAP;
+#pragma unroll 1
         for (int e = lane; e < D; e += 32) sh.ukey[e] = __ldcg(d.entKey + eb + e);
         __syncwarp();
+#pragma unroll 1
         for (int e = lane; e < D; e += 32) {                   // rank = position in index order (keys are distinct)
             const unsigned key = sh.ukey[e];
             int rank = 0;
+#pragma unroll 1
             for (int j = 0; j < D; ++j) rank += sh.ukey[j] < key ? 1 : 0;
             sh.skey[rank] = key; sh.sP[rank] = sh.tPoff[__ldcg(d.entTile + eb + e)] + __ldcg(d.entP + eb + e);
             sh.sV[rank] = __ldcg(d.entV + eb + e); sh.sL[rank] = __ldcg(d.entL + eb + e);
@@ -549,6 +580,7 @@ __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const do
         double total = 0.0;
         if (lane == 0) {                                       // the serial part: one integer add + one FP add per dirty value
             double s = 0.0; unsigned long long prev = 0;
+#pragma unroll 1
             for (int o = 0; o < D; ++o) {
                 const unsigned long long p = sh.sP[o];
                 sh.bef[o] = s;
@@ -560,6 +592,7 @@ __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const do
             if (!ok) fail = 1;
         }
         __syncwarp();
+#pragma unroll 1
         for (int o = lane; o < D; o += 32) {                   // certificates of the clean runs, in parallel
             const unsigned long long dp = sh.sP[o] - (o ? sh.sP[o - 1] : 0ull);
             int ok = 1;
@@ -576,15 +609,21 @@ __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const do
         const int D = sh.D;
         const size_t g0 = (size_t)b * T + (size_t)tid * K;
         int ko = 0;                                            // dirty values in front of this thread's first value
-        { int lo = 0, hi = D; while (lo < hi) { const int mid = (lo + hi) >> 1; if ((size_t)sh.skey[mid] < g0) lo = mid + 1; else hi = mid; } ko = lo; }
+        {
+            int lo = 0, hi = D;
+#pragma unroll 1
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if ((size_t)sh.skey[mid] < g0) lo = mid + 1; else hi = mid; }
+            ko = lo;
+        }
         double base = ko ? sh.aft[ko - 1] : 0.0;
         unsigned long long Pb = ko ? sh.sP[ko - 1] : 0ull, Pc = sh.tPoff[b] + Pex;
         double a = a_first;
         int ok = 1;
-        for (unsigned k = 0; k < K; ++k) {
+    #pragma unroll 1
+    for (unsigned k = 0; k < K; ++k) {
             const double v = vals[k * NT + tid], a1 = a + v;
             unsigned long long inc; int lvl; double c;
-            if (x3_classify(v, a, a1, m32, &inc, &lvl)) { base = sh.aft[ko]; Pb = sh.sP[ko]; ko++; c = base; }
+            if (fs3_classify(v, a, a1, m32, &inc, &lvl)) { base = sh.aft[ko]; Pb = sh.sP[ko]; ko++; c = base; }
             else { Pc += inc; c = x3_apply(base, Pc - Pb, inc ? lvl : -1, &ok); }
             if (g0 + k < d.n_glob) out[g0 + k] = c;
             a = a1;
@@ -598,6 +637,7 @@ __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const do
 // lower bound of r in the exact CDF, clamped: "while r > cum_sum[j+1] && j < n-1 { j += 1 }" (fs1.rs:224-226) with r and j both
 // non-decreasing over the slots, i.e. the first j with c_j >= r.  Searched inside [lo, hi) (c_{lo-1} < r guaranteed by the caller).
 __device__ __forceinline__ unsigned fs3_lower_bound(const double* c, unsigned lo, unsigned hi, double r) {
+#pragma unroll 1
     while (lo < hi) { const unsigned mid = lo + ((hi - lo) >> 1); if (__ldcg(c + mid) < r) lo = mid + 1; else hi = mid; }
     return lo;
 }
@@ -605,6 +645,7 @@ __device__ __forceinline__ unsigned fs3_lower_bound(const double* c, unsigned lo
 __device__ __forceinline__ unsigned fs3_warp_search(const double* c, unsigned n, double r) {
     const int lane = threadIdx.x & 31;
     unsigned lo = 0, hi = n;                                  // answer in [lo, hi]
+#pragma unroll 1
     while (hi - lo > 32) {
         const unsigned step = (hi - lo + 32) / 33;            // probes lo + (lane+1)*step - 1
         const unsigned long long pi = (unsigned long long)lo + (unsigned long long)(lane + 1) * step - 1ull;
@@ -649,15 +690,17 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
         if (tid < 32) s_bits[tid] = 0u;
         __syncthreads();
         int any_ident = 0;
+#pragma unroll 1
         for (unsigned l = tid; l < d.m; l += NT) { const int s = d.lmst[l]; if (s >> 1) atomicOr(&s_bits[((s >> 1) - 1) >> 5], 1u << (((s >> 1) - 1) & 31)); else any_ident = 1; }
         any_ident = __syncthreads_or(any_ident);
         if (tid < 32) {
             const unsigned bits = s_bits[tid];
             const int cnt = __popc(bits);
             int incl = cnt;
-#pragma unroll
+#pragma unroll 1
             for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += y; }
             int pos = incl - cnt;
+#pragma unroll 1
             for (unsigned x = bits; x; x &= x - 1) d.rowlist[pos++] = (unsigned short)(tid * 32 + __ffs(x) - 1);
             const unsigned fr = ~bits;
             const unsigned has = __ballot_sync(0xffffffffu, fr != 0u);
@@ -670,10 +713,12 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
     // ---- load this tile's weights; approximate sum of everything in front of the tile from the 64-particle partials ----
     const size_t g0 = (size_t)b * T + (size_t)tid * K;
     double q = 0.0;
+#pragma unroll 1
     for (unsigned k = 0; k < K; ++k) { const double v = g0 + k < ng ? __ldcg(d.wraw[par] + g0 + k) : 0.0; vals[k * NT + tid] = v; q += v * v; }
     double toff = 0.0;
     {
         const unsigned pfirst = (unsigned)(((size_t)b * T) / 64);      // partial p covers global slots [64 p, 64 p + 64)
+#pragma unroll 1
         for (unsigned p = tid; p < pfirst; p += NT) toff += __ldcg(d.part[par] + p);
     }
     fs3_block_sum2<NT>(toff, q, sh.red[0], sh.red[1]);
@@ -683,9 +728,10 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
     FS3_TRACE(1);
     // w = w_raw / S; best particle of the tile (LAST maximum, fs1.rs:269-274)
     double bw = -1.0; unsigned bi = 0;
+#pragma unroll 1
     for (unsigned k = 0; k < K; ++k) {
         double v = vals[k * NT + tid];
-        if (S > 0.0) v = v / S;
+        if (S > 0.0) v = fs3_div(v, S);
         vals[k * NT + tid] = v;
         const size_t i = g0 + k;
         if (i < ng) {
@@ -694,7 +740,7 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
             if (v >= bw) { bw = v; bi = (unsigned)i; }
         }
     }
-#pragma unroll
+#pragma unroll 1
     for (int o = 16; o > 0; o >>= 1) {      // arg-max with "last wins among equals"
         const double ow = __shfl_xor_sync(0xffffffffu, bw, o); const unsigned oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ow > bw || (ow == bw && oi > bi)) { bw = ow; bi = oi; }
@@ -707,36 +753,41 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
     double Q = (unsigned)tid < nt ? __ldcg(d.tileQ + tid) : 0.0, dummy = 0.0;
     fs3_block_sum2<NT>(Q, dummy, sh.red[1], sh.wd[1]);         // (also orders the arg-max partials above)
     if (tid == 0) {
+#pragma unroll 1
         for (int w = 1; w < NT / 32; ++w) { const double ow = sh.red[0][w]; const unsigned oi = (unsigned)sh.wi[0][w]; if (ow > bw || (ow == bw && oi > bi)) { bw = ow; bi = oi; } }
         d.tileBw[b] = bw; d.tileBi[b] = bi;
     }
-    if (S > 0.0) Q = (Q / S) / S;
-    double neff = Q > 0.0 ? 1.0 / Q : 0.0;
+    if (S > 0.0) Q = fs3_div(fs3_div(Q, S), S);
+    double neff = Q > 0.0 ? fs3_div(1.0, Q) : 0.0;
     const double slack = 16.0 * (double)(ng + 64) * 2.220446049250313e-16;
     if (!(fabs(neff - nth) > slack * fmax(fabs(nth), fabs(neff)))) {     // rare; the same decision in every CTA
         fs3_grid_sync<NT>(d, 6, nt);                           // wn_all is complete
         if (tid == 0) {
             double s = 0.0;
+#pragma unroll 1
             for (size_t i = 0; i < ng; ++i) { const double w = __ldcg(d.wn_all + i); s = s + w * w; }
             sh.bcast = s;
             if (b == 0) st->border_cnt += 1;
         }
         __syncthreads();
         Q = sh.bcast;
-        neff = Q > 0.0 ? 1.0 / Q : 0.0;
+        neff = Q > 0.0 ? fs3_div(1.0, Q) : 0.0;
     }
     const int gate = neff < nth ? 1 : 0;
     FS3_TRACE(2);
     double S2 = 0.0, r0 = 0.0;
-    const double inv = 1.0 / (double)ng;
+    const double inv = fs3_div(1.0, (double)ng);
     if (gate) {
         // ---------------- resample() re-normalises first (fs1.rs:207) ----------------
-        const double toff2 = S > 0.0 ? toff / S : toff;
+        const double toff2 = S > 0.0 ? fs3_div(toff, S) : toff;
         S2 = fs3_xsum<NT>(d, sh, vals, K, nt, toff2, 2, 1, m32, nullptr, par, 0.0, 0.0, 0.0, 0.0);
         FS3_TRACE(3);
-        if (S2 > 0.0) for (unsigned k = 0; k < K; ++k) vals[k * NT + tid] = vals[k * NT + tid] / S2;
+        if (S2 > 0.0) {
+#pragma unroll 1
+            for (unsigned k = 0; k < K; ++k) vals[k * NT + tid] = fs3_div(vals[k * NT + tid], S2);
+        }
         // ---------------- cum_sum fs1.rs:213-216 ----------------
-        const double toff3 = S2 > 0.0 ? toff2 / S2 : toff2;
+        const double toff3 = S2 > 0.0 ? fs3_div(toff2, S2) : toff2;
         (void)fs3_xsum<NT>(d, sh, vals, K, nt, toff3, 3, 2, m32, d.cum_all, par, S2, 0.0, 0.0, 0.0);
         FS3_TRACE(4);
         // ---------------- the comb r, r + 1/n, ... accumulated sequentially (fs1.rs:219-230) ----------------
@@ -745,7 +796,8 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
             r0 = u01 * (inv - 0.0) + 0.0;                      // Uniform::new(0, 1/n).sample
         }
         if (log2n < 0) {                                       // n not a power of two: every add rounds -> exact scan
-            for (unsigned k = 0; k < K; ++k) { const size_t i = g0 + k; vals[k * NT + tid] = i < ng ? (i == 0 ? r0 : inv) : 0.0; }
+        #pragma unroll 1
+    for (unsigned k = 0; k < K; ++k) { const size_t i = g0 + k; vals[k * NT + tid] = i < ng ? (i == 0 ? r0 : inv) : 0.0; }
             const double toff4 = b == 0 ? 0.0 : r0 + ((double)((size_t)b * T) - 1.0) * inv;
             __syncthreads();
             (void)fs3_xsum<NT>(d, sh, vals, K, nt, toff4, 4, 3, m32, d.rcomb_all, par, S2, r0, inv, 0.0);
@@ -760,6 +812,7 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
         const unsigned per = (d.n + nt - 1) / nt;              // local slots per CTA
         const unsigned t_lo = b * per, t_hi = min(d.n, t_lo + per);
         const double* cdf = d.cum_all;
+#pragma unroll 1
         for (unsigned tb = t_lo + (tid & ~31); tb < t_hi; tb += NT) {       // a warp takes 32 consecutive slots
             const unsigned t = tb + (tid & 31);
             const size_t tg = (size_t)d.off + t;
@@ -783,6 +836,7 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
             d.w[t] = inv;                                                                // fs1.rs:228
             const unsigned* srows = d.G > 1 ? reinterpret_cast<const unsigned*>(d.peer[jr] + d.o_rows[rcur]) : d.rows[rcur];
             unsigned* drows = d.rows[rcur ^ 1];
+#pragma unroll 1
             for (int x = 0; x < nrows; ++x) { const size_t ro = (size_t)d.rowlist[x] * d.ld; drows[ro + t] = srows[ro + jc]; }
             if (newrow >= 0) drows[(size_t)newrow * d.ld + t] = fs3_ref(jr, jc);
         }
@@ -796,6 +850,7 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
     __threadfence();
     if (gate) {
         const int newrow = d.rowinfo[1];
+#pragma unroll 1
         for (unsigned l = tid; l < d.m; l += NT) { const int s = d.lmst[l]; if ((s >> 1) == 0) d.lmst[l] = (s & 1) | ((newrow + 1) << 1); }
     }
     if (tid < FS3_SLOTS) { d.flagsg[tid] = 0; d.entCnt[tid] = 0u; }
@@ -803,8 +858,9 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
     if (tid < 32) {
         // best particle: the last maximum over the tiles (no resample) / the last slot (after a resample every weight is 1/n)
         double bw2 = -1.0; unsigned bi2 = 0;
+#pragma unroll 1
         for (unsigned x = tid; x < nt; x += 32) { const double ow = __ldcg(d.tileBw + x); const unsigned oi = __ldcg(d.tileBi + x); if (ow > bw2 || (ow == bw2 && oi > bi2)) { bw2 = ow; bi2 = oi; } }
-#pragma unroll
+#pragma unroll 1
         for (int o = 16; o > 0; o >>= 1) {
             const double ow = __shfl_xor_sync(0xffffffffu, bw2, o); const unsigned oi = __shfl_xor_sync(0xffffffffu, bi2, o);
             if (ow > bw2 || (ow == bw2 && oi > bi2)) { bw2 = ow; bi2 = oi; }
@@ -904,3 +960,40 @@ __global__ void __launch_bounds__(256) fs3_seed_lm_kernel(const __grid_constant_
     p[0] = lm_xy[2 * l] + sigma * z0; p[d.ld] = lm_xy[2 * l + 1] + sigma * z1;
     p[2 * (size_t)d.ld] = cov0; p[3 * (size_t)d.ld] = 0.0; p[4 * (size_t)d.ld] = 0.0; p[5 * (size_t)d.ld] = cov0;
 }
+
+// get_observations fs1.rs:277-299 (the simulator next to the filter): landmarks within max_range of the true pose, in
+// landmark order, range and bearing perturbed by N(0,1) * sqrt(R) drawn from Philox stream PFC_STREAM_OBS (call, landmark id).
+// One CTA; order-preserving compaction by ballot.  out_k[0] = number of observations.
+__global__ void __launch_bounds__(1024) fs3_get_observations_kernel(double x, double y, double yaw, const double* lm_xy, unsigned n_lm,
+                                                                    double max_range, double sr0, double sr1, uint64_t seed, uint32_t call,
+                                                                    Fs3Obs* out, unsigned* out_k) {
+    __shared__ unsigned s_w[32];
+    __shared__ unsigned s_base;
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (unsigned l0 = 0; l0 < n_lm; l0 += 1024) {
+        const unsigned id = l0 + threadIdx.x;
+        bool in = false; double d = 0.0, dx = 0.0, dy = 0.0;
+        if (id < n_lm) { dx = lm_xy[2 * id] - x; dy = lm_xy[2 * id + 1] - y; d = sqrt(dx * dx + dy * dy); in = d <= max_range; }
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        if (lane == 0) s_w[wid] = __popc(m);
+        __syncthreads();
+        unsigned off = s_base;
+        for (unsigned w = 0; w < wid; ++w) off += s_w[w];
+        if (in) {
+            const unsigned o = off + __popc(m & ((1u << lane) - 1u));
+            const double angle = fs_normalize_angle(pfc_atan2(dy, dx) - yaw);
+            double z0, z1;
+            pfc_normal_pair(pfc_rng_block(seed, PFC_STREAM_OBS, call, id), &z0, &z1);
+            out[o].d = d + z0 * sr0;                               // fs1.rs:291
+            out[o].angle = angle + z1 * sr1;                       // fs1.rs:292
+            out[o].lm_id = (int)id; out[o].pad = 0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { unsigned t = 0; for (unsigned w = 0; w < 32; ++w) t += s_w[w]; s_base += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out_k = s_base;
+}
+

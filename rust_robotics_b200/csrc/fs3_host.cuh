@@ -20,6 +20,7 @@ struct pfgpu_fs {
     double* stage = nullptr; size_t stage_bytes = 0;   // device staging buffer for upload / download / seed_map
     bool pdl = true;
     bool ekf_attr[2] = { false, false };
+    int ekf_helpers = 0;              // PFGPU_EKF_HELPERS: cap on the helper warps per CTA (0 = as many as fit, at most 3)
     int post_nt = 256; unsigned post_K = 1, post_tiles = 1, m32 = 0; int log2n = -1; size_t post_smem = 0;
 };
 
@@ -134,6 +135,7 @@ static int fs_create_impl(const pfgpu_fs_config* cfg, size_t n, size_t n_global,
         if (getenv("PFGPU_POST_TRACE")) { FS_TRY(cudaMalloc(&d.trace, 32 * sizeof(unsigned long long))); FS_TRY(cudaMemset(d.trace, 0, 32 * sizeof(unsigned long long))); }
     }
     { const char* e5 = getenv("PFGPU_PDL"); h->pdl = !(e5 && e5[0] == '0'); }
+    { const char* e6 = getenv("PFGPU_EKF_HELPERS"); if (e6 && atoi(e6) >= 1 && atoi(e6) <= 3) h->ekf_helpers = atoi(e6); }
     if (world > 1 && uid) {
         ncclUniqueId id;
         memcpy(&id, uid, sizeof(id));
@@ -322,14 +324,20 @@ extern "C" int pfgpu_fs_seed_map(pfgpu_fs* h, const double pose3[3], const doubl
 template <int MAXT>
 static int fs3_launch_ekf(pfgpu_fs* h, const Fs3ObsParam& po, const double u[2], int kk, int flags) {
     const Fs3Dev& d = h->d;
-    const unsigned threads = 32u * (unsigned)(kk + 1);
-    const size_t smem = (384 + (size_t)2 * kk * 64 + (size_t)2 * kk * 384) * sizeof(double);
+    // helper warps (predict ahead / weights behind): as many as fit the CTA beside the kk EKF warps, at most 3
+    int nh = kk > 0 ? std::min(3, MAXT / 32 - kk) : 1;
+    if (h->ekf_helpers > 0 && kk > 0) nh = std::min(nh, h->ekf_helpers);
+    const unsigned threads = 32u * (unsigned)(kk + nh);
+    auto smem_of = [](int k, int n) { return ((size_t)n * 192 + (size_t)n * k * 64 + (size_t)2 * k * 384) * sizeof(double); };
+    const size_t smem = smem_of(kk, nh);
     const unsigned groups = d.ld / 64;
     // persistent: one CTA per SM walks the 64-particle groups; without observations the launch is predict-only and latency
     // bound, so every group gets its own (one-warp) CTA
     const unsigned grid = kk > 0 ? std::min<unsigned>(groups, (unsigned)h->ctx.num_sms) : groups;
     if (!h->ekf_attr[MAXT == 512 ? 0 : 1]) {
-        PF_CUDA(cudaFuncSetAttribute(fs3_ekf_kernel<MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((384 + (size_t)2 * (MAXT / 32 - 1) * 448) * sizeof(double))));
+        size_t mx = 0;
+        for (int k = 0; k < MAXT / 32; ++k) mx = std::max(mx, smem_of(k, std::min(3, MAXT / 32 - k)));
+        PF_CUDA(cudaFuncSetAttribute(fs3_ekf_kernel<MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
         h->ekf_attr[MAXT == 512 ? 0 : 1] = true;
     }
     PF_LAUNCH_PDL(h->ctx, h->pdl, (fs3_ekf_kernel<MAXT>), grid, threads, smem, d, po, u[0], u[1], h->cfg.dt, sqrt(h->cfg.q00), sqrt(h->cfg.q11),
@@ -437,6 +445,32 @@ extern "C" int pfgpu_fs_last_neff(pfgpu_fs* h, double* neff) {
     PF_CUDA(cudaSetDevice(h->ctx.device));
     PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
     *neff = h->h_rec->neff;
+    return 0;
+}
+// get_observations fs1.rs:277-299 on the device: out (capacity n_landmarks) receives the observed (d, angle, lm_id) tuples
+extern "C" int pfgpu_fs_get_observations(pfgpu_fs* h, const double x_true[3], const double* landmarks_xy, size_t n_landmarks, uint32_t call,
+                                         pfgpu_fs_obs* out, size_t* k) {
+    if (!h || !x_true || (n_landmarks && (!landmarks_xy || !out)) || !k) return PFGPU_ERR_INVALID;
+    PF_CUDA(cudaSetDevice(h->ctx.device));
+    *k = 0;
+    if (!n_landmarks) return 0;
+    const size_t bytes_xy = n_landmarks * 2 * sizeof(double), bytes_out = n_landmarks * sizeof(Fs3Obs);
+    int rc = fs_stage(h, bytes_xy + bytes_out + 256);
+    if (rc) return rc;
+    char* base = reinterpret_cast<char*>(h->stage);
+    double* dxy = reinterpret_cast<double*>(base);
+    Fs3Obs* dob = reinterpret_cast<Fs3Obs*>(base + ((bytes_xy + 15) & ~(size_t)15));
+    unsigned* dk = reinterpret_cast<unsigned*>(base + ((bytes_xy + 15) & ~(size_t)15) + bytes_out);
+    PF_CUDA(cudaMemcpyAsync(dxy, landmarks_xy, bytes_xy, cudaMemcpyHostToDevice, h->ctx.stream));
+    PF_LAUNCH(h->ctx, fs3_get_observations_kernel, 1, 1024, 0, x_true[0], x_true[1], x_true[2], dxy, (unsigned)n_landmarks, h->cfg.max_range,
+              sqrt(h->cfg.r00), sqrt(h->cfg.r11), h->seed, call, dob, dk);
+    std::vector<Fs3Obs> tmp(n_landmarks);
+    unsigned kk = 0;
+    PF_CUDA(cudaMemcpyAsync(&kk, dk, sizeof(unsigned), cudaMemcpyDeviceToHost, h->ctx.stream));
+    PF_CUDA(cudaMemcpyAsync(tmp.data(), dob, bytes_out, cudaMemcpyDeviceToHost, h->ctx.stream));
+    PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+    for (unsigned j = 0; j < kk; ++j) { out[j].d = tmp[j].d; out[j].angle = tmp[j].angle; out[j].lm_id = (uint64_t)tmp[j].lm_id; }
+    *k = kk;
     return 0;
 }
 extern "C" int pfgpu_fs_last_gate(pfgpu_fs* h, int* did) {

@@ -3,7 +3,6 @@ import os
 import sys
 
 import numpy as np
-import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -14,7 +13,7 @@ from rust_robotics_b200 import dist as rdist, scenarios  # noqa: E402
 import _oracle  # noqa: E402
 
 
-def run_pf(kind, rank, world, local, n_global, steps, uid):
+def run_pf(grp, kind, rank, world, local, n_global, steps, uid):
     """sharded ParticleFilterLocalizer / MonteCarloLocalizer vs the full-size oracle"""
     mcl = kind == "mcl"
     sc = scenarios.PfScenario("c2" if mcl else "c1", steps=steps)
@@ -42,12 +41,12 @@ def run_pf(kind, rank, world, local, n_global, steps, uid):
             assert np.array_equal(g.last_indices(), o.last_indices()[lo:hi]), f"rank {rank} step {t}: indices"
     assert np.array_equal(g.get_particles(), o.particles()[lo:hi]), f"rank {rank}: particles differ"
     assert resamples > 0
-    dist.barrier()
+    grp.barrier()
     if rank == 0:
         print(f"MGPU_OK kind={kind} world={world} n={n_global} resamples={resamples}")
 
 
-def run_edge(rank, world, local, uid):
+def run_edge(grp, rank, world, local, uid):
     """The single-GPU edge cases of tests/test_gpu_parity.py::test_fastslam_edge_cases, sharded."""
     n, m = 1024 * world, 4
     lm_xy = np.array([[5.0, 0.0], [0.0, 5.0], [5.0, 5.0], [-5.0, 2.0]])
@@ -58,7 +57,9 @@ def run_edge(rank, world, local, uid):
     lo, hi = rdist.shard_bounds(n, rank, world)
 
     def same(tag):
+        grp.barrier()                         # nobody steps on while a peer still reads through remote references
         gp, gl = g.state(); op, ol = o.state()
+        grp.barrier()
         assert np.array_equal(gp, op[lo:hi]), f"rank {rank} {tag}: pose/weights differ"
         assert np.array_equal(gl, ol[lo:hi]), f"rank {rank} {tag}: landmarks differ"
 
@@ -75,22 +76,22 @@ def run_edge(rank, world, local, uid):
     for _ in range(6):
         assert g.fastslam_update([1.0, 0.0], z2) == bool(o.step([1.0, 0.0], z2))
     same("mixed fresh")
-    dist.barrier()
+    grp.barrier()
     if rank == 0:
         print(f"MGPU_OK edge world={world} mode={g.shard_mode()}")
 
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    dist.init_process_group("gloo", init_method="env://")
-    uid = rdist.broadcast_unique_id(dist, rdist.nccl_unique_id, rank)
+    grp = rdist.TcpGroup()
+    uid = rdist.broadcast_unique_id(grp, rdist.nccl_unique_id)
     if sys.argv[1] == "edge":
-        run_edge(rank, world, local, uid)
-        dist.destroy_process_group()
+        run_edge(grp, rank, world, local, uid)
+        grp.close()
         return
     if sys.argv[1] in ("pf", "mcl"):
-        run_pf(sys.argv[1], rank, world, local, int(sys.argv[2]), int(sys.argv[3]), uid)
-        dist.destroy_process_group()
+        run_pf(grp, sys.argv[1], rank, world, local, int(sys.argv[2]), int(sys.argv[3]), uid)
+        grp.close()
         return
     n_global, side, steps = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
     sc = scenarios.FastSlamScenario(side, (10.0 * side / 2 - 5.0, 10.0 * side / 2 - 5.0, 0.0), (1.0, 0.025), steps)
@@ -111,17 +112,17 @@ def main():
             assert np.array_equal(g.last_indices(), o.last_indices()[lo:hi]), f"rank {rank} step {t}: indices"
         bi, bp = g.get_best_particle()
         assert bi == o.best(), f"rank {rank} step {t}: best {bi} vs {o.best()}"
+    grp.barrier()
     gp, gl = g.state()
     op, ol = o.state()
     assert np.array_equal(gp, op[lo:hi]), f"rank {rank}: pose/weights differ"
     assert np.array_equal(gl, ol[lo:hi]), f"rank {rank}: landmarks differ"
     assert resamples > 0
-    dist.barrier()
+    grp.barrier()
     if rank == 0:
         st = g.stats()
-        print(f"MGPU_OK world={world} n={n_global} resamples={resamples} mode={g.shard_mode()} imported={st.imported_particles} "
-              f"compactions={st.compactions} serial_fallbacks={st.serial_fallbacks}")
-    dist.destroy_process_group()
+        print(f"MGPU_OK world={world} n={n_global} resamples={resamples} mode={g.shard_mode()} serial_fallbacks={st.serial_fallbacks}")
+    grp.close()
 
 
 if __name__ == "__main__":

@@ -1,5 +1,6 @@
-"""world_size-2 gloo tests (CPU) of the host-side multi-process plumbing: shard bounds, unique-id broadcast,
-max-over-ranks timing reduction, and bench.py's reference arm under torchrun (rank 0 prints, the others exit 0)."""
+"""world_size-2 tests (CPU) of the host-side multi-process plumbing, launched the way the driver launches bench.py
+(torchrun sets RANK / WORLD_SIZE / MASTER_*): shard bounds, unique-id broadcast, barrier, max over ranks through the
+torch-free TCP control plane (rust_robotics_b200/dist.py), and bench.py's reference arm (rank 0 prints, the others exit 0)."""
 import json
 import os
 import subprocess
@@ -10,19 +11,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WORKER = r'''
 import os, sys
 sys.path.insert(0, sys.argv[1])
-import torch.distributed as dist
 from rust_robotics_b200 import dist as rdist
-rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-dist.init_process_group("gloo", init_method="env://")
-uid = rdist.broadcast_unique_id(dist, lambda: bytes(range(128)), rank)
+grp = rdist.TcpGroup()
+rank, world = grp.rank, grp.world
+assert world == 2
+uid = rdist.broadcast_unique_id(grp, lambda: bytes(range(128)))
 assert uid == bytes(range(128)), uid
 lo, hi = rdist.shard_bounds(1 << 16, rank, world)
 assert hi - lo == (1 << 16) // world and lo == rank * ((1 << 16) // world)
-m = rdist.max_over_ranks(dist, 1.0 + rank)
+m = grp.max(1.0 + rank)
 assert m == float(world), m
-dist.barrier()
+for _ in range(3): grp.barrier()
 if rank == 0: print("DIST_OK")
-dist.destroy_process_group()
+grp.close()
 '''
 
 
@@ -32,7 +33,7 @@ def _torchrun(args, port):
     return subprocess.run(cmd, capture_output=True, text=True, timeout=600)
 
 
-def test_gloo_world2_plumbing(tmp_path):
+def test_world2_plumbing(tmp_path):
     w = tmp_path / "worker.py"
     w.write_text(WORKER)
     r = _torchrun([str(w), ROOT], 29533)

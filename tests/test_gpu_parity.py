@@ -503,3 +503,17 @@ def test_fastslam_sharded_in_process_edge_cases(oracle):
     for _ in range(6):
         assert rr.FastSlam1.step_all(ranks, [1.0, 0.0], z2) == bool(o.step([1.0, 0.0], z2))
     _shard_compare(ranks, o, "mixed fresh")
+
+
+def test_fastslam_get_observations_on_device(oracle):
+    """get_observations (fs1.rs:277-299) behind the ABI == the oracle's, bit for bit (same Philox stream), incl. the reference's own
+    test geometry (fs1.rs:325-341: one landmark in range, one outside)"""
+    g = rr.FastSlam1(64, 4, seed=42)
+    o = OracleFS(oracle, 64, 4, seed=42)
+    z = g.get_observations([0.0, 0.0, 0.0], [(5.0, 0.0), (100.0, 100.0)], 0)
+    assert len(z) == 1 and z[0][2] == 0 and abs(z[0][0] - 5.0) < 5.0
+    rng = np.random.default_rng(1)
+    for call in range(6):
+        lms = rng.uniform(-40, 40, size=(1500, 2))
+        xt = [rng.uniform(-5, 5), rng.uniform(-5, 5), rng.uniform(-3, 3)]
+        assert g.get_observations(xt, lms, call) == o.observations(xt, lms, 42, call)

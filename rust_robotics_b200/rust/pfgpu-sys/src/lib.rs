@@ -71,6 +71,10 @@ extern "C" {
     pub fn pfgpu_fs_download(h: *mut pfgpu_fs, pose_w: *mut f64, lm: *mut f64, n: usize) -> c_int;
     pub fn pfgpu_fs_step(h: *mut pfgpu_fs, u: *const f64, z: *const pfgpu_fs_obs, k: usize, did_resample: *mut c_int) -> c_int;
     pub fn pfgpu_fs_best(h: *mut pfgpu_fs, index_global: *mut usize, pose_w4: *mut f64) -> c_int;
+    pub fn pfgpu_fs_get_observations(h: *mut pfgpu_fs, x_true: *const f64, landmarks_xy: *const f64, n_landmarks: usize, call: u32,
+                                     out: *mut pfgpu_fs_obs, k: *mut usize) -> c_int;
+    pub fn pfgpu_fs_last_gate(h: *mut pfgpu_fs, did_resample: *mut c_int) -> c_int;
+    pub fn pfgpu_fs_last_neff(h: *mut pfgpu_fs, neff: *mut f64) -> c_int;
     pub fn pfgpu_fs_particle_landmarks(h: *mut pfgpu_fs, index_local: usize, lm6: *mut f64) -> c_int;
     pub fn pfgpu_fs_count(h: *mut pfgpu_fs, n_local: *mut usize, n_global: *mut usize, n_landmarks: *mut usize) -> c_int;
     pub fn pfgpu_fs_sync(h: *mut pfgpu_fs) -> c_int;
@@ -82,6 +86,9 @@ extern "C" {
     pub fn pfgpu_fs_create_sharded(cfg: *const pfgpu_fs_config, n_particles_global: usize, n_landmarks: usize, seed: u64,
                                    device: c_int, nccl_unique_id: *const c_void, rank: c_int, world: c_int,
                                    out: *mut *mut pfgpu_fs) -> c_int;
-    /// 0 = one GPU, 1 = sharded over NCCL collectives, 2 = sharded over peer memory (NVLink)
+    /// all ranks inside one process (devices may repeat)
+    pub fn pfgpu_fs_create_sharded_local(cfg: *const pfgpu_fs_config, n_particles_global: usize, n_landmarks: usize, seed: u64,
+                                         devices: *const c_int, world: c_int, out: *mut *mut pfgpu_fs) -> c_int;
+    /// 0 = one GPU, 2 = sharded over peer memory (NVLink)
     pub fn pfgpu_fs_shard_mode(h: *mut pfgpu_fs, mode: *mut c_int) -> c_int;
 }

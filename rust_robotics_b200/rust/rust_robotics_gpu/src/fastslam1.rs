@@ -9,17 +9,33 @@ pub struct Landmark { pub x: f64, pub y: f64, pub cov: Matrix2<f64> }           
 #[derive(Clone)]
 pub struct Particle { pub weight: f64, pub x: f64, pub y: f64, pub yaw: f64, pub landmarks: Vec<Landmark> }   // fs1.rs:45-51
 
-pub struct FastSlam { h: *mut sys::pfgpu_fs, n: usize, m: usize }
+pub struct FastSlam { h: *mut sys::pfgpu_fs, n: usize, m: usize, calls: u32 }
 unsafe impl Send for FastSlam {}
 
-/// create_particles fs1.rs:302-306
+/// create_particles fs1.rs:302-306.  NOTE for call sites: the reference returns `Vec<Particle>` and its free functions take
+/// `&mut Vec<Particle>`; here the same function names take / return the engine handle `FastSlam` (the
+/// alternative, upload + download around every call, is PCIe-bound).  Code that indexes the Vec calls `.download()`.
 pub fn create_particles(n_particles: usize, n_landmarks: usize) -> FastSlam {
+    let t = std::time::SystemTime::now().duration_since(std::time::UNIX_EPOCH).map(|d| d.as_nanos() as u64).unwrap_or(0);
+    create_particles_seeded(n_particles, n_landmarks, t.wrapping_mul(0x9E37_79B9_7F4A_7C15), 0)   // the reference is unseeded (fs1.rs:129,220)
+}
+pub fn create_particles_seeded(n_particles: usize, n_landmarks: usize, seed: u64, device: i32) -> FastSlam {
     let mut cfg = std::mem::MaybeUninit::<sys::pfgpu_fs_config>::uninit();
     unsafe { sys::pfgpu_fs_default_config(cfg.as_mut_ptr()) };
     let mut h = std::ptr::null_mut();
-    let rc = unsafe { sys::pfgpu_fs_create(cfg.as_ptr(), n_particles, n_landmarks, 42, 0, &mut h) };
+    let rc = unsafe { sys::pfgpu_fs_create(cfg.as_ptr(), n_particles, n_landmarks, seed, device, &mut h) };
     assert_eq!(rc, 0, "pfgpu_fs_create failed");
-    FastSlam { h, n: n_particles, m: n_landmarks }
+    FastSlam { h, n: n_particles, m: n_landmarks, calls: 0 }
+}
+/// get_observations fs1.rs:277-299 on the device (Philox stream OBS; the reference draws from rand::rng())
+pub fn get_observations(particles: &mut FastSlam, x_true: &nalgebra::Vector3<f64>, landmarks: &[(f64, f64)]) -> Vec<(f64, f64, usize)> {
+    let flat: Vec<f64> = landmarks.iter().flat_map(|&(x, y)| [x, y]).collect();
+    let mut out = vec![sys::pfgpu_fs_obs { d: 0.0, angle: 0.0, lm_id: 0 }; landmarks.len().max(1)];
+    let mut k = 0usize;
+    let rc = unsafe { sys::pfgpu_fs_get_observations(particles.h, x_true.as_ptr(), flat.as_ptr(), landmarks.len(), particles.calls, out.as_mut_ptr(), &mut k) };
+    assert_eq!(rc, 0, "pfgpu_fs_get_observations failed");
+    particles.calls += 1;
+    out[..k].iter().map(|o| (o.d, o.angle, o.lm_id as usize)).collect()
 }
 /// fastslam_update fs1.rs:237-266
 pub fn fastslam_update(particles: &mut FastSlam, u: Vector2<f64>, z: &[(f64, f64, usize)]) {

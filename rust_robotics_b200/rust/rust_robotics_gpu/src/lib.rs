@@ -3,7 +3,9 @@
 //! Same type and method names as the reference (crates/rust_robotics_localization/src/particle_filter.rs,
 //! crates/rust_robotics_slam/src/fastslam1.rs); every method body is ONE call into libpfgpu.so.  A downstream crate
 //! switches by changing `use rust_robotics_localization::ParticleFilterLocalizer` to
-//! `use rust_robotics_gpu::ParticleFilterLocalizer`.  NOT COMPILED HERE (no Rust toolchain in the build image).
+//! `use rust_robotics_gpu::ParticleFilterLocalizer`.  Build: `cargo build -p rust_robotics_gpu` with libpfgpu.so built in-tree
+//! (pfgpu-sys/build.rs finds it; PFGPU_LIB_DIR overrides).  NOT COMPILED IN THIS REPOSITORY (no Rust toolchain in the build image):
+//! the identical C ABI is exercised by the C++ mirror (host/, run by tests) and the Python mirror (api.py).
 pub mod fastslam1;
 pub mod monte_carlo_localization;
 pub mod particle_filter;

@@ -44,8 +44,14 @@ unsafe impl Send for MonteCarloLocalizer {}
 
 impl MonteCarloLocalizer {
     pub fn try_new(config: MonteCarloLocalizationConfig) -> RoboticsResult<Self> {                  // mcl.rs:150-164
+        // the reference draws from rand::rng() (mcl.rs:187,216,338): entropy, not a constant, so that independent localizers
+        // (Monte-Carlo trials) are not correlated; try_new_seeded pins the Philox seed for tests
+        let t = std::time::SystemTime::now().duration_since(std::time::UNIX_EPOCH).map(|d| d.as_nanos() as u64).unwrap_or(0);
+        Self::try_new_seeded(config, t.wrapping_mul(0x9E37_79B9_7F4A_7C15), 0)
+    }
+    pub fn try_new_seeded(config: MonteCarloLocalizationConfig, seed: u64, device: i32) -> RoboticsResult<Self> {
         let mut h = std::ptr::null_mut();
-        status(unsafe { sys::pfgpu_pf_create(&config.to_c(), 42, 0, &mut h) })?;
+        status(unsafe { sys::pfgpu_pf_create(&config.to_c(), seed, device, &mut h) })?;
         let mut s = Self { h, state_estimate: PFState::zeros(), covariance_dyn: DMatrix::zeros(4, 4), particles: vec![], dirty: true };
         s.refresh_cache()?;
         Ok(s)

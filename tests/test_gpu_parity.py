@@ -517,3 +517,28 @@ def test_fastslam_get_observations_on_device(oracle):
         lms = rng.uniform(-40, 40, size=(1500, 2))
         xt = [rng.uniform(-5, 5), rng.uniform(-5, 5), rng.uniform(-3, 3)]
         assert g.get_observations(xt, lms, call) == o.observations(xt, lms, 42, call)
+
+
+def test_cpp_mirror_runs(tmp_path):
+    """the C++ host mirror (rust_robotics_b200/host/*.hpp, what a C++ caller of the reference's API would use) driving the
+    C ABI: same seeds and inputs as the Python mirror -> identical numbers"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "mirror_run")
+    pkg = os.path.join(root, "rust_robotics_b200")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-DMIRROR_MAIN", os.path.join(pkg, "host", "mirror_check.cpp"), "-I", os.path.join(root, "include"),
+                    "-I", os.path.join(pkg, "host"), "-L", pkg, "-lpfgpu", f"-Wl,-rpath,{pkg}", "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = [float(x) for x in r.stdout.split()]
+    pf = rr.ParticleFilterLocalizer.try_with_initial_state([5.0, 5.0, 0.0, 0.0], rr.ParticleFilterConfig(1000, 0.5, 0.25), seed=42)
+    z = [(3.1, 2.0, 2.0), (5.0, 10.0, 2.0)]
+    e1 = pf.try_step([1.1, 0.0], z)
+    pf.try_predict_with_control([0.5, 0.63]); pf.try_update_with_observations(z); pf.resample()
+    e2 = pf.estimate()
+    fs = rr.FastSlam1(256, 4, seed=42)
+    did = fs.fastslam_update([1.0, 0.1], [(5.0, 0.1, 0), (7.0, -0.4, 2)])
+    bi, bp = fs.get_best_particle()
+    lm = fs.particle_landmarks(bi)
+    want = [e1[0], e1[1], e2[0], e2[3], 1000.0, bp[0], lm[0, 0] + lm[2, 1], 1.0 if did else 0.0]
+    assert got == [float(w) for w in want], (got, want)

@@ -65,6 +65,7 @@ struct Fs3Rec {                   // mapped pinned host memory: what a caller re
     int gate, err;
 };
 
+struct Fs3Res { double total; unsigned long long Ptot; int D; int fail; };
 struct Fs3Dev {
     unsigned n, n_glob, off, m, ld;           // local / global particles, first global slot, landmarks, column stride
     int G, rank;
@@ -87,6 +88,10 @@ struct Fs3Dev {
     unsigned* entCnt;                                          // [FS3_SLOTS] dirty values appended so far (any order)
     unsigned* entKey; unsigned* entTile; unsigned long long* entP; double* entV; int* entL;   // [FS3_SLOTS][FS3_ENT_CAP]
     unsigned* bar;                                             // [8] grid-barrier arrival counters of the running post kernel
+    unsigned* resflag;                                         // [8] "the chain of this round is evaluated" flags
+    Fs3Res* res;                                               // [8] its results: total, entry count, failure
+    unsigned long long* resTP; unsigned* resKey; unsigned long long* resP; double* resAft;   // [8][tiles] / [8][FS3_ENT_CAP] for the scans
+    double* tileEnd;                                           // [FS3_MAX_TILES] last CDF value of every tile (coarse level of the index search)
     unsigned short* rowlist; int* rowinfo;                     // live ancestry rows ([m]), [0] their count, [1] new row id or -1
     double* tileBw; unsigned* tileBi;         // [FS3_MAX_TILES] best (weight, global slot) per tile
     int* flagsg;                              // [FS3_SLOTS] "bad value seen" per sum (reset by the post kernel's last CTA)
@@ -321,9 +326,15 @@ fs3_ekf_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsP
         double lik[2] = { 1.0, 1.0 };
         int ok[2];
         fs_update_landmark_fastw<2>(L, px, py, pyaw, ob.d, ob.angle, r00, r11, lik, ok);
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-            if (!ok[q] && i0 + q < d.n) lik[q] = fs3_update_slow(&L[q], px[q], py[q], pyaw[q], ob.d, ob.angle, r00, r11);
+        if (!(ok[0] & ok[1])) {          // rare: a pair outside the fast form's domain -> the contract form, on a COPY (taking the address
+#pragma unroll                           // of L itself would park all twelve landmark doubles in local memory on every trip)
+            for (int q = 0; q < 2; ++q)
+                if (!ok[q] && i0 + q < d.n) {
+                    FsLm T = q ? L[1] : L[0];
+                    const double lk = fs3_update_slow(&T, q ? px[1] : px[0], q ? py[1] : py[0], q ? pyaw[1] : pyaw[0], ob.d, ob.angle, r00, r11);
+                    if (q) { L[1] = T; lik[1] = lk; } else { L[0] = T; lik[0] = lk; }
+                }
+        }
         double* o = lm_dst + i0;
         *reinterpret_cast<double2*>(o) = make_double2(L[0].x, L[1].x);
         *reinterpret_cast<double2*>(o + ld) = make_double2(L[0].y, L[1].y);
@@ -382,6 +393,8 @@ struct Fs3Sh {
     double total, tbase, bcast;
     unsigned long long Ptot;
     int D, fail, last;
+    unsigned jr[2];
+    double tend[FS3_MAX_TILES];                               // last CDF value of every tile
     x3_comb_table comb;
 };
 
@@ -483,6 +496,7 @@ __device__ __noinline__ void fs3_serial_walk(const Fs3Dev& d, Fs3Sh<NT>& sh, uns
             double c = sh.tbase;
 #pragma unroll 1
             for (size_t i = lo; i < lo + T && i < d.n_glob; ++i) { c = c + fs3_value(d, slot, i, par, S2, r0, inv); out[i] = c; }
+            if (slot == 3) d.tileEnd[blockIdx.x] = c;
         }
     }
     __syncthreads();
@@ -543,64 +557,153 @@ __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const do
     if (tid == 0) { d.tileP[(size_t)slot * FS3_MAX_TILES + b] = Ptile; if (slot == 0) d.tileQ[b] = extraQ; }
     FS3_TRACE(tb0);
     __syncthreads();
-    // ---- grid barrier + chain: warp 0 only; the other warps wait at the block barrier below ----
+    // ---- grid barrier + chain.  The LAST CTA to arrive evaluates the chain (every aggregate is published by then and it reads
+    // them uncontended: 128 CTAs fetching the same few sectors at once serialise in L2) and publishes the results; the others
+    // wait for its flag.  Warp 0 only; the other warps wait at the block barrier below. ----
     if (tid < 32) {
-        if (tid == 0) { fs3_bar_arrive(d, round); fs3_bar_wait(d, round, nt); }
-        __syncwarp();
-        FS3_TRACE(tb0 + 1);
-        // clean-increment sum in front of every tile (lane owns `per` consecutive tiles)
-        const unsigned per = (nt + 31u) / 32u, t0 = (unsigned)lane * per;
-        unsigned long long lsum = 0;
+        int leader = 0;
+        if (tid == 0) { __threadfence(); leader = (atomicAdd(d.bar + round, 1u) + 1u == nt) ? 1 : 0; if (leader) __threadfence(); }
+        leader = __shfl_sync(0xffffffffu, leader, 0);
+        Fs3Res* res = d.res + round;
+        const size_t rb = (size_t)round * FS3_ENT_CAP, rt = (size_t)round * FS3_MAX_TILES;
+        if (leader) {
+            FS3_TRACE(tb0 + 1);
+            // ONE round trip: every load the chain needs is issued before the first use (tile sums, entry count, and — speculatively,
+            // their count is not known yet — the first 32 appended entries)
+            const size_t eb = (size_t)slot * FS3_ENT_CAP;
+            unsigned long long tp[(FS3_MAX_TILES + 31) / 32];
+#pragma unroll
+            for (unsigned i = 0; i < (FS3_MAX_TILES + 31) / 32; ++i) tp[i] = (i * 32u + lane) < nt ? __ldcg(d.tileP + (size_t)slot * FS3_MAX_TILES + i * 32u + lane) : 0ull;
+            const unsigned cnt = __ldcg(d.entCnt + slot);
+            int fail = __ldcg(d.flagsg + slot);
+            unsigned ekey = __ldcg(d.entKey + eb + lane), etile = __ldcg(d.entTile + eb + lane);
+            unsigned long long eP = __ldcg(d.entP + eb + lane);
+            double eV = __ldcg(d.entV + eb + lane);
+            int eL = __ldcg(d.entL + eb + lane);
+            fail |= cnt > FS3_ENT_CAP ? 1 : 0;
+#pragma unroll
+            for (unsigned i = 0; i < (FS3_MAX_TILES + 31) / 32; ++i) if (i * 32u + lane < nt) sh.tPoff[i * 32u + lane] = tp[i];
+            __syncwarp();
+            // clean-increment sum in front of every tile: lane owns `per` consecutive tiles
+            const unsigned per = (nt + 31u) / 32u, t0 = (unsigned)lane * per;
+            unsigned long long lsum = 0;
 #pragma unroll 1
-        for (unsigned i = 0; i < per; ++i) if (t0 + i < nt) lsum += __ldcg(d.tileP + (size_t)slot * FS3_MAX_TILES + t0 + i);
-        const unsigned cnt = __ldcg(d.entCnt + slot);
-        int fail = __ldcg(d.flagsg + slot) | (cnt > FS3_ENT_CAP ? 1 : 0);
-        unsigned long long inc = lsum;
+            for (unsigned i = 0; i < per; ++i) if (t0 + i < nt) lsum += sh.tPoff[t0 + i];
+            unsigned long long inc = lsum;
 #pragma unroll 1
-        for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
-        const unsigned long long Ptot = __shfl_sync(0xffffffffu, inc, 31);
-        unsigned long long run = inc - lsum;
+            for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+            const unsigned long long Ptot = __shfl_sync(0xffffffffu, inc, 31);
+            unsigned long long run = inc - lsum;
 #pragma unroll 1
-        for (unsigned i = 0; i < per; ++i) if (t0 + i < nt) { sh.tPoff[t0 + i] = run; run += __ldcg(d.tileP + (size_t)slot * FS3_MAX_TILES + t0 + i); }
-        const int D = fail ? 0 : (int)cnt;
-        const size_t eb = (size_t)slot * FS3_ENT_CAP;
+            for (unsigned i = 0; i < per; ++i) if (t0 + i < nt) { const unsigned long long x = sh.tPoff[t0 + i]; sh.tPoff[t0 + i] = run; run += x; }
+            __syncwarp();
+            const int D = fail ? 0 : (int)cnt;
+            double total = 0.0;
+            if (D <= 32) {
+                // ---- the usual case, in registers: lane e holds entry e; rank by index, then every lane walks the chain with the
+                // operands shuffled in (two dependent operations per entry, no shared-memory latency inside the chain) ----
+                const bool have = lane < D;
+                if (!have) ekey = 0xFFFFFFFFu;
+                const unsigned long long Pg = have ? sh.tPoff[etile < nt ? etile : 0] + eP : 0ull;
+                int rank = 0;
+#pragma unroll 4
+                for (int j = 0; j < 32; ++j) rank += __shfl_sync(0xffffffffu, ekey, j) < ekey ? 1 : 0;
+                // move every entry to the lane of its rank (through shared memory: one conflict-free round)
+                if (have) { sh.skey[rank] = ekey; sh.sP[rank] = Pg; sh.sV[rank] = eV; sh.sL[rank] = eL; }
+                __syncwarp();
+                const unsigned long long myP = have ? sh.sP[lane] : 0ull;
+                const double myV = have ? sh.sV[lane] : 0.0;
+                double sacc = 0.0, mybef = 0.0, myaft = 0.0; unsigned long long prev = 0;
+#pragma unroll 4
+                for (int o = 0; o < 32; ++o) {
+                    const unsigned long long p = __shfl_sync(0xffffffffu, myP, o);
+                    const double v = __shfl_sync(0xffffffffu, myV, o);
+                    if (o < D) {
+                        const double bf = sacc;
+                        sacc = pfc_u2d(pfc_d2u(sacc) + (p - prev)) + v;
+                        prev = p;
+                        if (o == lane) { mybef = bf; myaft = sacc; }
+                    }
+                }
+                int ok = 1;
+                total = x3_apply(sacc, Ptot - prev, -1, &ok);
+                const unsigned long long pprev = __shfl_up_sync(0xffffffffu, myP, 1);
+                if (have) {
+                    (void)x3_apply(mybef, myP - (lane ? pprev : 0ull), sh.sL[lane], &ok);      // certificate of the clean run in front of me
+                    sh.bef[lane] = mybef; sh.aft[lane] = myaft;
+                }
+                if (!ok) fail = 1;
+            } else {
 #pragma unroll 1
-        for (int e = lane; e < D; e += 32) sh.ukey[e] = __ldcg(d.entKey + eb + e);
-        __syncwarp();
+                for (int e = lane; e < D; e += 32) sh.ukey[e] = __ldcg(d.entKey + eb + e);
+                __syncwarp();
 #pragma unroll 1
-        for (int e = lane; e < D; e += 32) {                   // rank = position in index order (keys are distinct)
-            const unsigned key = sh.ukey[e];
-            int rank = 0;
+                for (int e = lane; e < D; e += 32) {               // rank = position in index order (keys are distinct)
+                    const unsigned key = sh.ukey[e];
+                    int rank = 0;
 #pragma unroll 1
-            for (int j = 0; j < D; ++j) rank += sh.ukey[j] < key ? 1 : 0;
-            sh.skey[rank] = key; sh.sP[rank] = sh.tPoff[__ldcg(d.entTile + eb + e)] + __ldcg(d.entP + eb + e);
-            sh.sV[rank] = __ldcg(d.entV + eb + e); sh.sL[rank] = __ldcg(d.entL + eb + e);
-        }
-        __syncwarp();
-        double total = 0.0;
-        if (lane == 0) {                                       // the serial part: one integer add + one FP add per dirty value
-            double s = 0.0; unsigned long long prev = 0;
+                    for (int j = 0; j < D; ++j) rank += sh.ukey[j] < key ? 1 : 0;
+                    sh.skey[rank] = key; sh.sP[rank] = sh.tPoff[__ldcg(d.entTile + eb + e)] + __ldcg(d.entP + eb + e);
+                    sh.sV[rank] = __ldcg(d.entV + eb + e); sh.sL[rank] = __ldcg(d.entL + eb + e);
+                }
+                __syncwarp();
+                if (lane == 0) {                                   // the serial part: one integer add + one FP add per dirty value
+                    double sq = 0.0; unsigned long long prev = 0;
 #pragma unroll 1
-            for (int o = 0; o < D; ++o) {
-                const unsigned long long p = sh.sP[o];
-                sh.bef[o] = s;
-                s = pfc_u2d(pfc_d2u(s) + (p - prev)) + sh.sV[o];
-                sh.aft[o] = s; prev = p;
+                    for (int o = 0; o < D; ++o) {
+                        const unsigned long long p = sh.sP[o];
+                        sh.bef[o] = sq;
+                        sq = pfc_u2d(pfc_d2u(sq) + (p - prev)) + sh.sV[o];
+                        sh.aft[o] = sq; prev = p;
+                    }
+                    int ok = 1;
+                    total = x3_apply(sq, Ptot - prev, -1, &ok);
+                    if (!ok) fail = 1;
+                }
+                __syncwarp();
+#pragma unroll 1
+                for (int o = lane; o < D; o += 32) {               // certificates of the clean runs, in parallel
+                    const unsigned long long dp = sh.sP[o] - (o ? sh.sP[o - 1] : 0ull);
+                    int ok = 1;
+                    (void)x3_apply(sh.bef[o], dp, sh.sL[o], &ok);
+                    if (!ok) fail = 1;
+                }
             }
-            int ok = 1;
-            total = x3_apply(s, Ptot - prev, -1, &ok);
-            if (!ok) fail = 1;
-        }
-        __syncwarp();
+            __syncwarp();
+            fail = __any_sync(0xffffffffu, fail);
+            total = __shfl_sync(0xffffffffu, total, 0);
+            // publish: what the other CTAs need to finish on their own
+            if (out && !fail) {
 #pragma unroll 1
-        for (int o = lane; o < D; o += 32) {                   // certificates of the clean runs, in parallel
-            const unsigned long long dp = sh.sP[o] - (o ? sh.sP[o - 1] : 0ull);
-            int ok = 1;
-            (void)x3_apply(sh.bef[o], dp, sh.sL[o], &ok);
-            if (!ok) fail = 1;
+                for (unsigned t = lane; t < nt; t += 32) d.resTP[rt + t] = sh.tPoff[t];
+#pragma unroll 1
+                for (int o = lane; o < D; o += 32) { d.resKey[rb + o] = sh.skey[o]; d.resP[rb + o] = sh.sP[o]; d.resAft[rb + o] = sh.aft[o]; }
+            }
+            if (lane == 0) {
+                res->total = total; res->Ptot = Ptot; res->D = D; res->fail = fail;
+                sh.total = total; sh.Ptot = Ptot; sh.D = D; sh.fail = fail;
+                d.st->dirty_last = (int)cnt;
+            }
+            __syncwarp();
+            __threadfence();
+            if (lane == 0) atomicExch(d.resflag + round, 1u);
+        } else {
+            if (lane == 0) {
+                unsigned spins = 0;
+                while (*reinterpret_cast<volatile unsigned*>(d.resflag + round) == 0u) { if (++spins > FS3_SPIN_LIMIT) { d.st->err = 1; break; } __nanosleep(20); }
+                __threadfence();
+            }
+            __syncwarp();
+            FS3_TRACE(tb0 + 1);
+            const double total = __ldcg(&res->total);
+            const int D = __ldcg(&res->D), fail = __ldcg(&res->fail);
+            if (out && !fail) {                                   // the sorted dirty entries + my tile's increment prefix, for the emission
+                if (lane == 0) sh.tPoff[b] = __ldcg(d.resTP + rt + b);
+#pragma unroll 1
+                for (int o = lane; o < D; o += 32) { sh.skey[o] = __ldcg(d.resKey + rb + o); sh.sP[o] = __ldcg(d.resP + rb + o); sh.aft[o] = __ldcg(d.resAft + rb + o); }
+            }
+            if (lane == 0) { sh.total = total; sh.D = D; sh.fail = fail; }
         }
-        fail = __any_sync(0xffffffffu, fail);
-        if (lane == 0) { sh.total = total; sh.Ptot = Ptot; sh.D = D; sh.fail = fail; if (b == 0) d.st->dirty_last = (int)cnt; }
     }
     __syncthreads();
     FS3_TRACE(tb0 + 2);
@@ -626,6 +729,7 @@ __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const do
             if (fs3_classify(v, a, a1, m32, &inc, &lvl)) { base = sh.aft[ko]; Pb = sh.sP[ko]; ko++; c = base; }
             else { Pc += inc; c = x3_apply(base, Pc - Pb, inc ? lvl : -1, &ok); }
             if (g0 + k < d.n_glob) out[g0 + k] = c;
+            if (slot == 3 && tid == NT - 1 && k + 1 == K) d.tileEnd[b] = c;    // coarse level of the index search
             a = a1;
         }
         if (!ok) atomicAdd(&d.st->cert_fail, 1);
@@ -641,7 +745,7 @@ __device__ __forceinline__ unsigned fs3_lower_bound(const double* c, unsigned lo
     while (lo < hi) { const unsigned mid = lo + ((hi - lo) >> 1); if (__ldcg(c + mid) < r) lo = mid + 1; else hi = mid; }
     return lo;
 }
-// warp-cooperative 32-way search of one r over [0, n): returns the lower bound (all lanes)
+// warp-cooperative 32-way search of one r over c[0 .. n): returns the lower bound (all lanes)
 __device__ __forceinline__ unsigned fs3_warp_search(const double* c, unsigned n, double r) {
     const int lane = threadIdx.x & 31;
     unsigned lo = 0, hi = n;                                  // answer in [lo, hi]
@@ -658,6 +762,15 @@ __device__ __forceinline__ unsigned fs3_warp_search(const double* c, unsigned n,
     const unsigned pi = lo + (unsigned)lane;
     const bool below = pi < hi ? (__ldcg(c + pi) < r) : false;
     return lo + (unsigned)__popc(__ballot_sync(0xffffffffu, below));
+}
+// two-level lower bound of r in the whole CDF (all lanes of a warp): tile from the tiles' last values (shared memory), then inside it
+__device__ __forceinline__ unsigned fs3_cdf_search(const double* cdf, const double* tend, unsigned nt, unsigned T, unsigned ng, double r) {
+    unsigned lo = 0, hi = nt;
+#pragma unroll 1
+    while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (tend[mid] < r) lo = mid + 1; else hi = mid; }
+    if (lo >= nt) return ng;
+    const unsigned base = lo * T, len = min(T, ng - base);
+    return base + fs3_warp_search(cdf + base, len, r);
 }
 
 template <int NT>
@@ -713,12 +826,12 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
     // ---- load this tile's weights; approximate sum of everything in front of the tile from the 64-particle partials ----
     const size_t g0 = (size_t)b * T + (size_t)tid * K;
     double q = 0.0;
-#pragma unroll 1
-    for (unsigned k = 0; k < K; ++k) { const double v = g0 + k < ng ? __ldcg(d.wraw[par] + g0 + k) : 0.0; vals[k * NT + tid] = v; q += v * v; }
+#pragma unroll 4
+    for (unsigned k = 0; k < K; ++k) { const double v = g0 + k < ng ? d.wraw[par][g0 + k] : 0.0; vals[k * NT + tid] = v; q += v * v; }   // (through L1: a thread reads K consecutive doubles)
     double toff = 0.0;
     {
         const unsigned pfirst = (unsigned)(((size_t)b * T) / 64);      // partial p covers global slots [64 p, 64 p + 64)
-#pragma unroll 1
+#pragma unroll 4
         for (unsigned p = tid; p < pfirst; p += NT) toff += __ldcg(d.part[par] + p);
     }
     fs3_block_sum2<NT>(toff, q, sh.red[0], sh.red[1]);
@@ -807,38 +920,62 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
         fs3_grid_sync<NT>(d, 4, nt);                           // the whole CDF (and comb) is visible
         FS3_TRACE(5);
         // ---------------- index walk, pose clone, lazy map clone for this CTA's share of the local slots ----------------
+        // j_t = first j with c_j >= r_t, clamped to n - 1: "while r > cum_sum[j+1] && j < n-1 { j += 1 }" (fs1.rs:224-226) with r and
+        // j both non-decreasing over the slots.  The CTA's first and last slot bracket all of its answers; the bracketed piece of
+        // the CDF is staged in shared memory (it is about as long as the slot range) and every slot searches there.
         const int nrows = d.rowinfo[0], newrow = d.rowinfo[1];
         const int cur = st->cur, rcur = st->rcur;
         const unsigned per = (d.n + nt - 1) / nt;              // local slots per CTA
         const unsigned t_lo = b * per, t_hi = min(d.n, t_lo + per);
         const double* cdf = d.cum_all;
 #pragma unroll 1
-        for (unsigned tb = t_lo + (tid & ~31); tb < t_hi; tb += NT) {       // a warp takes 32 consecutive slots
-            const unsigned t = tb + (tid & 31);
-            const size_t tg = (size_t)d.off + t;
-            const bool valid = t < t_hi;
-            double r = 0.0;
-            if (valid) r = log2n >= 0 ? x3_comb_eval(&sh.comb, inv, tg) : __ldcg(d.rcomb_all + tg);
-            // the warp's first and last slot bracket every lane's answer
-            const double r_first = __shfl_sync(0xffffffffu, r, 0);
-            const double r_last = __shfl_sync(0xffffffffu, r, min(31, (int)(t_hi - 1 - tb)));
-            const unsigned jlo = fs3_warp_search(cdf, (unsigned)ng, r_first);
-            const unsigned jhi = fs3_warp_search(cdf, (unsigned)ng, r_last);
-            if (!valid) continue;
-            unsigned j = fs3_lower_bound(cdf, jlo, jhi, r);
-            if (j >= ng) j = (unsigned)ng - 1;
-            d.idx[t] = j;
-            const int jr = (int)(j / d.n); const unsigned jc = j % d.n;                 // owner rank and column of the ancestor
-            const double* sx = d.G > 1 ? reinterpret_cast<const double*>(d.peer[jr] + d.o_px[cur]) : d.px[cur];
-            const double* sy = d.G > 1 ? reinterpret_cast<const double*>(d.peer[jr] + d.o_py[cur]) : d.py[cur];
-            const double* sa = d.G > 1 ? reinterpret_cast<const double*>(d.peer[jr] + d.o_pyaw[cur]) : d.pyaw[cur];
-            d.px[cur ^ 1][t] = sx[jc]; d.py[cur ^ 1][t] = sy[jc]; d.pyaw[cur ^ 1][t] = sa[jc];     // particles[j].clone() fs1.rs:227
-            d.w[t] = inv;                                                                // fs1.rs:228
-            const unsigned* srows = d.G > 1 ? reinterpret_cast<const unsigned*>(d.peer[jr] + d.o_rows[rcur]) : d.rows[rcur];
-            unsigned* drows = d.rows[rcur ^ 1];
+        for (unsigned t = tid; t < nt; t += NT) sh.tend[t] = __ldcg(d.tileEnd + t);
+        __syncthreads();
+        if (t_lo < t_hi) {
+            if (tid < 64) {
+                const size_t te = (size_t)d.off + (tid < 32 ? t_lo : t_hi - 1);
+                const double re = log2n >= 0 ? x3_comb_eval(&sh.comb, inv, te) : __ldcg(d.rcomb_all + te);
+                const unsigned je = fs3_cdf_search(cdf, sh.tend, nt, (unsigned)T, (unsigned)ng, re);
+                if ((tid & 31) == 0) sh.jr[tid >> 5] = je;
+            }
+        }
+        __syncthreads();
+        if (t_lo < t_hi) {
+            const unsigned jlo = sh.jr[0], jhi = min(sh.jr[1], (unsigned)ng - 1u);        // answers lie in [jlo, jhi] (ng -> clamped)
+            const unsigned len = jlo <= jhi ? jhi - jlo + 1u : 0u;
+            const bool staged = len <= (unsigned)T;
+            if (staged) {
+#pragma unroll 4
+                for (unsigned i = tid; i < len; i += NT) vals[i] = __ldcg(cdf + jlo + i);
+            }
+            __syncthreads();
 #pragma unroll 1
-            for (int x = 0; x < nrows; ++x) { const size_t ro = (size_t)d.rowlist[x] * d.ld; drows[ro + t] = srows[ro + jc]; }
-            if (newrow >= 0) drows[(size_t)newrow * d.ld + t] = fs3_ref(jr, jc);
+            for (unsigned t = t_lo + tid; t < t_hi; t += NT) {
+                const size_t tg = (size_t)d.off + t;
+                const double r = log2n >= 0 ? x3_comb_eval(&sh.comb, inv, tg) : __ldcg(d.rcomb_all + tg);
+                unsigned lo = 0, hi = len;
+                if (staged) {
+#pragma unroll 1
+                    while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (vals[mid] < r) lo = mid + 1; else hi = mid; }
+                } else {
+#pragma unroll 1
+                    while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (__ldcg(cdf + jlo + mid) < r) lo = mid + 1; else hi = mid; }
+                }
+                unsigned j = jlo + lo;
+                if (j >= ng) j = (unsigned)ng - 1;
+                d.idx[t] = j;
+                const int jr = (int)(j / d.n); const unsigned jc = j % d.n;                 // owner rank and column of the ancestor
+                const double* sx = d.G > 1 ? reinterpret_cast<const double*>(d.peer[jr] + d.o_px[cur]) : d.px[cur];
+                const double* sy = d.G > 1 ? reinterpret_cast<const double*>(d.peer[jr] + d.o_py[cur]) : d.py[cur];
+                const double* sa = d.G > 1 ? reinterpret_cast<const double*>(d.peer[jr] + d.o_pyaw[cur]) : d.pyaw[cur];
+                d.px[cur ^ 1][t] = sx[jc]; d.py[cur ^ 1][t] = sy[jc]; d.pyaw[cur ^ 1][t] = sa[jc];     // particles[j].clone() fs1.rs:227
+                d.w[t] = inv;                                                                // fs1.rs:228
+                const unsigned* srows = d.G > 1 ? reinterpret_cast<const unsigned*>(d.peer[jr] + d.o_rows[rcur]) : d.rows[rcur];
+                unsigned* drows = d.rows[rcur ^ 1];
+#pragma unroll 4
+                for (int x = 0; x < nrows; ++x) { const size_t ro = (size_t)d.rowlist[x] * d.ld; drows[ro + t] = srows[ro + jc]; }
+                if (newrow >= 0) drows[(size_t)newrow * d.ld + t] = fs3_ref(jr, jc);
+            }
         }
         FS3_TRACE(6);
     }
@@ -854,7 +991,7 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
         for (unsigned l = tid; l < d.m; l += NT) { const int s = d.lmst[l]; if ((s >> 1) == 0) d.lmst[l] = (s & 1) | ((newrow + 1) << 1); }
     }
     if (tid < FS3_SLOTS) { d.flagsg[tid] = 0; d.entCnt[tid] = 0u; }
-    if (tid < 8) d.bar[tid] = 0u;
+    if (tid < 8) { d.bar[tid] = 0u; d.resflag[tid] = 0u; }
     if (tid < 32) {
         // best particle: the last maximum over the tiles (no resample) / the last slot (after a resample every weight is 1/n)
         double bw2 = -1.0; unsigned bi2 = 0;
@@ -869,7 +1006,7 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
         if (gate) {
             bi2 = (unsigned)ng - 1; bw2 = inv;
             const double rl = log2n >= 0 ? x3_comb_eval(&sh.comb, inv, ng - 1) : __ldcg(d.rcomb_all + ng - 1);
-            src = fs3_warp_search(d.cum_all, (unsigned)ng, rl);
+            src = fs3_cdf_search(d.cum_all, sh.tend, nt, (unsigned)T, (unsigned)ng, rl);
             if (src >= ng) src = (unsigned)ng - 1;
         }
         if (tid == 0) {

@@ -125,6 +125,12 @@ static int fs_create_impl(const pfgpu_fs_config* cfg, size_t n, size_t n_global,
         FS_TRY(cudaMalloc(&d.entP, nen * sizeof(unsigned long long))); FS_TRY(cudaMalloc(&d.entV, nen * sizeof(double)));
         FS_TRY(cudaMalloc(&d.entL, nen * sizeof(int)));
         FS_TRY(cudaMalloc(&d.bar, 8 * sizeof(unsigned))); FS_TRY(cudaMemset(d.bar, 0, 8 * sizeof(unsigned)));
+        FS_TRY(cudaMalloc(&d.resflag, 8 * sizeof(unsigned))); FS_TRY(cudaMemset(d.resflag, 0, 8 * sizeof(unsigned)));
+        FS_TRY(cudaMalloc(&d.res, 8 * sizeof(Fs3Res))); FS_TRY(cudaMemset(d.res, 0, 8 * sizeof(Fs3Res)));
+        FS_TRY(cudaMalloc(&d.resTP, (size_t)8 * FS3_MAX_TILES * sizeof(unsigned long long)));
+        FS_TRY(cudaMalloc(&d.resKey, (size_t)8 * FS3_ENT_CAP * sizeof(unsigned))); FS_TRY(cudaMalloc(&d.resP, (size_t)8 * FS3_ENT_CAP * sizeof(unsigned long long)));
+        FS_TRY(cudaMalloc(&d.resAft, (size_t)8 * FS3_ENT_CAP * sizeof(double)));
+        FS_TRY(cudaMalloc(&d.tileEnd, FS3_MAX_TILES * sizeof(double)));
         FS_TRY(cudaMalloc(&d.rowlist, 1024 * sizeof(unsigned short))); FS_TRY(cudaMalloc(&d.rowinfo, 2 * sizeof(int)));
         FS_TRY(cudaMemset(d.rowinfo, 0, 2 * sizeof(int)));
         FS_TRY(cudaMalloc(&d.tileBw, FS3_MAX_TILES * sizeof(double))); FS_TRY(cudaMalloc(&d.tileBi, FS3_MAX_TILES * sizeof(unsigned)));
@@ -222,7 +228,8 @@ extern "C" void pfgpu_fs_destroy(pfgpu_fs* h) {
     cudaFree(h->arena);
     cudaFree(d.st); cudaFree(d.lmst); cudaFree(d.w); cudaFree(d.wn_all); cudaFree(d.cum_all); cudaFree(d.rcomb_all); cudaFree(d.idx);
     cudaFree(d.tileP); cudaFree(d.tileQ); cudaFree(d.entCnt); cudaFree(d.entKey); cudaFree(d.entTile); cudaFree(d.entP); cudaFree(d.entV); cudaFree(d.entL);
-    cudaFree(d.bar); cudaFree(d.rowlist); cudaFree(d.rowinfo);
+    cudaFree(d.bar); cudaFree(d.rowlist); cudaFree(d.rowinfo); cudaFree(d.resflag); cudaFree(d.res); cudaFree(d.resTP); cudaFree(d.resKey);
+    cudaFree(d.resP); cudaFree(d.resAft); cudaFree(d.tileEnd);
     cudaFree(d.tileBw); cudaFree(d.tileBi); cudaFree(d.flagsg); cudaFree(d.trace); cudaFree(h->stage);
     if (h->h_rec) cudaFreeHost(h->h_rec);
     if (h->comm) ncclCommDestroy(h->comm);

@@ -1,0 +1,23 @@
+#!/bin/bash
+# usage: bash tools/gpu_mg.sh N   — multi-GPU parity tests (up to N GPUs) + bench at N ranks; logs under gpurun_out/
+N=${1:-2}
+cd $GRAFT_REPO_ROOT
+nvidia-smi -L > gpurun_out/mg${N}_gpus.txt 2>&1
+timeout 1500 python -m pytest tests/test_gpu_multi.py -x -q -m gpu > gpurun_out/mg${N}_pytest.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/mg${N}_pytest.log
+for n in 2 4 8; do
+  if [ $n -le $N ]; then
+    PFGPU_POST_TRACE=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29617 bench.py --gpus $n --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/mg${N}_bench_n$n.json 2> gpurun_out/mg${N}_bench_n$n.err
+    echo "bench n=$n rc=$?" >> gpurun_out/mg${N}_pytest.log
+  fi
+done
+timeout 600 python bench.py --gpus 1 --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/mg${N}_bench_n1.json 2> gpurun_out/mg${N}_bench_n1.err
+tail -6 gpurun_out/mg${N}_pytest.log
+for f in gpurun_out/mg${N}_bench_n*.json; do python - <<PY
+import json
+try:
+    d=json.load(open("$f")); q=d.get("c4_strong",{})
+    print("$f", "c3 %.3e %.4f ms" % (d["value"], d["ms_per_step"]), "c4 %.3e %.4f ms" % (q.get("value",0), q.get("ms_per_step",0)))
+except Exception as e: print("$f", "ERR", e)
+PY
+done

@@ -55,7 +55,8 @@ struct Fs3State {                 // device-resident; written by the last CTA of
     unsigned ekf_done, post_done; // CTA completion counters
     unsigned bar_count, bar_gen;  // grid barrier of the post kernel
     int err;                      // sticky: 1 = a barrier or a peer flag timed out
-    int serial_walks, cert_fail, dirty_last, border_cnt, pad0;
+    int serial_walks, cert_fail, dirty_last, border_cnt;
+    unsigned noise_call;          // nz[] holds the predict noise of EKF call `noise_call - 1` (0: none); written by the post kernel
     double S, Q, neff, S2, r0;
 };
 struct Fs3Rec {                   // mapped pinned host memory: what a caller reads after a step (one 64-byte record)
@@ -80,6 +81,8 @@ struct Fs3Dev {
     unsigned* rows[2];
     double* wraw[2]; double* part[2];         // own copies of wraw_all / part_all
     double* w;                                // [ld] normalised weights of the local slots (Particle::weight)
+    double* nz[2];                            // [ld] each: N(0,1) pair of every local slot for the NEXT predict (fs1.rs:129-130), precomputed
+                                              // by idle warps of the post kernel (it depends on seed, call and slot only)
     double* wn_all;                           // [n_glob] normalised weights of all slots (post-kernel scratch, fallback walks)
     double* cum_all;                          // [n_glob] exact CDF
     double* rcomb_all;                        // [n_glob] exact comb (only when n_glob is not a power of two)
@@ -136,8 +139,6 @@ __device__ __noinline__ double fs3_update_slow(FsLm* L, double px, double py, do
     int wrote;
     return fs_update_landmark(L, px, py, pyaw, z0, z1, r00, r11, &wrote);   // 1.0 whenever the weight is left alone
 }
-__device__ __forceinline__ void nb_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void nb_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void cp_async16(void* smem, const void* g) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
 }
@@ -146,8 +147,23 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* g) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-// named barriers: 4 per hand-off stage (stage = trip % number of helper warps)
-__device__ __forceinline__ int fs3_bid(int stage, int which) { return 1 + 4 * stage + which; }   // which: 0 pose full, 1 pose empty, 2 lik full, 3 lik empty
+// Hand-offs between the helper and the EKF warps: mbarriers in shared memory, 4 per stage (stage = trip % number of helper
+// warps): which = 0 pose full (1 arrival: the helper), 1 pose empty (k arrivals: one per EKF warp), 2 lik full (k), 3 lik empty (1).
+// Unlike a named barrier, waiting on a phase does not make the EKF warps wait for EACH OTHER: a warp whose pose is ready goes
+// on, so the warps drift apart and stop hitting the FP64 / XU pipes in the same phase of the computation at the same time.
+__device__ __forceinline__ void mb_init(unsigned long long* b, unsigned count) {
+    asm volatile("mbarrier.init.shared.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(unsigned long long* b) {
+    asm volatile("{ .reg .b64 t; mbarrier.arrive.shared.b64 t, [%0]; }" :: "r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
+}
+__device__ __forceinline__ void mb_wait(unsigned long long* b, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(b);
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
 __device__ __noinline__ void fs3_normal_pair(uint64_t seed, uint32_t call, uint64_t index, double* z0, double* z1) {
     pfc_normal_pair(pfc_rng_block(seed, PFC_STREAM_FS_PREDICT, call, index), z0, z1);
 }
@@ -167,8 +183,10 @@ fs3_ekf_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsP
     double* s_pose = s_dyn;                                         // [nh][3][64]
     double* s_lik = s_dyn + (size_t)nh * 192;                       // [nh][k][64]
     double* s_land = s_lik + (size_t)nh * k_obs * 64;               // [2][k][6][64]
-    const int nsync = 32 * (k_obs + 1);                             // one helper + the EKF warps meet at every hand-off
+    __shared__ unsigned long long s_mb[3][4];                       // [stage][which]
     Fs3State* st = d.st;
+    if (threadIdx.x < 12) { const int sg = threadIdx.x >> 2, wh = threadIdx.x & 3; mb_init(&s_mb[sg][wh], (wh == 1 || wh == 2) ? (unsigned)(k_obs > 0 ? k_obs : 1) : 1u); }
+    __syncthreads();
     if (d.G > 1 && d.wait_inline) {             // peers' rows / poses / maps are stable once their previous post kernel is over
         if (threadIdx.x == 0) fs3_wait_peers(d, 1, step);
         __syncthreads();
@@ -182,6 +200,7 @@ fs3_ekf_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsP
         double2 Wp = make_double2(0.0, 0.0);                              // weights of this helper's previous trip
         unsigned gprev = 0;
         bool first = true;
+        unsigned use = 0;                                                 // how often this helper's stage has been handed over
         for (unsigned g = blockIdx.x + (unsigned)h * gridDim.x; ; g += (unsigned)nh * gridDim.x) {
             const bool have = g < ngroups;
             double2 Wn = make_double2(0.0, 0.0);
@@ -193,10 +212,13 @@ fs3_ekf_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsP
                 const double2 A = *reinterpret_cast<const double2*>(d.pyaw[cur] + i0);
                 double xs[2] = { X.x, X.y }, ys[2] = { Y.x, Y.y }, as[2] = { A.x, A.y };
                 if (flags & 1) {       // predict_particle + motion_model fs1.rs:70-77,123-137, in place
+                    const bool pre = st->noise_call == call + 1u;        // the post kernel of the previous step drew this call's noise already
+                    double2 Z0 = make_double2(0.0, 0.0), Z1 = make_double2(0.0, 0.0);
+                    if (pre) { Z0 = *reinterpret_cast<const double2*>(d.nz[0] + i0); Z1 = *reinterpret_cast<const double2*>(d.nz[1] + i0); }
 #pragma unroll 1
                     for (int q = 0; q < 2; ++q) {
-                        double z0, z1;
-                        fs3_normal_pair(seed, call, (uint64_t)d.off + i0 + q, &z0, &z1);
+                        double z0 = q ? Z0.y : Z0.x, z1 = q ? Z1.y : Z1.x;
+                        if (!pre) fs3_normal_pair(seed, call, (uint64_t)d.off + i0 + q, &z0, &z1);
                         const double xq = q ? xs[1] : xs[0], yq = q ? ys[1] : ys[0], aq = q ? as[1] : as[0];
                         const double un0 = u0 + z0 * sq0;                      // fs1.rs:129
                         const double un1 = u1 + z1 * sq1;                      // fs1.rs:130
@@ -212,13 +234,13 @@ fs3_ekf_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsP
                     *reinterpret_cast<double2*>(d.pyaw[cur] + i0) = make_double2(as[0], as[1]);
                 }
                 if (k_obs > 0) {
-                    if (!first) nb_sync(fs3_bid(h, 1), nsync);                   // the EKF warps have read what this stage held
+                    if (!first) mb_wait(&s_mb[h][1], (use - 1u) & 1u);            // the EKF warps have read what this stage held
                     double* sp = s_pose + h * 192;
                     *reinterpret_cast<double2*>(sp + 2 * lane) = make_double2(xs[0], xs[1]);
                     *reinterpret_cast<double2*>(sp + 64 + 2 * lane) = make_double2(ys[0], ys[1]);
                     *reinterpret_cast<double2*>(sp + 128 + 2 * lane) = make_double2(as[0], as[1]);
-                    __threadfence_block();
-                    nb_arrive(fs3_bid(h, 0), nsync);
+                    __syncwarp();
+                    if (lane == 0) mb_arrive(&s_mb[h][0]);
                 }
             }
             // weights of this helper's previous trip (of this trip when there are no observations):
@@ -228,14 +250,15 @@ fs3_ekf_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsP
                 const unsigned i0 = ge * 64u + 2u * (unsigned)lane;
                 double w0 = k_obs > 0 ? Wp.x : Wn.x, w1 = k_obs > 0 ? Wp.y : Wn.y;
                 if (k_obs > 0) {
-                    nb_sync(fs3_bid(h, 2), nsync);
+                    mb_wait(&s_mb[h][2], (use - 1u) & 1u);                       // every EKF warp has published its factors of that trip
                     const double* sl = s_lik + (size_t)h * k_obs * 64;
 #pragma unroll 1
                     for (int j = 0; j < k_obs; ++j) {
                         const double2 l = *reinterpret_cast<const double2*>(sl + j * 64 + 2 * lane);
                         w0 = w0 * l.x; w1 = w1 * l.y;
                     }
-                    nb_arrive(fs3_bid(h, 3), nsync);
+                    __syncwarp();
+                    if (lane == 0) mb_arrive(&s_mb[h][3]);
                 }
                 const bool v0 = i0 < d.n, v1 = i0 + 1 < d.n;
                 if (!v0) w0 = 0.0;
@@ -253,7 +276,7 @@ fs3_ekf_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsP
                 }
             }
             if (!have) break;
-            Wp = Wn; gprev = g; first = false;
+            Wp = Wn; gprev = g; first = false; use++;
         }
         return;
     }
@@ -313,7 +336,8 @@ fs3_ekf_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsP
         if (it < 0) continue;
         const unsigned i0 = g * 64u + 2u * (unsigned)lane;
         // [C] the predicted pose of this group
-        nb_sync(fs3_bid(stage, 0), nsync);
+        const unsigned upar = (unsigned)(it / nh) & 1u;             // parity of this use of the stage
+        mb_wait(&s_mb[stage][0], upar);
         double px[2], py[2], pyaw[2];
         {
             const double* sp = s_pose + stage * 192;
@@ -321,7 +345,8 @@ fs3_ekf_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsP
             const double2 A = *reinterpret_cast<const double2*>(sp + 128 + 2 * lane);
             px[0] = X.x; px[1] = X.y; py[0] = Y.x; py[1] = Y.y; pyaw[0] = A.x; pyaw[1] = A.y;
         }
-        nb_arrive(fs3_bid(stage, 1), nsync);
+        __syncwarp();
+        if (lane == 0) mb_arrive(&s_mb[stage][1]);
         // [D] update_landmark for the two pairs
         double lik[2] = { 1.0, 1.0 };
         int ok[2];
@@ -343,10 +368,10 @@ fs3_ekf_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsP
         *reinterpret_cast<double2*>(o + 4 * ld) = make_double2(L[0].c10, L[1].c10);
         *reinterpret_cast<double2*>(o + 5 * ld) = make_double2(L[0].c11, L[1].c11);
         // [E] likelihood factors to the helper
-        if (it >= nh) nb_sync(fs3_bid(stage, 3), nsync);
+        if (it >= nh) mb_wait(&s_mb[stage][3], upar ^ 1u);          // the helper has consumed this stage's previous factors
         *reinterpret_cast<double2*>(s_lik + ((size_t)stage * k_obs + wj) * 64 + 2 * lane) = make_double2(lik[0], lik[1]);
-        __threadfence_block();
-        nb_arrive(fs3_bid(stage, 2), nsync);
+        __syncwarp();
+        if (lane == 0) mb_arrive(&s_mb[stage][2]);
         g += gridDim.x;
         if (g >= ngroups) break;
         stage = stage + 1 == nh ? 0 : stage + 1;
@@ -511,7 +536,8 @@ __device__ __noinline__ int fs3_classify(double v, double a0, double a1, unsigne
 // Contains ONE grid barrier (`round`).
 template <int NT>
 __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const double* vals, unsigned K, unsigned nt, double toff, int slot, int round,
-                                        unsigned m32, double* out, int par, double S2, double r0, double inv, double extraQ) {
+                                        unsigned m32, double* out, int par, double S2, double r0, double inv, double extraQ, unsigned long long comb_n = 0,
+                                        const uint64_t* noise_seed_ptr = nullptr, uint32_t noise_call = 0) {
     const int tid = threadIdx.x, lane = tid & 31, pp = round & 1;
     const unsigned b = blockIdx.x;
     const size_t T = (size_t)NT * K;
@@ -560,6 +586,16 @@ __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const do
     // ---- grid barrier + chain.  The LAST CTA to arrive evaluates the chain (every aggregate is published by then and it reads
     // them uncontended: 128 CTAs fetching the same few sectors at once serialise in L2) and publishes the results; the others
     // wait for its flag.  Warp 0 only; the other warps wait at the block barrier below. ----
+    if (comb_n && tid == 32) x3_comb_build(&sh.comb, r0, inv, (double)comb_n, comb_n);   // hidden behind the barrier wait + chain of warp 0
+    if (noise_seed_ptr && tid >= 64) {         // ... and so are the N(0,1) pairs of the next predict for this CTA's share of the local slots
+        const unsigned per = (d.n + nt - 1) / nt, t_lo = b * per, t_hi = min(d.n, t_lo + per);
+#pragma unroll 1
+        for (unsigned t = t_lo + (unsigned)(tid - 64); t < t_hi; t += (unsigned)(NT - 64)) {
+            double z0, z1;
+            fs3_normal_pair(*noise_seed_ptr, noise_call, (uint64_t)d.off + t, &z0, &z1);
+            d.nz[0][t] = z0; d.nz[1][t] = z1;
+        }
+    }
     if (tid < 32) {
         int leader = 0;
         if (tid == 0) { __threadfence(); leader = (atomicAdd(d.bar + round, 1u) + 1u == nt) ? 1 : 0; if (leader) __threadfence(); }
@@ -836,8 +872,13 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
     }
     fs3_block_sum2<NT>(toff, q, sh.red[0], sh.red[1]);
     FS3_TRACE(0);
+    // the comb of a resample this step might need: r = Uniform::new(0, 1/n).sample(rng) (fs1.rs:219-220), one draw per resample, and
+    // (n a power of two) its closed-form table, built by an otherwise idle warp inside the first exact sum
+    const double inv = fs3_div(1.0, (double)ng);
+    const double r0 = pfc_u01_52(pfc_blk_u64(pfc_rng_block(seed, PFC_STREAM_FS_RESAMPLE, st->resamples, 0), 0)) * (inv - 0.0) + 0.0;
     // ---------------- S = sum w_raw (normalize_weights fs1.rs:196-203) ----------------
-    const double S = fs3_xsum<NT>(d, sh, vals, K, nt, toff, 0, 0, m32, nullptr, par, 0.0, 0.0, 0.0, q);
+    const double S = fs3_xsum<NT>(d, sh, vals, K, nt, toff, 0, 0, m32, nullptr, par, 0.0, r0, inv, q, log2n >= 0 ? (unsigned long long)ng : 0ull,
+                                  NT >= 128 ? &seed : nullptr, step + 1u);
     FS3_TRACE(1);
     // w = w_raw / S; best particle of the tile (LAST maximum, fs1.rs:269-274)
     double bw = -1.0; unsigned bi = 0;
@@ -888,8 +929,7 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
     }
     const int gate = neff < nth ? 1 : 0;
     FS3_TRACE(2);
-    double S2 = 0.0, r0 = 0.0;
-    const double inv = fs3_div(1.0, (double)ng);
+    double S2 = 0.0;
     if (gate) {
         // ---------------- resample() re-normalises first (fs1.rs:207) ----------------
         const double toff2 = S > 0.0 ? fs3_div(toff, S) : toff;
@@ -904,18 +944,12 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
         (void)fs3_xsum<NT>(d, sh, vals, K, nt, toff3, 3, 2, m32, d.cum_all, par, S2, 0.0, 0.0, 0.0);
         FS3_TRACE(4);
         // ---------------- the comb r, r + 1/n, ... accumulated sequentially (fs1.rs:219-230) ----------------
-        {
-            const double u01 = pfc_u01_52(pfc_blk_u64(pfc_rng_block(seed, PFC_STREAM_FS_RESAMPLE, st->resamples, 0), 0));
-            r0 = u01 * (inv - 0.0) + 0.0;                      // Uniform::new(0, 1/n).sample
-        }
         if (log2n < 0) {                                       // n not a power of two: every add rounds -> exact scan
         #pragma unroll 1
     for (unsigned k = 0; k < K; ++k) { const size_t i = g0 + k; vals[k * NT + tid] = i < ng ? (i == 0 ? r0 : inv) : 0.0; }
             const double toff4 = b == 0 ? 0.0 : r0 + ((double)((size_t)b * T) - 1.0) * inv;
             __syncthreads();
             (void)fs3_xsum<NT>(d, sh, vals, K, nt, toff4, 4, 3, m32, d.rcomb_all, par, S2, r0, inv, 0.0);
-        } else if (tid == 0) {
-            x3_comb_build(&sh.comb, r0, inv, (double)ng, ng);  // closed form: one segment per binade
         }
         fs3_grid_sync<NT>(d, 4, nt);                           // the whole CDF (and comb) is visible
         FS3_TRACE(5);
@@ -1020,6 +1054,7 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
             rec->neff = neff; rec->gate = gate; rec->err = st->err;
             st->S = S; st->Q = Q; st->neff = neff; st->S2 = S2; st->r0 = r0; st->gate = gate;
             if (gate) { st->cur ^= 1; st->rcur ^= 1; st->resamples += 1; }
+            st->noise_call = NT >= 128 ? step + 2u : 0u;           // nz[] = noise of EKF call step + 1
             st->post_done = 0;
             __threadfence_system();
             *reinterpret_cast<volatile unsigned long long*>(&rec->seq) = (unsigned long long)step + 1ull;

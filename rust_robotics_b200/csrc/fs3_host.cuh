@@ -113,6 +113,7 @@ static int fs_create_impl(const pfgpu_fs_config* cfg, size_t n, size_t n_global,
         d.st = stp;
         FS_TRY(cudaMalloc(&d.lmst, mm * sizeof(int))); FS_TRY(cudaMemset(d.lmst, 0, mm * sizeof(int)));
         FS_TRY(cudaMalloc(&d.w, ld * sizeof(double))); FS_TRY(cudaMemset(d.w, 0, ld * sizeof(double)));
+        for (int b = 0; b < 2; ++b) { FS_TRY(cudaMalloc(&d.nz[b], ld * sizeof(double))); FS_TRY(cudaMemset(d.nz[b], 0, ld * sizeof(double))); }
         FS_TRY(cudaMalloc(&d.wn_all, (n_global + 64) * sizeof(double)));
         FS_TRY(cudaMalloc(&d.cum_all, (n_global + 64) * sizeof(double)));
         if (h->log2n < 0) FS_TRY(cudaMalloc(&d.rcomb_all, (n_global + 64) * sizeof(double)));
@@ -226,7 +227,7 @@ extern "C" void pfgpu_fs_destroy(pfgpu_fs* h) {
     Fs3Dev& d = h->d;
     for (int g = 0; g < h->world; ++g) if (g != h->rank && h->peer_ptr[g]) cudaIpcCloseMemHandle(h->peer_ptr[g]);   // (local mode: none were opened)
     cudaFree(h->arena);
-    cudaFree(d.st); cudaFree(d.lmst); cudaFree(d.w); cudaFree(d.wn_all); cudaFree(d.cum_all); cudaFree(d.rcomb_all); cudaFree(d.idx);
+    cudaFree(d.st); cudaFree(d.lmst); cudaFree(d.w); cudaFree(d.nz[0]); cudaFree(d.nz[1]); cudaFree(d.wn_all); cudaFree(d.cum_all); cudaFree(d.rcomb_all); cudaFree(d.idx);
     cudaFree(d.tileP); cudaFree(d.tileQ); cudaFree(d.entCnt); cudaFree(d.entKey); cudaFree(d.entTile); cudaFree(d.entP); cudaFree(d.entV); cudaFree(d.entL);
     cudaFree(d.bar); cudaFree(d.rowlist); cudaFree(d.rowinfo); cudaFree(d.resflag); cudaFree(d.res); cudaFree(d.resTP); cudaFree(d.resKey);
     cudaFree(d.resP); cudaFree(d.resAft); cudaFree(d.tileEnd);

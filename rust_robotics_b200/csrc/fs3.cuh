@@ -395,6 +395,12 @@ __global__ void fs3_signal_kernel(const __grid_constant__ Fs3Dev d, int which, u
     pf_grid_dep_sync();
     fs3_signal_peers(d, which, value);
 }
+__device__ __forceinline__ void fs3_mark_updated_warp(const Fs3Dev& d, const Fs3ObsParam& po, int k_obs, int lane) {
+    for (int j = lane; j < k_obs; j += 32) {
+        const int l = po.o[j].lm_id, s = d.lmst[l];
+        if (s >> 1) d.lmst[l] = (s & 1) ^ 1;
+    }
+}
 __global__ void fs3_mark_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsParam po, int k_obs) {
     pf_grid_dep_sync();
     fs3_mark_updated(d, po, k_obs);
@@ -419,6 +425,7 @@ struct Fs3Sh {
     unsigned long long Ptot;
     int D, fail, last;
     unsigned jr[2];
+    unsigned rowbits[32];                                     // bitmap of the live ancestry rows (CTA 0)
     double tend[FS3_MAX_TILES];                               // last CDF value of every tile
     x3_comb_table comb;
 };
@@ -530,14 +537,18 @@ __device__ __noinline__ void fs3_serial_walk(const Fs3Dev& d, Fs3Sh<NT>& sh, uns
 __device__ __noinline__ int fs3_classify(double v, double a0, double a1, unsigned m32, unsigned long long* inc, int* lvl) {
     return x3_classify(v, a0, a1, m32, inc, lvl);            // one copy of the code for the three passes of fs3_xsum
 }
+// Work that hides inside the first exact sum of a launch, on warps that would otherwise sleep at a block barrier while warp 0
+// waits for the grid and evaluates the chain: the lazy-clone bookkeeping + live-row list (CTA 0), the comb table, and the
+// N(0,1) pairs of the next predict.
+struct Fs3Hook { unsigned long long comb_n; uint64_t seed; uint32_t noise_call; int k_last; const Fs3ObsParam* po; };
+
 // One exact sequential sum over the n_glob values held tile-wise in shared memory (thread t owns values t*K .. t*K+K-1 of its
 // tile, stored at vals[k*NT + t]).  toff = approximate sum of everything in front of this tile.  Returns the exact total
 // (identical in every CTA); with out != nullptr also stores the exact inclusive prefix of every value to out[global index].
 // Contains ONE grid barrier (`round`).
 template <int NT>
 __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const double* vals, unsigned K, unsigned nt, double toff, int slot, int round,
-                                        unsigned m32, double* out, int par, double S2, double r0, double inv, double extraQ, unsigned long long comb_n = 0,
-                                        const uint64_t* noise_seed_ptr = nullptr, uint32_t noise_call = 0) {
+                                        unsigned m32, double* out, int par, double S2, double r0, double inv, double extraQ, const Fs3Hook* hook = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, pp = round & 1;
     const unsigned b = blockIdx.x;
     const size_t T = (size_t)NT * K;
@@ -586,14 +597,49 @@ __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const do
     // ---- grid barrier + chain.  The LAST CTA to arrive evaluates the chain (every aggregate is published by then and it reads
     // them uncontended: 128 CTAs fetching the same few sectors at once serialise in L2) and publishes the results; the others
     // wait for its flag.  Warp 0 only; the other warps wait at the block barrier below. ----
-    if (comb_n && tid == 32) x3_comb_build(&sh.comb, r0, inv, (double)comb_n, comb_n);   // hidden behind the barrier wait + chain of warp 0
-    if (noise_seed_ptr && tid >= 64) {         // ... and so are the N(0,1) pairs of the next predict for this CTA's share of the local slots
-        const unsigned per = (d.n + nt - 1) / nt, t_lo = b * per, t_hi = min(d.n, t_lo + per);
+    if (hook && tid >= 32) {
+        if (tid < 64) {                            // warp 1
+            if (b == 0) {
+                // lazy-clone bookkeeping of the EKF launch that just ran, then the rows a resample would have to compose: one bit per
+                // row some landmark still reads through; the identity landmarks would get ONE new row (the first free id: with an
+                // identity landmark at most m - 1 rows are live).  Other CTAs read the list only after >= 3 grid barriers.
+                unsigned* s_bits = sh.rowbits;
+                fs3_mark_updated_warp(d, *hook->po, hook->k_last, lane);
+                __syncwarp();
+                int any_ident = 0;
+                s_bits[lane] = 0u;                                       // 32-word bitmap of the live rows (m <= 1024)
+                __syncwarp();
 #pragma unroll 1
-        for (unsigned t = t_lo + (unsigned)(tid - 64); t < t_hi; t += (unsigned)(NT - 64)) {
-            double z0, z1;
-            fs3_normal_pair(*noise_seed_ptr, noise_call, (uint64_t)d.off + t, &z0, &z1);
-            d.nz[0][t] = z0; d.nz[1][t] = z1;
+                for (unsigned l = lane; l < d.m; l += 32) {
+                    const int st_l = d.lmst[l];
+                    if (st_l >> 1) { const unsigned r = (unsigned)((st_l >> 1) - 1); atomicOr(&s_bits[r >> 5], 1u << (r & 31)); } else any_ident = 1;
+                }
+                any_ident = __any_sync(0xffffffffu, any_ident);
+                __syncwarp();
+                const unsigned bits = s_bits[lane];
+                const int cntb = __popc(bits);
+                int incl = cntb;
+#pragma unroll 1
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+                int pos = incl - cntb;
+#pragma unroll 1
+                for (unsigned x = bits; x; x &= x - 1) d.rowlist[pos++] = (unsigned short)(lane * 32 + __ffs(x) - 1);
+                const unsigned fr = ~bits;
+                const unsigned has = __ballot_sync(0xffffffffu, fr != 0u);
+                if (lane == 31) d.rowinfo[0] = incl;
+                if (lane == 0) d.rowinfo[1] = -1;
+                __syncwarp();
+                if (any_ident && lane == __ffs(has) - 1) d.rowinfo[1] = lane * 32 + __ffs(fr) - 1;
+            }
+            if (hook->comb_n && lane == 0) x3_comb_build(&sh.comb, r0, inv, (double)hook->comb_n, hook->comb_n);
+        } else {                                   // warps 2..: the N(0,1) pairs of the next predict for this CTA's share of the local slots
+            const unsigned per = (d.n + nt - 1) / nt, t_lo = b * per, t_hi = min(d.n, t_lo + per);
+#pragma unroll 1
+            for (unsigned t = t_lo + (unsigned)(tid - 64); t < t_hi; t += (unsigned)(NT - 64)) {
+                double z0, z1;
+                fs3_normal_pair(hook->seed, hook->noise_call, (uint64_t)d.off + t, &z0, &z1);
+                d.nz[0][t] = z0; d.nz[1][t] = z1;
+            }
         }
     }
     if (tid < 32) {
@@ -620,6 +666,7 @@ __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const do
 #pragma unroll
             for (unsigned i = 0; i < (FS3_MAX_TILES + 31) / 32; ++i) if (i * 32u + lane < nt) sh.tPoff[i * 32u + lane] = tp[i];
             __syncwarp();
+            if (slot == 0) FS3_TRACE(16);
             // clean-increment sum in front of every tile: lane owns `per` consecutive tiles
             const unsigned per = (nt + 31u) / 32u, t0 = (unsigned)lane * per;
             unsigned long long lsum = 0;
@@ -633,6 +680,7 @@ __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const do
 #pragma unroll 1
             for (unsigned i = 0; i < per; ++i) if (t0 + i < nt) { const unsigned long long x = sh.tPoff[t0 + i]; sh.tPoff[t0 + i] = run; run += x; }
             __syncwarp();
+            if (slot == 0) FS3_TRACE(17);
             const int D = fail ? 0 : (int)cnt;
             double total = 0.0;
             if (D <= 32) {
@@ -649,6 +697,7 @@ __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const do
                 __syncwarp();
                 const unsigned long long myP = have ? sh.sP[lane] : 0ull;
                 const double myV = have ? sh.sV[lane] : 0.0;
+                if (slot == 0) FS3_TRACE(18);
                 double sacc = 0.0, mybef = 0.0, myaft = 0.0; unsigned long long prev = 0;
 #pragma unroll 4
                 for (int o = 0; o < 32; ++o) {
@@ -708,6 +757,7 @@ __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const do
             __syncwarp();
             fail = __any_sync(0xffffffffu, fail);
             total = __shfl_sync(0xffffffffu, total, 0);
+            if (slot == 0) FS3_TRACE(19);
             // publish: what the other CTAs need to finish on their own
             if (out && !fail) {
 #pragma unroll 1
@@ -723,6 +773,7 @@ __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const do
             __syncwarp();
             __threadfence();
             if (lane == 0) atomicExch(d.resflag + round, 1u);
+            if (slot == 0) { FS3_TRACE(20); if (d.trace && b == 0 && tid == 0) d.trace[21] += 1; }
         } else {
             if (lane == 0) {
                 unsigned spins = 0;
@@ -830,35 +881,6 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
             __syncthreads();
         }
     }
-    if (b == 0) {
-        // lazy-clone bookkeeping of the EKF launch that just ran, then the rows a resample would have to compose: one bit per
-        // row some landmark still reads through; the identity landmarks would get ONE new row (the first free id: with an
-        // identity landmark at most m - 1 rows are live).  Other CTAs read the list only after >= 3 grid barriers.
-        fs3_mark_updated(d, po, k_last);
-        __shared__ unsigned s_bits[32];
-        if (tid < 32) s_bits[tid] = 0u;
-        __syncthreads();
-        int any_ident = 0;
-#pragma unroll 1
-        for (unsigned l = tid; l < d.m; l += NT) { const int s = d.lmst[l]; if (s >> 1) atomicOr(&s_bits[((s >> 1) - 1) >> 5], 1u << (((s >> 1) - 1) & 31)); else any_ident = 1; }
-        any_ident = __syncthreads_or(any_ident);
-        if (tid < 32) {
-            const unsigned bits = s_bits[tid];
-            const int cnt = __popc(bits);
-            int incl = cnt;
-#pragma unroll 1
-            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += y; }
-            int pos = incl - cnt;
-#pragma unroll 1
-            for (unsigned x = bits; x; x &= x - 1) d.rowlist[pos++] = (unsigned short)(tid * 32 + __ffs(x) - 1);
-            const unsigned fr = ~bits;
-            const unsigned has = __ballot_sync(0xffffffffu, fr != 0u);
-            if (tid == 31) d.rowinfo[0] = incl;
-            if (tid == 0) d.rowinfo[1] = -1;
-            __syncwarp();
-            if (any_ident && tid == __ffs(has) - 1) d.rowinfo[1] = tid * 32 + __ffs(fr) - 1;
-        }
-    }
     // ---- load this tile's weights; approximate sum of everything in front of the tile from the 64-particle partials ----
     const size_t g0 = (size_t)b * T + (size_t)tid * K;
     double q = 0.0;
@@ -877,8 +899,9 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
     const double inv = fs3_div(1.0, (double)ng);
     const double r0 = pfc_u01_52(pfc_blk_u64(pfc_rng_block(seed, PFC_STREAM_FS_RESAMPLE, st->resamples, 0), 0)) * (inv - 0.0) + 0.0;
     // ---------------- S = sum w_raw (normalize_weights fs1.rs:196-203) ----------------
-    const double S = fs3_xsum<NT>(d, sh, vals, K, nt, toff, 0, 0, m32, nullptr, par, 0.0, r0, inv, q, log2n >= 0 ? (unsigned long long)ng : 0ull,
-                                  NT >= 128 ? &seed : nullptr, step + 1u);
+    Fs3Hook hook;
+    hook.comb_n = log2n >= 0 ? (unsigned long long)ng : 0ull; hook.seed = seed; hook.noise_call = step + 1u; hook.k_last = k_last; hook.po = &po;
+    const double S = fs3_xsum<NT>(d, sh, vals, K, nt, toff, 0, 0, m32, nullptr, par, 0.0, r0, inv, q, &hook);
     FS3_TRACE(1);
     // w = w_raw / S; best particle of the tile (LAST maximum, fs1.rs:269-274)
     double bw = -1.0; unsigned bi = 0;
@@ -975,6 +998,7 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
         }
         __syncthreads();
         if (t_lo < t_hi) {
+            FS3_TRACE(22);
             const unsigned jlo = sh.jr[0], jhi = min(sh.jr[1], (unsigned)ng - 1u);        // answers lie in [jlo, jhi] (ng -> clamped)
             const unsigned len = jlo <= jhi ? jhi - jlo + 1u : 0u;
             const bool staged = len <= (unsigned)T;
@@ -983,6 +1007,7 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
                 for (unsigned i = tid; i < len; i += NT) vals[i] = __ldcg(cdf + jlo + i);
             }
             __syncthreads();
+            FS3_TRACE(23);
 #pragma unroll 1
             for (unsigned t = t_lo + tid; t < t_hi; t += NT) {
                 const size_t tg = (size_t)d.off + t;

@@ -243,6 +243,8 @@ def measure(rr, grp, cfg_key, K, W, rank, world, local_rank, with_e2e, sampler_c
     n_global = cfg["particles_total"] or cfg["particles_per_gpu"] * world
     total = W + 3 * K + 4
     sc = getattr(scenarios, cfg["scenario"])(steps=total)
+    if os.environ.get("BENCH_EMPTY_OBS"):      # experiment: no observations (the EKF launch degenerates to predict; what does the post kernel cost then?)
+        sc.obs = [[] for _ in sc.obs]
     arrs = obs_arrays(rr, sc)
     fcfg = rr.FsConfig(nth=nth_value(n_global))
     if world > 1:
@@ -429,7 +431,11 @@ def run_pf(args):
             "roofline": {"bound": "hbm", "kernel": "pf_predict_weight_kernel (predict + range likelihood, pf.rs:279-329)",
                          "achieved": alg / (kms * 1e-3) / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": alg / (kms * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": kms,
-                         "note": "FP64-bound when observations_per_step is large (config 2: 360 sqrt+exp+div per particle)"},
+                         "note": "FP64-bound when observations_per_step is large (config 2: 360 sqrt+exp+div per particle)",
+                         # config 2 is bounded by the FP64 pipe, not HBM: the reference's formula costs 12 f64 operations per
+                         # (particle, beam) counting sqrt / exp / div as one each (pf.rs:317-328,476-479) + 13 per particle for predict
+                         "fp64_algorithmic_tflops": n * (12.0 * kobs + 13.0) / (kms * 1e-3) / 1e12,
+                         "fp64_peak_tflops_nominal": 37.2},
             "clocks": clocks, "serial_fallbacks": int(st1.serial_fallbacks)}
     if not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -7,7 +7,7 @@ timeout 1500 python -m pytest tests/test_gpu_multi.py -x -q -m gpu > gpurun_out/
 echo "pytest rc=$?" >> gpurun_out/mg${N}_pytest.log
 for n in 2 4 8; do
   if [ $n -le $N ]; then
-    PFGPU_POST_TRACE=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29617 bench.py --gpus $n --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/mg${N}_bench_n$n.json 2> gpurun_out/mg${N}_bench_n$n.err
+    PFGPU_POST_TRACE=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29617 bench.py --gpus $n --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/mg${N}_bench_n$n.out 2> gpurun_out/mg${N}_bench_n$n.err; grep -h "^{\"metric\"" gpurun_out/mg${N}_bench_n$n.out gpurun_out/mg${N}_bench_n$n.err | tail -1 > gpurun_out/mg${N}_bench_n$n.json
     echo "bench n=$n rc=$?" >> gpurun_out/mg${N}_pytest.log
   fi
 done

@@ -85,7 +85,8 @@ int  pfgpu_pf_step(pfgpu_pf*, const double u[2], const double* obs3, size_t k, d
 int  pfgpu_pf_estimate(pfgpu_pf*, double est[4], double cov16_colmajor[16]); /* estimate()/calc_covariance() pf.rs:348-365 */
 int  pfgpu_pf_neff(pfgpu_pf*, double* neff);                                 /* calc_n_eff pf.rs:416-423 */
 int  pfgpu_pf_set_range_noise(pfgpu_pf*, double range_noise);                /* pf.rs:228-236 */
-int  pfgpu_pf_last_indices(pfgpu_pf*, uint32_t* idx, size_t cap, size_t* n); /* parity hook: ancestry of the last resample (global indices) */
+/* parity hook: ancestry of the last step's resample (global indices); *n = 0 when the last step did not resample */
+int  pfgpu_pf_last_indices(pfgpu_pf*, uint32_t* idx, size_t cap, size_t* n);
 int  pfgpu_pf_sync(pfgpu_pf*);
 
 /* ============================================ FastSLAM 1.0 ========================================== */
@@ -146,7 +147,7 @@ int  pfgpu_fs_get_observations(pfgpu_fs*, const double x_true[3], const double* 
 int  pfgpu_fs_best(pfgpu_fs*, size_t* index_global, double pose_w4[4]);
 /* landmarks of one particle (what render_gif_slam.rs:183-191 reads): lm6 = m x 6 */
 int  pfgpu_fs_particle_landmarks(pfgpu_fs*, size_t index_local, double* lm6);
-int  pfgpu_fs_last_indices(pfgpu_fs*, uint32_t* idx, size_t cap, size_t* n);
+int  pfgpu_fs_last_indices(pfgpu_fs*, uint32_t* idx, size_t cap, size_t* n);  /* *n = 0 when the last step did not resample */
 int  pfgpu_fs_last_neff(pfgpu_fs*, double* neff);
 int  pfgpu_fs_last_gate(pfgpu_fs*, int* did_resample);     /* whether the last step resampled (fs1.rs:263); synchronises */
 int  pfgpu_fs_count(pfgpu_fs*, size_t* n_local, size_t* n_global, size_t* n_landmarks);

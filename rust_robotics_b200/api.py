@@ -282,7 +282,7 @@ class _PfBase:
         idx = np.empty(n, dtype=np.uint32)
         cnt = C.c_size_t()
         _check(self.L, self.L.pfgpu_pf_last_indices(self.h, idx.ctypes.data_as(c_u32p), n, C.byref(cnt)))
-        return idx
+        return idx[:cnt.value]
 
     def sync(self):
         _check(self.L, self.L.pfgpu_pf_sync(self.h))
@@ -503,7 +503,7 @@ class FastSlam1:
         idx = np.empty(self.n_local, dtype=np.uint32)
         cnt = C.c_size_t()
         _check(self.L, self.L.pfgpu_fs_last_indices(self.h, idx.ctypes.data_as(c_u32p), self.n_local, C.byref(cnt)))
-        return idx
+        return idx[:cnt.value]
 
     def last_neff(self):
         v = C.c_double()

@@ -559,18 +559,31 @@ __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const do
     double ts = 0.0; bool bad = false;
 #pragma unroll 1
     for (unsigned k = 0; k < K; ++k) { const double v = vals[k * NT + tid]; ts += v; if (!(v >= 0.0) || !(v <= 1.7976931348623157e308)) bad = true; }
+    if (slot == 0) FS3_TRACE(28);
     const double a_first = toff + fs3_scan_d<NT>(ts, sh.wd[pp]);
+    if (slot == 0) FS3_TRACE(29);
     unsigned long long P = 0; int nd = 0;
-    {
+    // Almost every thread's K prefixes stay inside one binade, clear of its edges: then each value is classified at that binade
+    // without a running prefix (no loop-carried FP chain, a dozen integer instructions per value).  The same predicate, from the
+    // same operands, selects the path in the three passes below.
+    const int e_run = x3_interior(a_first, a_first + ts, m32);
+    if (e_run >= 0) {
+#pragma unroll 2
+        for (unsigned k = 0; k < K; ++k) {
+            unsigned long long inc;
+            if (x3_classify_at(vals[k * NT + tid], e_run, &inc)) nd++; else P += inc;
+        }
+    } else {
         double a = a_first;
-    #pragma unroll 1
-    for (unsigned k = 0; k < K; ++k) {
+#pragma unroll 1
+        for (unsigned k = 0; k < K; ++k) {
             const double v = vals[k * NT + tid], a1 = a + v;
             unsigned long long inc; int lvl;
             if (fs3_classify(v, a, a1, m32, &inc, &lvl)) nd++; else P += inc;
             a = a1;
         }
     }
+    if (slot == 0) FS3_TRACE(30);
     unsigned long long Pex, Ptile; int dex, ndtile;
     fs3_scan_ui<NT>(P, nd, &Pex, &dex, &Ptile, &ndtile, sh.wu[pp], sh.wi[pp]);
     if (nd > 0) {                                              // rare: itemise this thread's dirty values (any order; sorted by the chain)
@@ -579,8 +592,8 @@ __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const do
     #pragma unroll 1
     for (unsigned k = 0; k < K; ++k) {
             const double v = vals[k * NT + tid], a1 = a + v;
-            unsigned long long inc; int lvl;
-            if (fs3_classify(v, a, a1, m32, &inc, &lvl)) {
+            unsigned long long inc; int lvl = e_run;
+            if (e_run >= 0 ? x3_classify_at(v, e_run, &inc) : fs3_classify(v, a, a1, m32, &inc, &lvl)) {
                 if (e < FS3_ENT_CAP) {
                     const size_t o = (size_t)slot * FS3_ENT_CAP + e;
                     d.entKey[o] = (unsigned)((size_t)b * T + (size_t)tid * K + k); d.entTile[o] = b; d.entP[o] = Pr; d.entV[o] = v; d.entL[o] = lvl;
@@ -807,18 +820,28 @@ __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const do
         }
         double base = ko ? sh.aft[ko - 1] : 0.0;
         unsigned long long Pb = ko ? sh.sP[ko - 1] : 0ull, Pc = sh.tPoff[b] + Pex;
-        double a = a_first;
+        double a = a_first, c = base;
         int ok = 1;
-    #pragma unroll 1
-    for (unsigned k = 0; k < K; ++k) {
-            const double v = vals[k * NT + tid], a1 = a + v;
-            unsigned long long inc; int lvl; double c;
-            if (fs3_classify(v, a, a1, m32, &inc, &lvl)) { base = sh.aft[ko]; Pb = sh.sP[ko]; ko++; c = base; }
-            else { Pc += inc; c = x3_apply(base, Pc - Pb, inc ? lvl : -1, &ok); }
-            if (g0 + k < d.n_glob) out[g0 + k] = c;
-            if (slot == 3 && tid == NT - 1 && k + 1 == K) d.tileEnd[b] = c;    // coarse level of the index search
-            a = a1;
+        if (e_run >= 0) {
+#pragma unroll 2
+            for (unsigned k = 0; k < K; ++k) {
+                unsigned long long inc;
+                if (x3_classify_at(vals[k * NT + tid], e_run, &inc)) { base = sh.aft[ko]; Pb = sh.sP[ko]; ko++; c = base; }
+                else { Pc += inc; c = x3_apply(base, Pc - Pb, inc ? e_run : -1, &ok); }
+                if (g0 + k < d.n_glob) out[g0 + k] = c;
+            }
+        } else {
+#pragma unroll 1
+            for (unsigned k = 0; k < K; ++k) {
+                const double v = vals[k * NT + tid], a1 = a + v;
+                unsigned long long inc; int lvl;
+                if (fs3_classify(v, a, a1, m32, &inc, &lvl)) { base = sh.aft[ko]; Pb = sh.sP[ko]; ko++; c = base; }
+                else { Pc += inc; c = x3_apply(base, Pc - Pb, inc ? lvl : -1, &ok); }
+                if (g0 + k < d.n_glob) out[g0 + k] = c;
+                a = a1;
+            }
         }
+        if (slot == 3 && tid == NT - 1) d.tileEnd[b] = c;      // coarse level of the index search
         if (!ok) atomicAdd(&d.st->cert_fail, 1);
         FS3_TRACE(tb0 + 3);
     }
@@ -889,7 +912,7 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
     double toff = 0.0;
     {
         const unsigned pfirst = (unsigned)(((size_t)b * T) / 64);      // partial p covers global slots [64 p, 64 p + 64)
-#pragma unroll 4
+#pragma unroll 8
         for (unsigned p = tid; p < pfirst; p += NT) toff += __ldcg(d.part[par] + p);
     }
     fs3_block_sum2<NT>(toff, q, sh.red[0], sh.red[1]);
@@ -1008,32 +1031,65 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
             }
             __syncthreads();
             FS3_TRACE(23);
+            // four slots per thread and trip: their searches, pose gathers and row gathers are independent, so the dependent memory
+            // round trips (index -> ancestor's pose -> ancestor's row entries) overlap four-fold
 #pragma unroll 1
-            for (unsigned t = t_lo + tid; t < t_hi; t += NT) {
-                const size_t tg = (size_t)d.off + t;
-                const double r = log2n >= 0 ? x3_comb_eval(&sh.comb, inv, tg) : __ldcg(d.rcomb_all + tg);
-                unsigned lo = 0, hi = len;
-                if (staged) {
+            for (unsigned t0 = t_lo + tid; t0 < t_hi; t0 += 4 * NT) {
+                unsigned jj[4]; int jrk[4]; unsigned jcol[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned t = t0 + (unsigned)u * NT;
+                    jj[u] = 0; jrk[u] = 0; jcol[u] = 0;
+                    if (t < t_hi) {
+                        const size_t tg = (size_t)d.off + t;
+                        const double r = log2n >= 0 ? x3_comb_eval(&sh.comb, inv, tg) : __ldcg(d.rcomb_all + tg);
+                        unsigned lo = 0, hi = len;
+                        if (staged) {
 #pragma unroll 1
-                    while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (vals[mid] < r) lo = mid + 1; else hi = mid; }
-                } else {
+                            while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (vals[mid] < r) lo = mid + 1; else hi = mid; }
+                        } else {
 #pragma unroll 1
-                    while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (__ldcg(cdf + jlo + mid) < r) lo = mid + 1; else hi = mid; }
+                            while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (__ldcg(cdf + jlo + mid) < r) lo = mid + 1; else hi = mid; }
+                        }
+                        unsigned j = jlo + lo;
+                        if (j >= ng) j = (unsigned)ng - 1;
+                        jj[u] = j; jrk[u] = (int)(j / d.n); jcol[u] = j % d.n;              // owner rank and column of the ancestor
+                    }
                 }
-                unsigned j = jlo + lo;
-                if (j >= ng) j = (unsigned)ng - 1;
-                d.idx[t] = j;
-                const int jr = (int)(j / d.n); const unsigned jc = j % d.n;                 // owner rank and column of the ancestor
-                const double* sx = d.G > 1 ? reinterpret_cast<const double*>(d.peer[jr] + d.o_px[cur]) : d.px[cur];
-                const double* sy = d.G > 1 ? reinterpret_cast<const double*>(d.peer[jr] + d.o_py[cur]) : d.py[cur];
-                const double* sa = d.G > 1 ? reinterpret_cast<const double*>(d.peer[jr] + d.o_pyaw[cur]) : d.pyaw[cur];
-                d.px[cur ^ 1][t] = sx[jc]; d.py[cur ^ 1][t] = sy[jc]; d.pyaw[cur ^ 1][t] = sa[jc];     // particles[j].clone() fs1.rs:227
-                d.w[t] = inv;                                                                // fs1.rs:228
-                const unsigned* srows = d.G > 1 ? reinterpret_cast<const unsigned*>(d.peer[jr] + d.o_rows[rcur]) : d.rows[rcur];
+                double gx[4], gy[4], ga[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double* sx = d.G > 1 ? reinterpret_cast<const double*>(d.peer[jrk[u]] + d.o_px[cur]) : d.px[cur];
+                    const double* sy = d.G > 1 ? reinterpret_cast<const double*>(d.peer[jrk[u]] + d.o_py[cur]) : d.py[cur];
+                    const double* sa = d.G > 1 ? reinterpret_cast<const double*>(d.peer[jrk[u]] + d.o_pyaw[cur]) : d.pyaw[cur];
+                    gx[u] = sx[jcol[u]]; gy[u] = sy[jcol[u]]; ga[u] = sa[jcol[u]];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned t = t0 + (unsigned)u * NT;
+                    if (t < t_hi) {
+                        d.idx[t] = jj[u];
+                        d.px[cur ^ 1][t] = gx[u]; d.py[cur ^ 1][t] = gy[u]; d.pyaw[cur ^ 1][t] = ga[u];     // particles[j].clone() fs1.rs:227
+                        d.w[t] = inv;                                                            // fs1.rs:228
+                    }
+                }
                 unsigned* drows = d.rows[rcur ^ 1];
-#pragma unroll 4
-                for (int x = 0; x < nrows; ++x) { const size_t ro = (size_t)d.rowlist[x] * d.ld; drows[ro + t] = srows[ro + jc]; }
-                if (newrow >= 0) drows[(size_t)newrow * d.ld + t] = fs3_ref(jr, jc);
+#pragma unroll 2
+                for (int x = 0; x < nrows; ++x) {
+                    const size_t ro = (size_t)d.rowlist[x] * d.ld;
+                    unsigned e[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const unsigned* srows = d.G > 1 ? reinterpret_cast<const unsigned*>(d.peer[jrk[u]] + d.o_rows[rcur]) : d.rows[rcur];
+                        e[u] = srows[ro + jcol[u]];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { const unsigned t = t0 + (unsigned)u * NT; if (t < t_hi) drows[ro + t] = e[u]; }
+                }
+                if (newrow >= 0) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { const unsigned t = t0 + (unsigned)u * NT; if (t < t_hi) drows[(size_t)newrow * d.ld + t] = fs3_ref(jrk[u], jcol[u]); }
+                }
             }
         }
         FS3_TRACE(6);

@@ -445,10 +445,12 @@ extern "C" int pfgpu_fs_particle_landmarks(pfgpu_fs* h, size_t il, double* lm6) 
 extern "C" int pfgpu_fs_last_indices(pfgpu_fs* h, uint32_t* idx, size_t cap, size_t* n) {
     if (!h || !idx) return PFGPU_ERR_INVALID;
     PF_CUDA(cudaSetDevice(h->ctx.device));
+    PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+    if (!h->h_rec->gate) { if (n) *n = 0; return 0; }         // the last step did not resample: no ancestry (as the oracle reports)
     size_t c = cap < h->d.n ? cap : h->d.n;
     PF_CUDA(cudaMemcpyAsync(idx, h->d.idx, c * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->ctx.stream));
     PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
-    if (n) *n = h->d.n;
+    if (n) *n = c;
     return 0;
 }
 extern "C" int pfgpu_fs_last_neff(pfgpu_fs* h, double* neff) {

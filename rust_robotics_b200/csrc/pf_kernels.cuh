@@ -152,13 +152,16 @@ __global__ void __launch_bounds__(PF_NT) pf_gather_kernel(PfDev d) {
 }
 __global__ void pf_flip_kernel(PfDev d) { if (*d.gate) { *d.cur ^= 1; d.counters[0] += 1; } }
 
+__device__ __forceinline__ double pf_finite_or_zero(double c) { return (c - c == 0.0) ? c : 0.0; }
 // compute_estimate + compute_covariance (pf.rs:382-413) in one pass with a shifted centre c (the previous
 // estimate): sum w, sum w(p-c), sum w(p-c)(p-c)^T; finalised by pf_moments_final_kernel.  Tolerance-level
 // quantity (1e-6): summed in tree order, not in the reference's sequential order.
 __global__ void __launch_bounds__(PF_NT) pf_moments_kernel(PfDev d, int nblocks) {
     __shared__ double sm[PF_NT / 32];
     const Pose4* pose = pf_pose(d, *d.cur);
-    const double c0 = d.scal[4], c1 = d.scal[5], c2 = d.scal[6], c3 = d.scal[7];
+    // centre = previous estimate, or 0 when that is not finite (an overflowed pose must not poison every later estimate:
+    // the reference's refresh_cache recomputes from scratch, pf.rs:382-413).  pf_moments_final_kernel applies the same rule.
+    const double c0 = pf_finite_or_zero(d.scal[4]), c1 = pf_finite_or_zero(d.scal[5]), c2 = pf_finite_or_zero(d.scal[6]), c3 = pf_finite_or_zero(d.scal[7]);
     double acc[PF_MOM];
 #pragma unroll
     for (int k = 0; k < PF_MOM; ++k) acc[k] = 0.0;
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(PF_NT) pf_moments_reduce_kernel(const double* 
 __global__ void pf_moments_final_kernel(PfDev d, const double* mom15) {
     if (threadIdx.x != 0) return;
     const double W = mom15[0];
-    double c[4] = { d.scal[4], d.scal[5], d.scal[6], d.scal[7] };
+    double c[4] = { pf_finite_or_zero(d.scal[4]), pf_finite_or_zero(d.scal[5]), pf_finite_or_zero(d.scal[6]), pf_finite_or_zero(d.scal[7]) };
     double M1[4] = { mom15[1], mom15[2], mom15[3], mom15[4] };
     double M2[4][4];
     int q = 5;

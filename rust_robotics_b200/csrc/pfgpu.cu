@@ -326,27 +326,32 @@ extern "C" int pfgpu_pf_init_state(pfgpu_pf* h, const double s[4]) {
     PF_LAUNCH(h->ctx, pf_init_state_kernel, cdiv_u(h->d.n, PF_NT), PF_NT, 0, h->d, s[0], s[1], s[2], s[3], h->seed, h->cfg.mode);
     return pf_refresh_cache(h);
 }
+// device temporary of the bulk transfers: released on every exit path (PF_CUDA / PF_LAUNCH return early on errors)
+struct PfScopedDev {
+    double* p = nullptr;
+    ~PfScopedDev() { if (p) cudaFree(p); }
+};
 extern "C" int pfgpu_pf_upload(pfgpu_pf* h, const double* aos5, size_t n) {
     if (!h || !aos5 || n != h->d.n) return PFGPU_ERR_INVALID;
     PF_CUDA(cudaSetDevice(h->ctx.device));
-    double* tmp = nullptr;
-    PF_CUDA(cudaMalloc(&tmp, n * 5 * sizeof(double)));
+    PfScopedDev t;
+    PF_CUDA(cudaMalloc(&t.p, n * 5 * sizeof(double)));
+    double* tmp = t.p;
     PF_CUDA(cudaMemcpyAsync(tmp, aos5, n * 5 * sizeof(double), cudaMemcpyHostToDevice, h->ctx.stream));
     PF_LAUNCH(h->ctx, pf_unpack_kernel, cdiv_u(n, PF_NT), PF_NT, 0, h->d, tmp);
     int rc = pf_refresh_cache(h);
     PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
-    cudaFree(tmp);
     return rc;
 }
 extern "C" int pfgpu_pf_download(pfgpu_pf* h, double* aos5, size_t n) {
     if (!h || !aos5 || n != h->d.n) return PFGPU_ERR_INVALID;
     PF_CUDA(cudaSetDevice(h->ctx.device));
-    double* tmp = nullptr;
-    PF_CUDA(cudaMalloc(&tmp, n * 5 * sizeof(double)));
+    PfScopedDev t;
+    PF_CUDA(cudaMalloc(&t.p, n * 5 * sizeof(double)));
+    double* tmp = t.p;
     PF_LAUNCH(h->ctx, pf_pack_kernel, cdiv_u(n, PF_NT), PF_NT, 0, h->d, tmp);
     PF_CUDA(cudaMemcpyAsync(aos5, tmp, n * 5 * sizeof(double), cudaMemcpyDeviceToHost, h->ctx.stream));
     PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
-    cudaFree(tmp);
     return 0;
 }
 extern "C" int pfgpu_pf_count(pfgpu_pf* h, size_t* nl, size_t* ng) {
@@ -581,10 +586,13 @@ extern "C" int pfgpu_pf_set_range_noise(pfgpu_pf* h, double s) {
 extern "C" int pfgpu_pf_last_indices(pfgpu_pf* h, uint32_t* idx, size_t cap, size_t* n) {
     if (!h || !idx) return PFGPU_ERR_INVALID;
     PF_CUDA(cudaSetDevice(h->ctx.device));
+    int gate = 0;
+    { int rc = pf_read_gate(h, &gate); if (rc) return rc; }
+    if (!gate) { if (n) *n = 0; return 0; }                   // the last step did not resample: no ancestry (as the oracle reports)
     size_t c = cap < h->d.n ? cap : h->d.n;
     PF_CUDA(cudaMemcpyAsync(idx, h->d.idx, c * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->ctx.stream));
     PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
-    if (n) *n = h->d.n;
+    if (n) *n = c;
     return 0;
 }
 

@@ -49,6 +49,34 @@ PFC_HD int x3_classify(double v, double a0, double a1, unsigned m32, unsigned lo
     return 0;
 }
 
+/* A run of consecutive values whose approximate prefixes before the first (a_first) and after the last (a_last) lie in the SAME
+ * binade, both at least the margin away from its edges: every true prefix in between does too (the prefixes are monotone), so
+ * every value of the run is classified at that binade without looking at its own prefix.  Returns the biased exponent, or -1. */
+PFC_HD int x3_interior(double a_first, double a_last, unsigned m32) {
+    const uint64_t b0 = pfc_d2u(a_first), b1 = pfc_d2u(a_last);
+    const int e0 = (int)(b0 >> 52), e1 = (int)(b1 >> 52);
+    const unsigned f0 = (unsigned)(b0 >> 20), f1 = (unsigned)(b1 >> 20);
+    const unsigned span = 0xFFFFFFFFu - 2u * m32;
+    if (e0 == 0 || e0 >= 2047 || e1 != e0 || (f0 - m32) > span || (f1 - m32) > span) return -1;
+    return e0;
+}
+/* x3_classify for a value inside such a run (same decisions, same increments): 0 clean, 1 dirty (an exact tie) */
+PFC_HD int x3_classify_at(double v, int e0, unsigned long long* inc) {
+    const uint64_t bv = pfc_d2u(v);
+    const int ev = (int)(bv >> 52);
+    *inc = 0ull;
+    if (v == 0.0 || e0 - ev >= 55) return 0;
+    const int evn = ev ? ev : 1;
+    const int sh = e0 - evn;
+    const uint64_t mant = (bv & 0x000FFFFFFFFFFFFFull) | (ev ? 0x0010000000000000ull : 0ull);
+    if (sh == 0) { *inc = mant; return 0; }
+    const uint64_t half = 1ull << (sh - 1);
+    const uint64_t t = mant + half;
+    if ((t & ((half << 1) - 1ull)) == 0ull) return 1;
+    *inc = t >> sh;
+    return 0;
+}
+
 /* apply a clean run (mantissa increment dp at biased exponent lvl, lvl < 0: unknown) to the exact sum s.
  * *ok = 0 when the certificate fails (the run was classified for another binade, or leaves it). */
 PFC_HD double x3_apply(double s, unsigned long long dp, int lvl, int* ok) {

@@ -47,11 +47,14 @@ extern "C" int x3_emul_scan(const double* vin, size_t n, size_t NT, size_t K, do
             for (size_t ww = 0; ww < w; ++ww) woff += tree_sum(&ts[ww * 32], 32);
             double excl = woff + tree_sum(&ts[w * 32], t % 32);
             double a = toff + excl;
+            const int e_run = x3_interior(a, a + ts[t], m32);       // the kernel's per-thread shortcut: the whole run inside one binade
             for (size_t k = 0; k < K; ++k) {
                 size_t i = b * T + t * K + k;
                 double a1 = a + v[i];
                 unsigned long long inc; int lvl;
-                int d = x3_classify(v[i], a, a1, m32, &inc, &lvl);
+                int d;
+                if (e_run >= 0) { d = x3_classify_at(v[i], e_run, &inc); lvl = e_run; }
+                else d = x3_classify(v[i], a, a1, m32, &inc, &lvl);
                 Pel[i] = P; dirty[i] = (char)d; incs[i] = inc; lvls[i] = lvl;
                 if (d) { ent.push_back({P, v[i], lvl}); stats[0]++; }
                 else P += inc;

@@ -241,7 +241,7 @@ def measure(rr, grp, cfg_key, K, W, rank, world, local_rank, with_e2e, sampler_c
     from rust_robotics_b200 import dist as rdist, scenarios
     cfg = CONFIGS[cfg_key]
     n_global = cfg["particles_total"] or cfg["particles_per_gpu"] * world
-    total = W + 3 * K + 4
+    total = W + 4 * K + 4
     sc = getattr(scenarios, cfg["scenario"])(steps=total)
     if os.environ.get("BENCH_EMPTY_OBS"):      # experiment: no observations (the EKF launch degenerates to predict; what does the post kernel cost then?)
         sc.obs = [[] for _ in sc.obs]
@@ -263,33 +263,44 @@ def measure(rr, grp, cfg_key, K, W, rank, world, local_rank, with_e2e, sampler_c
         g.fastslam_update(sc.control, sc.obs[step], want_flag=False, obs_array=arrs[step]); step += 1
     barrier()
     # ---- timed region 1: K steps, L2 flushed before each, one event pair per step ----
-    st0 = g.stats()
-    g.time_main_kernel(True)
-    barrier()
-    first = step
     flush_mode = os.environ.get("BENCH_FLUSH_MODE", "flush")
-    for t in range(K):
-        if flush_mode != "none":
-            g.flush_l2()
-        g.mark(2 * t)
-        g.fastslam_update(sc.control, sc.obs[step], want_flag=False, obs_array=arrs[step]); step += 1
-        g.mark(2 * t + 1)
-    barrier()
-    step_ms = [g.elapsed_ms(2 * t, 2 * t + 1) for t in range(K)]
+
+    def flushed_pass(kernel_events):
+        nonlocal step
+        s0 = g.stats()
+        g.time_main_kernel(kernel_events)
+        barrier()
+        first = step
+        for t in range(K):
+            if flush_mode != "none":
+                g.flush_l2()
+            g.mark(2 * t)
+            g.fastslam_update(sc.control, sc.obs[step], want_flag=False, obs_array=arrs[step]); step += 1
+            g.mark(2 * t + 1)
+        barrier()
+        ms = [g.elapsed_ms(2 * t, 2 * t + 1) for t in range(K)]
+        s1 = g.stats()
+        g.time_main_kernel(False)
+        return first, ms, s0, s1
+
+    # pass A: the K steps `value` is quoted on.  No events inside a step: an event pair around the EKF launch costs ~8 us per step (it
+    # breaks the programmatic dependent launch of the kernel behind it), so the kernel is timed on its own pass below.
+    first, step_ms, st0, st1 = flushed_pass(False)
     if os.environ.get("BENCH_VERBOSE") and rank == 0:
         ss = sorted(step_ms)
         sys.stderr.write("step ms: min %.3f  p50 %.3f  p90 %.3f  p99 %.3f  max %.3f  sum %.1f; worst steps %s\n" % (
             ss[0], ss[len(ss) // 2], ss[int(len(ss) * 0.9)], ss[int(len(ss) * 0.99)], ss[-1], sum(ss),
             sorted(range(K), key=lambda i: -step_ms[i])[:8]))
-    st1 = g.stats()
-    g.time_main_kernel(False)
     t_flushed = grp.max(sum(step_ms) * 1e-3)
     launches = st1.kernel_launches - st0.kernel_launches
     resamples = st1.resamples - st0.resamples
-    kernel_ms = st1.main_kernel_ms_sum / max(st1.main_kernel_count, 1)
     obs_timed = sc.obs[first:first + K]
     n_local = n_global // world
-    alg_bytes = sum(n_local * (BYTES_POSE_WEIGHT + BYTES_PER_OBS * len(z)) for z in obs_timed) / K
+    # pass B: the next K steps, same protocol, with a CUDA event pair around every launch of the dominant kernel (roofline)
+    first_b, step_ms_b, _, stb = flushed_pass(True)
+    kernel_ms = stb.main_kernel_ms_sum / max(stb.main_kernel_count, 1)
+    alg_bytes = sum(n_local * (BYTES_POSE_WEIGHT + BYTES_PER_OBS * len(z)) for z in sc.obs[first_b:first_b + K]) / K
+    t_flushed_b = grp.max(sum(step_ms_b) * 1e-3)
     # ---- timed region 2: the next K steps back to back, no flush (steady state, informational) ----
     barrier()
     g.mark(8000)
@@ -329,7 +340,7 @@ def measure(rr, grp, cfg_key, K, W, rank, world, local_rank, with_e2e, sampler_c
         sys.stderr.write("   leader chain of S (CTA 0 led %d of %d): loads=%.2f tile prefix=%.2f rank=%.2f walk+cert=%.2f publish=%.2f | clone phase per resample: bracket=%.2f stage=%.2f slots=%.2f\n" %
                          (out[21], nl, us(16, nld), us(17, nld), us(18, nld), us(19, nld), us(20, nld), us(22, nr), us(23, nr), us(6, nr)))
     res = {"cfg": cfg, "sc": sc, "n_global": n_global, "t_flushed": t_flushed, "t_noflush": t_noflush, "launches": int(launches),
-           "resamples": int(resamples), "kernel_ms": kernel_ms, "alg_bytes": alg_bytes, "obs_timed": obs_timed, "e2e": e2e,
+           "resamples": int(resamples), "kernel_ms": kernel_ms, "t_flushed_kernel_pass": t_flushed_b, "alg_bytes": alg_bytes, "obs_timed": obs_timed, "e2e": e2e,
            "serial_fallbacks": int(st1.serial_fallbacks), "K": K}
     g.close()
     return res
@@ -362,6 +373,9 @@ def run_ours(args, rank, world, local_rank):
                 "roofline": {"bound": "hbm", "kernel": "fs3_ekf_kernel (predict + per-observation EKF + weight products, fs1.rs:245-256)",
                              "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, **load_traffic(),
                              "algorithmic_bytes_per_launch": r["alg_bytes"], "avg_launch_ms": r["kernel_ms"],
+                             "timed_on": "a second pass of K flushed steps with a CUDA event pair around every launch of this kernel; those steps took "
+                                         "%.4f ms each (the event pairs break the programmatic dependent launch), so `value` is quoted on the pass without them"
+                                         % (r["t_flushed_kernel_pass"] / K * 1e3),
                              "note": "per GPU; algorithmic bytes = particles x (64 + 96 x observations of the step), SURVEY.md 8(d)"},
                 "clocks": clocks, "serial_fallbacks": r["serial_fallbacks"]}
         if second:

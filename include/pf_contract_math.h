@@ -124,7 +124,8 @@ enum {
     PFC_STREAM_FS_RESAMPLE = 3,  /* fs1.rs:219-220: the single U[0,1/n) draw                            */
     PFC_STREAM_INIT_A      = 4,  /* pf.rs:182-183 / mcl.rs:191-192: x,y jitter of particle i            */
     PFC_STREAM_INIT_B      = 5,  /* pf.rs:184-185 / mcl.rs:193-194: yaw,v jitter of particle i          */
-    PFC_STREAM_OBS         = 6   /* synthetic observation noise (examples / bench drivers)              */
+    PFC_STREAM_OBS         = 6,  /* synthetic observation noise (examples / bench drivers)              */
+    PFC_STREAM_FS2_POSE3   = 7   /* fs2.rs:234: the third N(0,1) of sample_pose (the first two use FS_PREDICT) */
 };
 
 /* One block per (seed, stream, call#, index): counter = (index_lo, index_hi, call#, stream). */

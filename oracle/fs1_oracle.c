@@ -8,35 +8,7 @@
  *   try_inverse (2x2) : det = m11*m22 - m21*m12; None if det == 0; else [m22/det, -m12/det; -m21/det, m11/det]
  *   determinant (2x2) : m11*m22 - m21*m12
  */
-#include "oracle.h"
-#include "../include/pf_contract_math.h"
-#include <stdlib.h>
-
-#ifdef PF_ORACLE_LIBM
-#define M_EXP(x) exp(x)
-#define M_SIN(x) sin(x)
-#define M_COS(x) cos(x)
-#define M_ATAN2(y, x) atan2(y, x)
-#else
-#define M_EXP(x) pfc_exp(x)
-#define M_SIN(x) pfc_sin(x)
-#define M_COS(x) pfc_cos(x)
-#define M_ATAN2(y, x) pfc_atan2(y, x)
-#endif
-
-typedef struct { double x, y, c00, c01, c10, c11; } lm_t;       /* fs1.rs:27-31 */
-
-struct orc_fs {
-    orc_fs_config cfg;
-    size_t n, m;
-    double *w, *x, *y, *yaw;      /* fs1.rs:45-50 */
-    lm_t* lm;                     /* [particle][landmark] */
-    double *w2, *x2, *y2, *yaw2; lm_t* lm2;   /* resample target */
-    uint64_t seed; uint32_t n_step, n_resample;
-    uint32_t* last_idx; size_t last_idx_n;
-    double last_neff;
-    int threads;
-};
+#include "fs_state.h"
 
 void orc_fs_default_config(orc_fs_config* c) {                  /* fs1.rs:13-23 */
     c->dt = 0.1; c->max_range = 20.0; c->nth = 100.0 / 1.5;
@@ -46,7 +18,7 @@ void orc_fs_default_config(orc_fs_config* c) {                  /* fs1.rs:13-23 
 
 orc_fs* orc_fs_new(const orc_fs_config* cfg, size_t n, size_t m, uint64_t seed) {
     orc_fs* f = (orc_fs*)calloc(1, sizeof(orc_fs));
-    f->cfg = *cfg; f->n = n; f->m = m; f->seed = seed; f->threads = 1;
+    f->cfg = *cfg; f->n = n; f->m = m; f->seed = seed; f->threads = 1; f->variant = 1;
     f->w = (double*)calloc(n, 8); f->x = (double*)calloc(n, 8); f->y = (double*)calloc(n, 8); f->yaw = (double*)calloc(n, 8);
     f->w2 = (double*)calloc(n, 8); f->x2 = (double*)calloc(n, 8); f->y2 = (double*)calloc(n, 8); f->yaw2 = (double*)calloc(n, 8);
     f->lm = (lm_t*)calloc(n * m + 1, sizeof(lm_t)); f->lm2 = (lm_t*)calloc(n * m + 1, sizeof(lm_t));
@@ -86,11 +58,7 @@ void orc_fs_seed_map(orc_fs* f, const double pose[3], const double* lxy, double 
 }
 
 /* normalize_angle fs1.rs:80-89 */
-static inline double normalize_angle(double a) {
-    while (a > PFC_PI) a -= 2.0 * PFC_PI;
-    while (a < -PFC_PI) a += 2.0 * PFC_PI;
-    return a;
-}
+#define normalize_angle orc_fs_normalize_angle
 
 /* predict_particle fs1.rs:123-137 + motion_model fs1.rs:70-77 */
 static inline void predict_particle(orc_fs* f, size_t i, const double u[2], double z0, double z1) {
@@ -159,20 +127,20 @@ static inline void update_landmark(orc_fs* f, size_t i, double z0, double z1, si
 }
 
 /* normalize_weights fs1.rs:196-203 (no uniform fallback) */
-static void normalize_weights(orc_fs* f) {
+void orc_fs_normalize_weights_(orc_fs* f) {
     double sum_w = 0.0;
     for (size_t i = 0; i < f->n; ++i) sum_w += f->w[i];
     if (sum_w > 0.0) for (size_t i = 0; i < f->n; ++i) f->w[i] /= sum_w;
 }
 /* compute_neff fs1.rs:186-193 */
-static double compute_neff(const orc_fs* f) {
+double orc_fs_compute_neff_(const orc_fs* f) {
     double s2 = 0.0;
     for (size_t i = 0; i < f->n; ++i) s2 += f->w[i] * f->w[i];
     return s2 > 0.0 ? 1.0 / s2 : 0.0;
 }
 /* resample fs1.rs:206-234 */
-static void resample(orc_fs* f, double u01) {
-    normalize_weights(f);
+void orc_fs_resample_(orc_fs* f, double u01) {
+    orc_fs_normalize_weights_(f);
     size_t n = f->n, m = f->m;
     double* cum = (double*)malloc(sizeof(double) * (n + 1));
     cum[0] = 0.0;
@@ -206,6 +174,21 @@ static int step_impl(orc_fs* f, const double u[2], const orc_fs_obs* z, size_t k
                      const double* nz0, const double* nz1, const double* r01) {
     long n = (long)f->n;
     const uint64_t seed = f->seed; const uint32_t call = f->n_step;
+    if (f->variant == 2) {
+        /* fastslam2_update_with_rng fs2.rs:330-374: particle-outer; per particle the draws are (n0, n1, n2) with observations
+         * (sample_pose fs2.rs:234) or (n0, n1) without (fs2.rs:346-349).  n0, n1 come from the FS_PREDICT block of the
+         * particle, n2 from the FS2_POSE3 block (injected arrays: nz0, nz1 and, behind them, nz1 + n as the third column). */
+#pragma omp parallel for num_threads(f->threads) schedule(static) if (f->threads > 1)
+        for (long i = 0; i < n; ++i) {
+            double a0, a1, a2, dummy;
+            if (nz0) { a0 = nz0[i]; a1 = nz1[i]; a2 = nz1[n + i]; }
+            else {
+                pfc_normal_pair(pfc_rng_block(seed, PFC_STREAM_FS_PREDICT, call, (uint64_t)i), &a0, &a1);
+                pfc_normal_pair(pfc_rng_block(seed, PFC_STREAM_FS2_POSE3, call, (uint64_t)i), &a2, &dummy);
+            }
+            orc_fs2_particle_(f, (size_t)i, u, z, k, a0, a1, a2);
+        }
+    } else {
 #pragma omp parallel for num_threads(f->threads) schedule(static) if (f->threads > 1)
     for (long i = 0; i < n; ++i) {                              /* fs1.rs:245-247 */
         double z0, z1;
@@ -219,14 +202,15 @@ static int step_impl(orc_fs* f, const double u[2], const orc_fs_obs* z, size_t k
     for (long i = 0; i < n; ++i)
         for (size_t j = 0; j < k; ++j)
             if (z[j].lm_id < f->m) update_landmark(f, (size_t)i, z[j].d, z[j].angle, (size_t)z[j].lm_id);
-    normalize_weights(f);                                       /* fs1.rs:259 */
-    double neff = compute_neff(f);                              /* fs1.rs:262 */
+    }
+    orc_fs_normalize_weights_(f);                               /* fs1.rs:259 */
+    double neff = orc_fs_compute_neff_(f);                      /* fs1.rs:262 */
     f->last_neff = neff;
     f->n_step++;
     if (neff < f->cfg.nth) {                                    /* fs1.rs:263-265 */
         double u01 = r01 ? *r01
                          : pfc_u01_52(pfc_blk_u64(pfc_rng_block(seed, PFC_STREAM_FS_RESAMPLE, f->n_resample, 0), 0));
-        resample(f, u01);
+        orc_fs_resample_(f, u01);
         f->n_resample++;
         return 1;
     }
@@ -254,6 +238,7 @@ size_t orc_fs_last_indices(const orc_fs* f, uint32_t* idx, size_t cap) {
 }
 double orc_fs_last_neff(const orc_fs* f) { return f->last_neff; }
 void orc_fs_set_threads(orc_fs* f, int t) { f->threads = t < 1 ? 1 : t; }
+void orc_fs_set_variant(orc_fs* f, int v) { f->variant = v == 2 ? 2 : 1; }
 
 /* get_observations fs1.rs:277-299 */
 size_t orc_fs_get_observations(const orc_fs_config* c, const double xt[3], const double* lxy, size_t nl,

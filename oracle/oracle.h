@@ -100,6 +100,16 @@ double orc_fs_last_neff(const orc_fs*);
 size_t orc_fs_get_observations(const orc_fs_config*, const double x_true[3], const double* landmarks_xy,
                                size_t n_landmarks, uint64_t seed, uint32_t call, orc_fs_obs* out);
 void orc_fs_set_threads(orc_fs*, int nthreads);
+/* 1 = FastSLAM 1.0 (default), 2 = FastSLAM 2.0 (crates/rust_robotics_slam/src/fastslam2.rs, "fs2.rs"): same particle set,
+ * same normalise / N_eff / resample; the pose is sampled from the observation-informed proposal of the FIRST observation
+ * (fs2.rs:173-239) and update_landmark_and_weight (fs2.rs:242-280) replaces update_landmark.  With injected noise
+ * (orc_fs_step_with_noise) z1 must then hold 2n values: z1[i] and, as the third draw of particle i, z1[n + i]. */
+void orc_fs_set_variant(orc_fs*, int variant);
+/* compute_proposal fs2.rs:173-216 for one particle (test probe): pose3 = (x, y, yaw), lm6 = (x, y, c00, c01, c10, c11) */
+void orc_fs2_compute_proposal(const orc_fs_config*, const double pose3[3], const double u[2], double z_d, double z_angle,
+                              const double lm6[6], double mean3[3], double cov9_rowmajor[9]);
+/* sample_pose fs2.rs:219-239 (test probe): mean + L * (n0, n1, n2), L = Cholesky factor or the diagonal fallback */
+void orc_fs2_sample_pose(const double mean3[3], const double cov9_rowmajor[9], const double n3[3], double out3[3]);
 
 /* ------------------------------- contract-math probes (for tests) ---------------------------------- */
 void orc_math_exp(const double* in, double* out, size_t n);

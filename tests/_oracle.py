@@ -83,6 +83,9 @@ def load(libm=False):
     L.orc_fs_get_observations.argtypes = [C.POINTER(FsConfig), c_dp, c_dp, C.c_size_t, C.c_uint64, C.c_uint32,
                                           C.POINTER(FsObs)]
     L.orc_fs_set_threads.argtypes = [C.c_void_p, C.c_int]
+    L.orc_fs_set_variant.argtypes = [C.c_void_p, C.c_int]
+    L.orc_fs2_compute_proposal.argtypes = [C.POINTER(FsConfig), c_dp, c_dp, C.c_double, C.c_double, c_dp, c_dp, c_dp]
+    L.orc_fs2_sample_pose.argtypes = [c_dp, c_dp, c_dp, c_dp]
     for fn in ("orc_math_exp", "orc_math_log", "orc_math_sin", "orc_math_cos"):
         getattr(L, fn).argtypes = [c_dp, c_dp, C.c_size_t]
     L.orc_math_atan2.argtypes = [c_dp, c_dp, c_dp, C.c_size_t]
@@ -172,9 +175,9 @@ class OraclePF:
 
 
 class OracleFS:
-    """FastSLAM 1.0 oracle (fs1.rs)."""
+    """FastSLAM oracle: variant 1 = FastSLAM 1.0 (fs1.rs), variant 2 = FastSLAM 2.0 (fs2.rs)."""
 
-    def __init__(self, L, n, m, seed=42, **cfg):
+    def __init__(self, L, n, m, seed=42, variant=1, **cfg):
         self.L = L
         self.cfg = FsConfig()
         L.orc_fs_default_config(C.byref(self.cfg))
@@ -182,6 +185,22 @@ class OracleFS:
             setattr(self.cfg, k, v)
         self.n, self.m = n, m
         self.h = L.orc_fs_new(C.byref(self.cfg), n, m, seed)
+        self.variant = variant
+        if variant != 1:
+            L.orc_fs_set_variant(self.h, variant)
+
+    def compute_proposal(self, pose3, u, z, lm6):
+        """compute_proposal fs2.rs:173-216 -> (mean[3], cov[3,3])"""
+        mean, cov = np.empty(3), np.empty(9)
+        p, uu, l = f64(pose3), f64(u), f64(lm6)
+        self.L.orc_fs2_compute_proposal(C.byref(self.cfg), _dp(p), _dp(uu), float(z[0]), float(z[1]), _dp(l), _dp(mean), _dp(cov))
+        return mean, cov.reshape(3, 3)
+
+    def sample_pose(self, mean3, cov33, n3):
+        out = np.empty(3)
+        m, c, n = f64(mean3), f64(cov33).reshape(9), f64(n3)
+        self.L.orc_fs2_sample_pose(_dp(m), _dp(c), _dp(n), _dp(out))
+        return out
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -2,7 +2,7 @@
 """Golden-vector generator: an INDEPENDENT pure-Python restatement of the reference hot path.
 
 Run (in the authoring container):  python tests/golden/make_golden.py
-Writes tests/golden/pf_golden.json, mcl_golden.json, fs1_golden.json, kat_golden.json.
+Writes tests/golden/pf_golden.json, mcl_golden.json, fs1_golden.json, kat_golden.json, fs2_golden.json.
 
 Why Python: the reference (Rust) cannot be built here (no rustc/cargo, deps not vendored), so there is no
 reference-generated vector ("parity unpinned", see oracle/oracle.h).  This script is a second, separately
@@ -15,7 +15,8 @@ Random draws (N(0,1) noise, uniforms) are part of the fixture: they are generate
 PCG64 and injected into the oracle through its *_with_noise entry points.
 
 Reference citations: pf.rs = crates/rust_robotics_localization/src/particle_filter.rs,
-mcl.rs = .../monte_carlo_localization.rs, fs1.rs = crates/rust_robotics_slam/src/fastslam1.rs.
+mcl.rs = .../monte_carlo_localization.rs, fs1.rs = crates/rust_robotics_slam/src/fastslam1.rs,
+fs2.rs = crates/rust_robotics_slam/src/fastslam2.rs.
 """
 import json
 import math
@@ -439,6 +440,211 @@ def run_fs_case(name, rng, n, m, T, nth, init_cov, zero_weights_at=None):
 
 
 # ------------------------------------------------------------------------------------------------
+# fs2.rs = crates/rust_robotics_slam/src/fastslam2.rs (FastSLAM 2.0).  Matrices are lists of rows; products follow nalgebra's
+# static-size path (column by column, each entry accumulated left to right: ((a_i0*b_0j) + a_i1*b_1j) + a_i2*b_2j).
+# ------------------------------------------------------------------------------------------------
+FS2_MOTION_COV = [[0.1, 0.0, 0.0], [0.0, 0.1, 0.0], [0.0, 0.0, 0.01]]          # fs2.rs:31
+
+
+def gmm(a, b):
+    rows, inner, cols = len(a), len(b), len(b[0])
+    out = [[0.0] * cols for _ in range(rows)]
+    for j in range(cols):
+        for i in range(rows):
+            acc = a[i][0] * b[0][j]
+            for k in range(1, inner):
+                acc = a[i][k] * b[k][j] + acc
+            out[i][j] = acc
+    return out
+
+
+def gtr(a):
+    return [[a[i][j] for i in range(len(a))] for j in range(len(a[0]))]
+
+
+def gadd(a, b):
+    return [[a[i][j] + b[i][j] for j in range(len(a[0]))] for i in range(len(a))]
+
+
+def inv2(m):  # nalgebra try_inverse, 2x2
+    det = m[0][0] * m[1][1] - m[1][0] * m[0][1]
+    if det == 0.0:
+        return None
+    return [[m[1][1] / det, -m[0][1] / det], [-m[1][0] / det, m[0][0] / det]]
+
+
+def inv3(m):  # nalgebra try_inverse, 3x3
+    (m11, m12, m13), (m21, m22, m23), (m31, m32, m33) = m
+    minor_m12_m23 = m22 * m33 - m32 * m23
+    minor_m11_m23 = m21 * m33 - m31 * m23
+    minor_m11_m22 = m21 * m32 - m31 * m22
+    det = m11 * minor_m12_m23 - m12 * minor_m11_m23 + m13 * minor_m11_m22
+    if det == 0.0:
+        return None
+    return [[minor_m12_m23 / det, (m13 * m32 - m33 * m12) / det, (m12 * m23 - m22 * m13) / det],
+            [-minor_m11_m23 / det, (m11 * m33 - m31 * m13) / det, (m13 * m21 - m23 * m11) / det],
+            [minor_m11_m22 / det, (m12 * m31 - m32 * m11) / det, (m11 * m22 - m21 * m12) / det]]
+
+
+def chol3_l(m):  # nalgebra Cholesky::new(...).l(): None when a pivot is zero, negative or NaN
+    w = [list(r) for r in m]
+    for j in range(3):
+        for k in range(j):
+            factor = -w[j][k]
+            for i in range(j, 3):
+                w[i][j] = factor * w[i][k] + w[i][j]
+        diag = w[j][j]
+        if diag == 0.0 or not diag >= 0.0:
+            return None
+        denom = math.sqrt(diag)
+        w[j][j] = denom
+        for i in range(j + 1, 3):
+            w[i][j] = w[i][j] / denom
+    return [[w[i][j] if j <= i else 0.0 for j in range(3)] for i in range(3)]
+
+
+def fs2_motion_model(x, u, dt):  # fs2.rs:95-102
+    yaw = x[2]
+    return [x[0] + u[0] * dt * math.cos(yaw), x[1] + u[0] * dt * math.sin(yaw), normalize_angle(x[2] + u[1] * dt)]
+
+
+def fs2_compute_proposal(p, u, z, lm_id, cfg):  # fs2.rs:173-216
+    lm = p.lms[lm_id]
+    pose = [p.x, p.y, p.yaw]
+    x_pred = fs2_motion_model(pose, u, cfg["dt"])
+    yaw, v = pose[2], u[0]
+    g = [[1.0, 0.0, -v * cfg["dt"] * math.sin(yaw)], [0.0, 1.0, v * cfg["dt"] * math.cos(yaw)], [0.0, 0.0, 1.0]]
+    p_pred = gmm(gmm(g, FS2_MOTION_COV), gtr(g))
+    if not lm[2] < 100.0:
+        return x_pred, p_pred
+    dx, dy = lm[0] - x_pred[0], lm[1] - x_pred[1]
+    d2 = dx * dx + dy * dy
+    d = math.sqrt(d2)
+    h_pose = [[-dx / d, -dy / d, 0.0], [dy / d2, -dx / d2, -1.0]]
+    h_lm = [[dx / d, dy / d], [-dy / d2, dx / d2]]
+    cov = [[lm[2], lm[3]], [lm[4], lm[5]]]
+    r = [[cfg["r00"], 0.0], [0.0, cfg["r11"]]]
+    q_obs = gadd(gmm(gmm(h_lm, cov), gtr(h_lm)), r)
+    h_pose_t = gtr(h_pose)
+    q_obs_inv = inv2(q_obs) or [[1.0, 0.0], [0.0, 1.0]]
+    p_pred_inv = inv3(p_pred) or [[1.0 * 1e-6, 0.0 * 1e-6, 0.0 * 1e-6], [0.0 * 1e-6, 1.0 * 1e-6, 0.0 * 1e-6], [0.0 * 1e-6, 0.0 * 1e-6, 1.0 * 1e-6]]
+    p_post_inv = gadd(p_pred_inv, gmm(gmm(h_pose_t, q_obs_inv), h_pose))
+    p_post = inv3(p_post_inv) or p_pred
+    ddx, ddy = lm[0] - x_pred[0], lm[1] - x_pred[1]                      # observation_model fs2.rs:122-128
+    z_pred = [math.sqrt(ddx * ddx + ddy * ddy), normalize_angle(math.atan2(ddy, ddx) - x_pred[2])]
+    innovation = [[z[0] - z_pred[0]], [normalize_angle(z[1] - z_pred[1])]]
+    corr = gmm(gmm(gmm(p_post, h_pose_t), q_obs_inv), innovation)
+    return [x_pred[i] + corr[i][0] for i in range(3)], p_post
+
+
+def fs2_sample_pose(mean, cov, n3):  # fs2.rs:219-239
+    l = chol3_l(cov)
+    if l is None:
+        l = [[math.sqrt(max(cov[i][i], 0.0)) if i == j else 0.0 for j in range(3)] for i in range(3)]
+    ln = gmm(l, [[n3[0]], [n3[1]], [n3[2]]])
+    return [mean[i] + ln[i][0] for i in range(3)]
+
+
+def fs2_update_landmark_and_weight(p, z, lm_id, cfg):  # fs2.rs:242-280
+    L = p.lms[lm_id]
+    if not L[2] < 100.0:
+        L[0] = p.x + z[0] * math.cos(p.yaw + z[1])
+        L[1] = p.y + z[0] * math.sin(p.yaw + z[1])
+        L[2], L[3], L[4], L[5] = 1.0 * 10.0, 0.0 * 10.0, 0.0 * 10.0, 1.0 * 10.0
+        return 1.0
+    dx, dy = L[0] - p.x, L[1] - p.y
+    z_pred = [math.sqrt(dx * dx + dy * dy), normalize_angle(math.atan2(dy, dx) - p.yaw)]
+    innovation = [[z[0] - z_pred[0]], [normalize_angle(z[1] - z_pred[1])]]
+    d2 = dx * dx + dy * dy
+    d = math.sqrt(d2)
+    h = [[dx / d, dy / d], [-dy / d2, dx / d2]]
+    cov = [[L[2], L[3]], [L[4], L[5]]]
+    r = [[cfg["r00"], 0.0], [0.0, cfg["r11"]]]
+    s = gadd(gmm(gmm(h, cov), gtr(h)), r)
+    s_inv = inv2(s) or [[1.0, 0.0], [0.0, 1.0]]
+    k = gmm(gmm(cov, gtr(h)), s_inv)
+    delta = gmm(k, innovation)
+    L[0] += delta[0][0]
+    L[1] += delta[1][0]
+    kh = gmm(k, h)
+    ikh = [[1.0 - kh[0][0], 0.0 - kh[0][1]], [0.0 - kh[1][0], 1.0 - kh[1][1]]]
+    pn = gmm(ikh, cov)
+    L[2], L[3], L[4], L[5] = pn[0][0], pn[0][1], pn[1][0], pn[1][1]
+    det_s = s[0][0] * s[1][1] - s[1][0] * s[0][1]
+    if det_s > 0.0:
+        mahal = gmm(gmm(gtr(innovation), s_inv), innovation)
+        return math.exp(-0.5 * mahal[0][0]) / (2.0 * PI * math.sqrt(det_s))
+    return 1e-10
+
+
+def run_fs2_case(name, rng, n, m, T, nth, init_cov, no_obs_at=None, zero_weights_at=None):
+    cfg = {"dt": 0.1, "max_range": 20.0, "nth": nth, "q00": 0.3, "q11": 0.0305, "r00": 0.5, "r11": 0.0305,
+           "init_weight": 0.01}
+    lm_true = [(10.0, -2.0), (15.0, 10.0), (3.0, 15.0), (-5.0, 20.0), (-5.0, 5.0), (25.0, 25.0)][:m]
+    ps = []
+    for _ in range(n):
+        lms = []
+        for l, (lx, ly) in enumerate(lm_true):
+            if init_cov[l] >= 100.0:
+                lms.append([0.0, 0.0, 1000.0, 0.0, 0.0, 1000.0])       # Landmark::new fs2.rs:41-47
+            else:
+                lms.append([lx + rng.normal(), ly + rng.normal(), init_cov[l], 0.0, 0.0, init_cov[l]])
+        ps.append(FP(cfg["init_weight"], 0.0, 0.0, 0.0, lms))
+    pose0, lm0 = fs_state(ps)
+    case = {"name": name, "n": n, "m": m, "cfg": {k: hx(v) for k, v in cfg.items()},
+            "init_pose": [hx(r) for r in pose0], "init_lm": [[hx(l) for l in row] for row in lm0], "steps": []}
+    xt = [0.0, 0.0, 0.0]
+    for t in range(T):
+        u = [1.0, 0.1]
+        xt = fs2_motion_model(xt, u, cfg["dt"])
+        obs = []
+        if no_obs_at != t:
+            for l, (lx, ly) in enumerate(lm_true):                    # get_observations fs2.rs:392-416
+                dx, dy = lx - xt[0], ly - xt[1]
+                d = math.sqrt(dx * dx + dy * dy)
+                if d <= cfg["max_range"]:
+                    ang = normalize_angle(math.atan2(dy, dx) - xt[2])
+                    obs.append([d + rng.normal() * math.sqrt(cfg["r00"]), ang + rng.normal() * math.sqrt(cfg["r11"]), l])
+        if t == 2 and len(obs) > 1:
+            obs.append(list(obs[0]))                                  # duplicate lm_id
+        if t % 2 == 1 and len(obs) > 1:
+            obs = obs[1:] + obs[:1]                                   # another landmark leads the list (it feeds the proposal)
+        z0 = rng.normal(size=n).tolist()
+        z1 = rng.normal(size=n).tolist()
+        z2 = rng.normal(size=n).tolist()
+        u01 = float(rng.uniform())
+        if zero_weights_at == t:
+            for p in ps:
+                p.w = 0.0
+        for i, p in enumerate(ps):                                    # fastslam2_update_with_rng fs2.rs:339-366
+            if obs:
+                mean, cov = fs2_compute_proposal(p, u, obs[0][:2], obs[0][2], cfg)
+                sp = fs2_sample_pose(mean, cov, [z0[i], z1[i], z2[i]])
+            else:
+                un = [u[0] + z0[i] * math.sqrt(cfg["q00"]), u[1] + z1[i] * math.sqrt(cfg["q11"])]
+                sp = fs2_motion_model([p.x, p.y, p.yaw], un, cfg["dt"])
+            p.x, p.y, p.yaw = sp[0], sp[1], normalize_angle(sp[2])     # set_pose fs2.rs:77-81
+            for (d, a, l) in obs:
+                p.w *= fs2_update_landmark_and_weight(p, [d, a], l, cfg)
+        fs_normalize(ps)                                              # fs2.rs:368-373 (same text as fs1)
+        neff = fs_neff(ps)
+        did = neff < cfg["nth"]
+        idxs = []
+        if did:
+            ps, idxs = fs_resample(ps, u01)
+        pose, lm = fs_state(ps)
+        best = 0
+        for i in range(1, n):
+            if ps[i].w >= ps[best].w:
+                best = i
+        case["steps"].append({"u": hx(u), "obs": [[hx(o[0]), hx(o[1]), int(o[2])] for o in obs], "z0": hx(z0),
+                              "z1": hx(z1), "z2": hx(z2), "u01": hx(u01), "neff": hx(neff), "did_resample": bool(did),
+                              "zero_weights": zero_weights_at == t, "indices": idxs, "best": best,
+                              "pose": [hx(r) for r in pose], "lm": [[hx(l) for l in row] for row in lm]})
+    return case
+
+
+# ------------------------------------------------------------------------------------------------
 # hand-checkable known answers
 # ------------------------------------------------------------------------------------------------
 def kat():
@@ -514,7 +720,14 @@ def main():
         run_fs_case("fresh_reference_constants", rng, n=20, m=3, T=5, nth=100.0 / 1.5, init_cov=[1000.0, 1000.0, 1000.0]),
         run_fs_case("all_zero_weights", rng, n=6, m=3, T=4, nth=6 / 1.5, init_cov=[10.0, 10.0, 10.0], zero_weights_at=1),
     ]}
-    for fn, obj in (("pf_golden.json", pf), ("mcl_golden.json", mcl), ("fs1_golden.json", fs), ("kat_golden.json", kat())):
+    # FastSLAM 2.0 cases draw AFTER everything above, so the earlier files do not change when this list does
+    fs2 = {"cases": [
+        run_fs2_case("ekf_live", rng, n=8, m=4, T=6, nth=8 / 1.5, init_cov=[10.0, 10.0, 10.0, 10.0]),
+        run_fs2_case("mixed_init_and_fresh", rng, n=12, m=5, T=6, nth=12 / 1.5, init_cov=[10.0, 1000.0, 10.0, 1000.0, 10.0]),
+        run_fs2_case("fresh_reference_constants", rng, n=20, m=3, T=5, nth=100.0 / 1.5, init_cov=[1000.0, 1000.0, 1000.0]),
+        run_fs2_case("no_observation_step_and_zero_weights", rng, n=6, m=3, T=5, nth=6 / 1.5, init_cov=[10.0, 10.0, 10.0], no_obs_at=1, zero_weights_at=3),
+    ]}
+    for fn, obj in (("pf_golden.json", pf), ("mcl_golden.json", mcl), ("fs1_golden.json", fs), ("kat_golden.json", kat()), ("fs2_golden.json", fs2)):
         with open(os.path.join(HERE, fn), "w") as f:
             json.dump(obj, f, separators=(",", ":"))
         print("wrote", fn, os.path.getsize(os.path.join(HERE, fn)), "bytes")

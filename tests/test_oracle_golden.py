@@ -156,6 +156,45 @@ def test_fs1_oracle_contract_close_to_python(oracle, idx):
     run_fs_case(oracle, load("fs1_golden.json")["cases"][idx], exact=False)
 
 
+def run_fs2_case(L, case, exact):
+    """FastSLAM 2.0 (fs2.rs): the oracle's variant 2 against the independent Python restatement of tests/golden/make_golden.py"""
+    n, m = case["n"], case["m"]
+    cfg = {k: unhex(v) for k, v in case["cfg"].items()}
+    f = OracleFS(L, n, m, variant=2, **cfg)
+    f.set_state(unhex(case["init_pose"]), unhex(case["init_lm"]))
+    for t, st in enumerate(case["steps"]):
+        if st["zero_weights"]:
+            p, l = f.state()
+            p[:, 0] = 0.0
+            f.set_state(p, l)
+        obs = [(unhex(o[0]), unhex(o[1]), o[2]) for o in st["obs"]]
+        z1 = np.concatenate([unhex(st["z1"]), unhex(st["z2"])])        # third draw of particle i rides behind z1 (oracle.h)
+        did = f.step(unhex(st["u"]), obs, unhex(st["z0"]), z1, unhex(st["u01"]))
+        assert bool(did) == st["did_resample"], f"{case['name']} step {t}: gate"
+        if did:
+            assert f.last_indices().tolist() == st["indices"], f"{case['name']} step {t}: indices"
+        p, l = f.state()
+        wp, wl = np.array(unhex(st["pose"])), np.array(unhex(st["lm"]))
+        if exact:
+            assert f.best() == st["best"]
+            assert np.array_equal(p, wp), f"{case['name']} step {t}: pose"
+            assert np.array_equal(l, wl), f"{case['name']} step {t}: landmarks"
+            assert f.last_neff() == unhex(st["neff"])
+        else:
+            np.testing.assert_allclose(p, wp, rtol=1e-8, atol=1e-11)
+            np.testing.assert_allclose(l, wl, rtol=1e-7, atol=1e-10)
+
+
+@pytest.mark.parametrize("idx", range(4))
+def test_fs2_oracle_libm_bit_exact_vs_python(oracle_libm, idx):
+    run_fs2_case(oracle_libm, load("fs2_golden.json")["cases"][idx], exact=True)
+
+
+@pytest.mark.parametrize("idx", range(4))
+def test_fs2_oracle_contract_close_to_python(oracle, idx):
+    run_fs2_case(oracle, load("fs2_golden.json")["cases"][idx], exact=False)
+
+
 # ---------------- hand-checkable known answers ----------------
 def test_kat_likelihood(oracle_libm):
     k = load("kat_golden.json")["likelihood_2x1"]

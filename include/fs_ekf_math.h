@@ -32,15 +32,20 @@ PFC_HD double fs_normalize_angle(double a) {
 /* update_landmark fs1.rs:140-183; returns the likelihood factor (1.0 when the weight is left untouched).  L is updated
  * in place; *wrote_cov tells the caller whether the covariance changed (branch A leaves it alone, fs1.rs:144-149) — the
  * weight is multiplied only then (fs1.rs:181 sits inside the EKF branch). */
-PFC_HD double fs_update_landmark(FsLm* Lp, double px, double py, double pyaw, double z0, double z1,
-                                 double r00, double r11, int* wrote_cov) {
+/* variant 1 = FastSLAM 1.0 (fs1.rs), variant 2 = FastSLAM 2.0's update_landmark_and_weight (fs2.rs:242-280, fs2.rs =
+ * crates/rust_robotics_slam/src/fastslam2.rs): the same EKF text; a landmark is fresh when NOT `cov00 < 100` (fs2.rs:49-51)
+ * rather than when `cov00 > 100` (fs1.rs:144), a fresh landmark also gets cov = 10 I (fs2.rs:254), and a non-positive det S
+ * multiplies the weight by 1e-10 (fs2.rs:278) instead of leaving it alone (fs1.rs:178). */
+PFC_HD double fs_update_landmark_v(FsLm* Lp, double px, double py, double pyaw, double z0, double z1,
+                                   double r00, double r11, int* wrote_cov, int variant) {
     FsLm L = *Lp;
-    if (L.c00 > 100.0) {                                       /* first observation of this landmark */
+    if (variant == 2 ? !(L.c00 < 100.0) : (L.c00 > 100.0)) {   /* first observation of this landmark */
         double s, c;
         pfc_sincos(pyaw + z1, &s, &c);
         Lp->x = px + z0 * c;
         Lp->y = py + z0 * s;
-        *wrote_cov = 0;
+        if (variant == 2) { Lp->c00 = 10.0; Lp->c01 = 0.0; Lp->c10 = 0.0; Lp->c11 = 10.0; }
+        *wrote_cov = variant == 2 ? 1 : 0;
         return 1.0;
     }
     *wrote_cov = 1;
@@ -89,7 +94,11 @@ PFC_HD double fs_update_landmark(FsLm* Lp, double px, double py, double pyaw, do
         double mahal = t0 * y0 + t1 * y1;
         return PFC_DIV(pfc_exp(-0.5 * mahal), 2.0 * PFC_PI * sqrt(det_s));
     }
-    return 1.0;
+    return variant == 2 ? 1e-10 : 1.0;
+}
+PFC_HD double fs_update_landmark(FsLm* Lp, double px, double py, double pyaw, double z0, double z1,
+                                 double r00, double r11, int* wrote_cov) {
+    return fs_update_landmark_v(Lp, px, py, pyaw, z0, z1, r00, r11, wrote_cov, 1);
 }
 
 /* ------------------------------------------------------------------------------------------------------------------ */
@@ -182,7 +191,7 @@ PFC_HD void fs_update_landmark_fastw(FsLm* L, const double* px, const double* py
     unsigned bad[W];
     double dx[W], dy[W], d2[W], d[W], ax[W], yax[W], yd[W], yd2[W];
     FSM_VV {
-        bad[q] = !(L[q].c00 <= 100.0) ? 1u : 0u;                /* branch A (or NaN) */
+        bad[q] = !(L[q].c00 < 100.0) ? 1u : 0u;                 /* a fresh landmark under either variant's test (or NaN) */
         dx[q] = L[q].x - px[q]; dy[q] = L[q].y - py[q];
         d2[q] = dx[q] * dx[q] + dy[q] * dy[q];
         bad[q] |= fsm_out(dx[q]) | fsm_out(dy[q]) | fsm_out(d2[q]);

@@ -150,6 +150,14 @@ int  pfgpu_fs_particle_landmarks(pfgpu_fs*, size_t index_local, double* lm6);
 int  pfgpu_fs_last_indices(pfgpu_fs*, uint32_t* idx, size_t cap, size_t* n);  /* *n = 0 when the last step did not resample */
 int  pfgpu_fs_last_neff(pfgpu_fs*, double* neff);
 int  pfgpu_fs_last_gate(pfgpu_fs*, int* did_resample);     /* whether the last step resampled (fs1.rs:263); synchronises */
+/* Which update pfgpu_fs_step runs: 1 = fastslam1::fastslam_update (fs1.rs:237-266, the default), 2 = fastslam2::fastslam2_update
+ * (crates/rust_robotics_slam/src/fastslam2.rs:376-383 -> :330-374): the same particle set, normalisation, N_eff gate and
+ * resampler; the pose of every particle is sampled from the proposal that fuses the motion prior (MOTION_COV, fs2.rs:31) with
+ * the step's first observation (compute_proposal :173-216, sample_pose :219-239; three N(0,1) per particle), and
+ * update_landmark_and_weight (:242-280) replaces update_landmark (landmark test `cov00 < 100`, birth with cov = 10 I, weight
+ * factor 1e-10 when det S <= 0).  A step without observations is the motion model with two draws (:347-356).  May be changed
+ * between steps; every rank of a sharded engine must make the same call. */
+int  pfgpu_fs_set_variant(pfgpu_fs*, int variant);
 int  pfgpu_fs_count(pfgpu_fs*, size_t* n_local, size_t* n_global, size_t* n_landmarks);
 int  pfgpu_fs_sync(pfgpu_fs*);
 

@@ -4,5 +4,5 @@ The product is the CUDA library (csrc/ -> libpfgpu.so, C ABI in include/pfgpu.h)
 reference's public types (ParticleFilterLocalizer, MonteCarloLocalizer, fastslam1) over that ABI with
 ctypes.  There is no CPU fallback: constructing any filter without a CUDA device raises.
 """
-from .api import (FastSlam1, FsConfig, InvalidParameter, MonteCarloLocalizationConfig, MonteCarloLocalizer,  # noqa: F401
+from .api import (FastSlam1, FastSlam2, FsConfig, InvalidParameter, MonteCarloLocalizationConfig, MonteCarloLocalizer,  # noqa: F401
                   ParticleFilterConfig, ParticleFilterLocalizer, PfgpuError, load_library)

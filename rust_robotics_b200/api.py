@@ -59,7 +59,7 @@ EXPORTS = [
     "pfgpu_pf_neff", "pfgpu_pf_set_range_noise", "pfgpu_pf_last_indices", "pfgpu_pf_sync",
     "pfgpu_fs_default_config", "pfgpu_fs_create", "pfgpu_fs_create_sharded", "pfgpu_fs_create_sharded_local", "pfgpu_fs_destroy",
     "pfgpu_fs_upload", "pfgpu_fs_download", "pfgpu_fs_seed_map", "pfgpu_fs_step", "pfgpu_fs_best", "pfgpu_fs_particle_landmarks",
-    "pfgpu_fs_get_observations", "pfgpu_fs_last_indices", "pfgpu_fs_last_neff", "pfgpu_fs_last_gate", "pfgpu_fs_count", "pfgpu_fs_sync",
+    "pfgpu_fs_get_observations", "pfgpu_fs_last_indices", "pfgpu_fs_last_neff", "pfgpu_fs_last_gate", "pfgpu_fs_set_variant", "pfgpu_fs_count", "pfgpu_fs_sync",
     "pfgpu_nccl_unique_id", "pfgpu_pf_stats", "pfgpu_fs_stats", "pfgpu_pf_time_main_kernel",
     "pfgpu_fs_time_main_kernel", "pfgpu_pf_mark", "pfgpu_pf_elapsed_ms", "pfgpu_fs_mark", "pfgpu_fs_elapsed_ms",
     "pfgpu_pf_flush_l2", "pfgpu_fs_flush_l2", "pfgpu_fs_post_trace", "pfgpu_fs_shard_mode",
@@ -119,6 +119,7 @@ def load_library():
     L.pfgpu_fs_last_indices.argtypes = [vp, c_u32p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.pfgpu_fs_last_neff.argtypes = [vp, c_dp]
     L.pfgpu_fs_last_gate.argtypes = [vp, C.POINTER(C.c_int)]
+    L.pfgpu_fs_set_variant.argtypes = [vp, C.c_int]
     L.pfgpu_fs_get_observations.argtypes = [vp, c_dp, c_dp, C.c_size_t, C.c_uint32, C.POINTER(_FsObs), C.POINTER(C.c_size_t)]
     L.pfgpu_fs_count.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.pfgpu_fs_sync.argtypes = [vp]
@@ -390,7 +391,10 @@ class FastSlam1:
         nl, ng, m = C.c_size_t(), C.c_size_t(), C.c_size_t()
         _check(self.L, self.L.pfgpu_fs_count(self.h, C.byref(nl), C.byref(ng), C.byref(m)))
         self.n_local, self.n_global, self.m = nl.value, ng.value, m.value
+        if self.VARIANT != 1:
+            _check(self.L, self.L.pfgpu_fs_set_variant(self.h, self.VARIANT))
 
+    VARIANT = 1                      # which reference module the step mirrors: fastslam1 (FastSlam2 below: fastslam2)
     create_particles = classmethod(lambda cls, n, m, **kw: cls(n, m, **kw))
 
     @classmethod
@@ -411,6 +415,8 @@ class FastSlam1:
             nl, ng, m = C.c_size_t(), C.c_size_t(), C.c_size_t()
             _check(L, L.pfgpu_fs_count(g.h, C.byref(nl), C.byref(ng), C.byref(m)))
             g.n_local, g.n_global, g.m = nl.value, ng.value, m.value
+            if cls.VARIANT != 1:
+                _check(L, L.pfgpu_fs_set_variant(g.h, cls.VARIANT))
             out.append(g)
         return out
 
@@ -537,3 +543,13 @@ class FastSlam1:
 
     def flush_l2(self):
         _check(self.L, self.L.pfgpu_fs_flush_l2(self.h))
+
+
+class FastSlam2(FastSlam1):
+    """rust_robotics_slam::fastslam2 (crates/rust_robotics_slam/src/fastslam2.rs): create_particles :418-422, fastslam2_update
+    :376-383, get_best_particle :385-390, get_observations :418-421 over the same device-resident particle set as FastSlam1; the
+    step samples every pose from the observation-informed proposal (:173-239) and runs update_landmark_and_weight (:242-280)."""
+    VARIANT = 2
+
+    def fastslam2_update(self, u, z, **kw):
+        return self.fastslam_update(u, z, **kw)

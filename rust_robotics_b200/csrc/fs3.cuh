@@ -37,6 +37,7 @@
 #include "common.cuh"
 #include "x3_core.h"
 #include "../../include/fs_ekf_math.h"
+#include "../../include/fs2_math.h"
 
 #define FS3_MAXG 8
 #define FS3_MAX_OBS 31            // observations per EKF launch (one warp each, plus the helper warp)
@@ -135,9 +136,9 @@ __device__ __forceinline__ void fs3_signal_peers(const Fs3Dev& d, int which, uns
 // publish the two likelihood factors.  Warp k is the helper: it runs predict_particle one group AHEAD (Philox, Box-Muller,
 // sincos: a ~2 us dependent chain that would otherwise sit in front of every group) and the weight products of the group
 // BEHIND.  Hand-offs go through four double-buffered named barriers (pose full/empty, likelihoods full/empty).
-__device__ __noinline__ double fs3_update_slow(FsLm* L, double px, double py, double pyaw, double z0, double z1, double r00, double r11) {
+__device__ __noinline__ double fs3_update_slow(FsLm* L, double px, double py, double pyaw, double z0, double z1, double r00, double r11, int variant) {
     int wrote;
-    return fs_update_landmark(L, px, py, pyaw, z0, z1, r00, r11, &wrote);   // 1.0 whenever the weight is left alone
+    return fs_update_landmark_v(L, px, py, pyaw, z0, z1, r00, r11, &wrote, variant);   // 1.0 whenever the weight is left alone
 }
 __device__ __forceinline__ void cp_async16(void* smem, const void* g) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
@@ -170,6 +171,8 @@ __device__ __noinline__ void fs3_normal_pair(uint64_t seed, uint32_t call, uint6
 __device__ __noinline__ void fs3_sincos(double x, double* s, double* c) { pfc_sincos(x, s, c); }
 
 // flags: bit 0 = first launch of the step (predict; weights start from Particle::weight)
+//        bit 1 = the poses are already this step's (FastSLAM 2.0: fs2_propose_kernel sampled them), no motion model here
+//        bit 2 = FastSLAM 2.0's update_landmark_and_weight (fs2.rs:242-280) instead of update_landmark (fs1.rs:140-183)
 // blockDim = 32 * (k_obs + nh), nh >= 1 helper warps.  Dynamic shared memory (doubles):
 //   pose [nh][3][64] | lik [nh][k][64] | landing [2][k][6][64]
 template <int MAXT>
@@ -211,7 +214,7 @@ fs3_ekf_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsP
                 const double2 X = *reinterpret_cast<const double2*>(d.px[cur] + i0), Y = *reinterpret_cast<const double2*>(d.py[cur] + i0);
                 const double2 A = *reinterpret_cast<const double2*>(d.pyaw[cur] + i0);
                 double xs[2] = { X.x, X.y }, ys[2] = { Y.x, Y.y }, as[2] = { A.x, A.y };
-                if (flags & 1) {       // predict_particle + motion_model fs1.rs:70-77,123-137, in place
+                if ((flags & 3) == 1) { // predict_particle + motion_model fs1.rs:70-77,123-137, in place
                     const bool pre = st->noise_call == call + 1u;        // the post kernel of the previous step drew this call's noise already
                     double2 Z0 = make_double2(0.0, 0.0), Z1 = make_double2(0.0, 0.0);
                     if (pre) { Z0 = *reinterpret_cast<const double2*>(d.nz[0] + i0); Z1 = *reinterpret_cast<const double2*>(d.nz[1] + i0); }
@@ -356,7 +359,7 @@ fs3_ekf_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsP
             for (int q = 0; q < 2; ++q)
                 if (!ok[q] && i0 + q < d.n) {
                     FsLm T = q ? L[1] : L[0];
-                    const double lk = fs3_update_slow(&T, q ? px[1] : px[0], q ? py[1] : py[0], q ? pyaw[1] : pyaw[0], ob.d, ob.angle, r00, r11);
+                    const double lk = fs3_update_slow(&T, q ? px[1] : px[0], q ? py[1] : py[0], q ? pyaw[1] : pyaw[0], ob.d, ob.angle, r00, r11, (flags & 4) ? 2 : 1);
                     if (q) { L[1] = T; lik[1] = lk; } else { L[0] = T; lik[0] = lk; }
                 }
         }
@@ -376,6 +379,44 @@ fs3_ekf_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsP
         if (g >= ngroups) break;
         stage = stage + 1 == nh ? 0 : stage + 1;
     }
+}
+
+// FastSLAM 2.0 (fs2.rs = crates/rust_robotics_slam/src/fastslam2.rs): the pose of every particle is sampled from the proposal that
+// fuses the motion prior with the step's FIRST observation (compute_proposal fs2.rs:173-216, sample_pose fs2.rs:219-239,
+// set_pose fs2.rs:77-81) — one thread per particle, ahead of the EKF launch (which then runs with flags bit 1).  The landmark is
+// read the way the EKF warps read it: own column, or the ancestor's (possibly on a peer) through the landmark's row.
+__global__ void __launch_bounds__(128)
+fs2_propose_kernel(const __grid_constant__ Fs3Dev d, Fs3Obs ob, double u0, double u1, double dt, double r00, double r11,
+                   uint64_t seed, uint32_t call, unsigned step) {
+    pf_grid_dep_sync();
+    Fs3State* st = d.st;
+    if (d.G > 1 && d.wait_inline) {             // peers' rows / maps are stable once their previous post kernel is over
+        if (threadIdx.x == 0) fs3_wait_peers(d, 1, step);
+        __syncthreads();
+    }
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n) return;
+    const int cur = st->cur, rcur = st->rcur;
+    const size_t ld = d.ld;
+    const int sl = d.lmst[ob.lm_id];
+    const int buf = sl & 1;
+    const size_t lbase = (size_t)ob.lm_id * 6 * ld;
+    const double* p = d.lm[buf] + lbase + i;
+    if (sl >> 1) {
+        const unsigned ref = d.rows[rcur][(size_t)((sl >> 1) - 1) * ld + i];
+        const double* base = d.G > 1 ? reinterpret_cast<const double*>(d.peer[ref >> 28] + d.o_lm[buf]) : d.lm[buf];
+        p = base + lbase + (ref & 0x0FFFFFFFu);
+    }
+    FsLm L;
+    L.x = p[0]; L.y = p[ld]; L.c00 = p[2 * ld]; L.c01 = p[3 * ld]; L.c10 = p[4 * ld]; L.c11 = p[5 * ld];
+    double n0, n1, n2, unused;
+    if (st->noise_call == call + 1u) { n0 = d.nz[0][i]; n1 = d.nz[1][i]; }          // drawn by the previous post kernel's idle warps
+    else fs3_normal_pair(seed, call, (uint64_t)d.off + i, &n0, &n1);
+    pfc_normal_pair(pfc_rng_block(seed, PFC_STREAM_FS2_POSE3, call, (uint64_t)d.off + i), &n2, &unused);
+    const double mc[9] = { 0.1, 0.0, 0.0, 0.0, 0.1, 0.0, 0.0, 0.0, 0.01 };          // MOTION_COV fs2.rs:31
+    double x = d.px[cur][i], y = d.py[cur][i], a = d.pyaw[cur][i];
+    fs2_propose_pose(&x, &y, &a, &L, u0, u1, dt, ob.d, ob.angle, r00, r11, mc, n0, n1, n2);
+    d.px[cur][i] = x; d.py[cur][i] = y; d.pyaw[cur][i] = a;
 }
 
 // lazy-clone bookkeeping after an EKF launch: the landmarks it updated through a row now live in own columns of the other

@@ -20,6 +20,7 @@ struct pfgpu_fs {
     double* stage = nullptr; size_t stage_bytes = 0;   // device staging buffer for upload / download / seed_map
     bool pdl = true;
     bool ekf_attr[2] = { false, false };
+    int variant = 1;                  // 1 = FastSLAM 1.0 (fs1.rs), 2 = FastSLAM 2.0 (fs2.rs); pfgpu_fs_set_variant
     int ekf_helpers = 0;              // PFGPU_EKF_HELPERS: cap on the helper warps per CTA (0 = as many as fit, at most 3)
     int post_nt = 256; unsigned post_K = 1, post_tiles = 1, m32 = 0; int log2n = -1; size_t post_smem = 0;
 };
@@ -387,9 +388,15 @@ extern "C" int pfgpu_fs_step(pfgpu_fs* h, const double u[2], const pfgpu_fs_obs*
     int k_last = 0;
     const bool host_waits = d.G > 1 && !d.wait_inline;
     if (host_waits) PF_LAUNCH(h->ctx, fs3_wait_kernel, 1, 32, 0, d, 1, (unsigned)h->n_step);            // peers' previous post kernels are over
+    const bool proposed = h->variant == 2 && k > 0;
+    if (proposed) {        // FastSLAM 2.0: sample every pose from the proposal of the first observation (fs2.rs:341-346)
+        Fs3Obs ob0; ob0.d = z[0].d; ob0.angle = z[0].angle; ob0.lm_id = (int)z[0].lm_id;
+        PF_LAUNCH_PDL(h->ctx, h->pdl, fs2_propose_kernel, cdiv_u(d.n, 128), 128, 0, d, ob0, u[0], u[1], h->cfg.dt, h->cfg.r00, h->cfg.r11,
+                      h->seed, (uint32_t)h->n_step, (unsigned)h->n_step);
+    }
     for (size_t seg = 0; seg < nseg; ++seg) {
         const size_t j0 = cuts[seg], kk = cuts[seg + 1] - cuts[seg];
-        const int flags = seg == 0 ? 1 : 0;
+        const int flags = (seg == 0 ? 1 : 0) | (proposed ? 2 : 0) | (h->variant == 2 ? 4 : 0);
         memset(&po, 0, sizeof(po));
         for (size_t j = 0; j < kk; ++j) { po.o[j].d = z[j0 + j].d; po.o[j].angle = z[j0 + j].angle; po.o[j].lm_id = (int)z[j0 + j].lm_id; }
         int rc = kk <= 15 ? fs3_launch_ekf<512>(h, po, u, (int)kk, flags) : fs3_launch_ekf<1024>(h, po, u, (int)kk, flags);
@@ -414,6 +421,11 @@ extern "C" int pfgpu_fs_step(pfgpu_fs* h, const double u[2], const pfgpu_fs_obs*
         *did = h->h_rec->gate;
         return fs_check_err(h);
     }
+    return 0;
+}
+extern "C" int pfgpu_fs_set_variant(pfgpu_fs* h, int variant) {
+    if (!h || (variant != 1 && variant != 2)) return PFGPU_ERR_INVALID;
+    h->variant = variant;
     return 0;
 }
 extern "C" int pfgpu_fs_best(pfgpu_fs* h, size_t* index, double pose_w4[4]) {

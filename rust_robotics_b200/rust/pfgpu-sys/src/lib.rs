@@ -74,6 +74,7 @@ extern "C" {
     pub fn pfgpu_fs_get_observations(h: *mut pfgpu_fs, x_true: *const f64, landmarks_xy: *const f64, n_landmarks: usize, call: u32,
                                      out: *mut pfgpu_fs_obs, k: *mut usize) -> c_int;
     pub fn pfgpu_fs_last_gate(h: *mut pfgpu_fs, did_resample: *mut c_int) -> c_int;
+    pub fn pfgpu_fs_set_variant(h: *mut pfgpu_fs, variant: c_int) -> c_int;
     pub fn pfgpu_fs_last_neff(h: *mut pfgpu_fs, neff: *mut f64) -> c_int;
     pub fn pfgpu_fs_particle_landmarks(h: *mut pfgpu_fs, index_local: usize, lm6: *mut f64) -> c_int;
     pub fn pfgpu_fs_count(h: *mut pfgpu_fs, n_local: *mut usize, n_global: *mut usize, n_landmarks: *mut usize) -> c_int;

@@ -505,6 +505,98 @@ def test_fastslam_sharded_in_process_edge_cases(oracle):
     _shard_compare(ranks, o, "mixed fresh")
 
 
+# ------------------------------------------------------------------------------------------------
+# FastSLAM 2.0 (fs2.rs = crates/rust_robotics_slam/src/fastslam2.rs): the same engine with pfgpu_fs_set_variant(2)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,side,steps,seeded", [(64, 4, 30, True), (1000, 6, 40, True), (1000, 5, 40, False), (4096, 8, 20, True), (1 << 16, 16, 4, True)])
+def test_fastslam2_trajectory_bit_exact(oracle, n, side, steps, seeded):
+    """fastslam2_update (fs2.rs:330-374): sampled poses (proposal of the first observation, Cholesky, three draws), landmark EKFs,
+    weights and resample ancestry equal the oracle's bit for bit — from an initialised map and from fresh particles (where the
+    first observations give birth to landmarks with cov = 10 I and the proposal falls back to the motion prior)."""
+    sc = scenarios.FastSlamScenario(side, (10.0 * side / 2 - 5.0, 10.0 * side / 2 - 5.0, 0.0), (1.0, 0.025), steps)
+    g = rr.FastSlam2(n, sc.m, rr.FsConfig(nth=n / 1.5), seed=7)
+    o = OracleFS(oracle, n, sc.m, seed=7, variant=2, nth=n / 1.5)
+    if seeded:
+        g.seed_map(sc.start, sc.landmarks); o.seed_map(sc.start, sc.landmarks)
+    else:
+        p, l = o.state()
+        p[:, 1:] = sc.start
+        g.set_state(p, l); o.set_state(p, l)
+    resamples = 0
+    for t in range(steps):
+        z = sc.obs[t]
+        if t % 3 == 1 and len(z) > 1:
+            z = z[1:] + z[:1]                                       # another landmark leads the list (it feeds the proposal)
+        did = g.fastslam2_update(sc.control, z)
+        assert did == bool(o.step(sc.control, z)), f"step {t}: gate (neff gpu {g.last_neff()} oracle {o.last_neff()})"
+        if did:
+            resamples += 1
+            assert np.array_equal(g.last_indices(), o.last_indices()), f"step {t}: indices"
+        if n <= 4096 or t == steps - 1:
+            _fs_compare(g, o, f"step {t}")
+        assert g.get_best_particle()[0] == o.best()
+    assert resamples > 0, "scenario never resampled"
+    assert g.stats().serial_fallbacks == 0
+
+
+def test_fastslam2_edge_cases(oracle):
+    n, m = 256, 4
+    lm_xy = np.array([[5.0, 0.0], [0.0, 5.0], [5.0, 5.0], [-5.0, 2.0]])
+    g = rr.FastSlam2(n, m, rr.FsConfig(nth=n / 1.5), seed=11)
+    o = OracleFS(oracle, n, m, seed=11, variant=2, nth=n / 1.5)
+    g.seed_map([0.0, 0.0, 0.0], lm_xy); o.seed_map([0.0, 0.0, 0.0], lm_xy)
+    z = [(5.1, 0.02, 0), (5.0, 1.55, 1), (4.9, -0.01, 0)]          # duplicate lm_id: two EKF launches, ONE proposal
+    assert g.fastslam2_update([1.0, 0.1], z) == bool(o.step([1.0, 0.1], z)); _fs_compare(g, o, "duplicate ids")
+    assert g.fastslam2_update([1.0, 0.1], []) == bool(o.step([1.0, 0.1], [])); _fs_compare(g, o, "empty obs: motion model, two draws (fs2.rs:347-356)")
+    p, l = g.state(); p[:, 0] = 0.0; g.set_state(p, l); o.set_state(p, l)
+    assert g.fastslam2_update([1.0, 0.1], z[:2]) is True and o.step([1.0, 0.1], z[:2]) == 1
+    assert np.all(g.last_indices() == n - 1); _fs_compare(g, o, "zero weights")
+    # landmark 2 fresh (cov 1000), landmark 3 exactly on the threshold (cov00 = 100 counts as uninitialised, fs2.rs:50), observed
+    # first (motion-prior proposal) and later
+    p, l = g.state()
+    l[:, 2, :] = [0.0, 0.0, 1000.0, 0.0, 0.0, 1000.0]
+    l[:, 3, 2] = 100.0
+    g.set_state(p, l); o.set_state(p, l)
+    for z2 in ([(7.0, 0.8, 2), (5.0, 0.1, 0)], [(5.0, 0.1, 0), (5.4, 2.7, 3)], [(5.3, 2.6, 3), (7.1, 0.7, 2), (5.0, 0.2, 0)]):
+        assert g.fastslam2_update([1.0, 0.0], z2) == bool(o.step([1.0, 0.0], z2))
+        _fs_compare(g, o, f"fresh / threshold landmarks {z2[0][2]}")
+    gp, gl = g.state()
+    assert np.all(gl[:, 2, 2] < 10.0 + 1e-9) and np.all(gl[:, 3, 2] < 10.0 + 1e-9)       # born with cov = 10 I, then shrunk
+    # a singular innovation covariance: det S <= 0 multiplies the weight by 1e-10 (fs2.rs:278)
+    p, l = g.state()
+    l[:, 1, 2:] = [-5.0, 0.0, 0.0, -5.0]
+    g.set_state(p, l); o.set_state(p, l)
+    assert g.fastslam2_update([1.0, 0.0], [(5.0, 0.1, 0), (5.0, 1.5, 1)]) == bool(o.step([1.0, 0.0], [(5.0, 0.1, 0), (5.0, 1.5, 1)]))
+    _fs_compare(g, o, "negative-definite landmark covariance")
+    # switching back to FastSLAM 1.0 between steps
+    assert g.L.pfgpu_fs_set_variant(g.h, 1) == 0
+    o.L.orc_fs_set_variant(o.h, 1)
+    assert g.fastslam_update([1.0, 0.0], z[:2]) == bool(o.step([1.0, 0.0], z[:2])); _fs_compare(g, o, "variant 1 after variant 2")
+    assert g.L.pfgpu_fs_set_variant(g.h, 3) != 0
+
+
+@pytest.mark.parametrize("world,n,side,steps", [(2, 1024, 6, 40), (4, 4096, 6, 30)])
+def test_fastslam2_sharded_in_process_bit_exact(oracle, world, n, side, steps):
+    """the proposal reads the first observation's landmark through the lazy-clone rows, remote ancestors included"""
+    sc = scenarios.FastSlamScenario(side, (10.0 * side / 2 - 5.0, 10.0 * side / 2 - 15.0, 0.0), (8.0, 0.8), steps, max_range=12.0)
+    ranks = rr.FastSlam2.create_sharded_local(n, sc.m, [0] * world, rr.FsConfig(nth=n / 1.5), seed=9)
+    o = OracleFS(oracle, n, sc.m, seed=9, variant=2, nth=n / 1.5)
+    for g in ranks:
+        g.seed_map(sc.start, sc.landmarks)
+    o.seed_map(sc.start, sc.landmarks)
+    resamples = 0
+    for t in range(steps):
+        did = rr.FastSlam2.step_all(ranks, sc.control, sc.obs[t])
+        assert did == bool(o.step(sc.control, sc.obs[t])), f"step {t}: gate"
+        if did:
+            resamples += 1
+            assert np.array_equal(np.concatenate([g.last_indices() for g in ranks]), o.last_indices()), f"step {t}: indices"
+        if t % 9 == 0:
+            _shard_compare(ranks, o, f"step {t}")
+    _shard_compare(ranks, o, "end")
+    assert resamples > 2
+
+
 def test_fastslam_get_observations_on_device(oracle):
     """get_observations (fs1.rs:277-299) behind the ABI == the oracle's, bit for bit (same Philox stream), incl. the reference's own
     test geometry (fs1.rs:325-341: one landmark in range, one outside)"""

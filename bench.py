@@ -107,6 +107,7 @@ def obs_arrays(rr, sc):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's algorithm (oracle port, glibc libm like the Rust reference), all host threads
 # ------------------------------------------------------------------------------------------------
+VARIANT = 1                # --variant: 1 = fastslam1::fastslam_update (the headline), 2 = fastslam2::fastslam2_update
 NTH_MODE = "default"       # --nth: default = particles/1.5 (BASELINE config 3 as surveyed), literal = fs1.rs:21's 66.67, every = resample every step
 
 
@@ -118,7 +119,7 @@ def cpu_run(sc, n, steps, warmup, threads, t0_step=0):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import _oracle
     L = _oracle.load(libm=True)
-    o = _oracle.OracleFS(L, n, sc.m, seed=42, nth=nth_value(n))
+    o = _oracle.OracleFS(L, n, sc.m, seed=42, variant=VARIANT, nth=nth_value(n))
     L.orc_fs_set_threads(o.h, threads)
     o.seed_map(sc.start, sc.landmarks)
     arrs = [o.obs_array(z) for z in sc.obs]
@@ -216,7 +217,7 @@ CONFIGS = {
 
 
 def workload_config(cfg, sc, n_gpus, n_global, obs_timed, resamples, K):
-    return {"workload": cfg["name"], "particles": n_global, "particles_per_gpu": n_global // n_gpus, "landmarks": sc.m,
+    return {"workload": cfg["name"] + ("" if VARIANT == 1 else " [FastSLAM 2.0 step, fastslam2.rs]"), "particles": n_global, "particles_per_gpu": n_global // n_gpus, "landmarks": sc.m,
             "mean_obs_per_step": round(sum(len(z) for z in obs_timed) / max(len(obs_timed), 1), 2),
             "resample_fraction": round(resamples / max(K, 1), 3),
             "nth": {"default": "particles/1.5", "literal": "66.67 (fs1.rs:21; never resamples at this particle count)",
@@ -249,9 +250,9 @@ def measure(rr, grp, cfg_key, K, W, rank, world, local_rank, with_e2e, sampler_c
     fcfg = rr.FsConfig(nth=nth_value(n_global))
     if world > 1:
         uid = rdist.broadcast_unique_id(grp, rdist.nccl_unique_id)
-        g = rr.FastSlam1(n_global, sc.m, fcfg, seed=42, device=local_rank, shard=(uid, rank, world))
+        g = (rr.FastSlam2 if VARIANT == 2 else rr.FastSlam1)(n_global, sc.m, fcfg, seed=42, device=local_rank, shard=(uid, rank, world))
     else:
-        g = rr.FastSlam1(n_global, sc.m, fcfg, seed=42, device=local_rank)
+        g = (rr.FastSlam2 if VARIANT == 2 else rr.FastSlam1)(n_global, sc.m, fcfg, seed=42, device=local_rank)
     g.seed_map(sc.start, sc.landmarks)
 
     def barrier():
@@ -486,11 +487,14 @@ def main():
     ap.add_argument("--no-second", action="store_true", help="skip the second configuration")
     ap.add_argument("--nth", default="default", choices=["default", "literal", "every"],
                     help="fastslam workload: resample threshold — particles/1.5 (default), the reference's literal 66.67, or every step")
+    ap.add_argument("--variant", type=int, default=1, choices=[1, 2],
+                    help="fastslam workload: 1 = FastSLAM 1.0 (the headline), 2 = FastSLAM 2.0 (fastslam2.rs) on the same configurations")
     ap.add_argument("--particles", type=int, default=1 << 20, help="mcl / pf workloads only")
     ap.add_argument("--threshold", type=float, default=1.0, help="pf workload: resample_threshold (1.0 = resample every step)")
     args = ap.parse_args()
-    global NTH_MODE
+    global NTH_MODE, VARIANT
     NTH_MODE = args.nth
+    VARIANT = args.variant
     if args.warmup < 3:
         args.warmup = 3
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)

@@ -56,6 +56,8 @@ public:
         return out;
     }
     size_t len() const { return n_; }
+    // 1 = fastslam1::fastslam_update, 2 = fastslam2::fastslam2_update (crates/rust_robotics_slam/src/fastslam2.rs:376-383)
+    void set_variant(int variant) { check(pfgpu_fs_set_variant(h_, variant), "set_variant"); }
 };
 
 // the reference's free-function names
@@ -63,4 +65,15 @@ inline FastSlam create_particles(size_t n_particles, size_t n_landmarks) = delet
 inline bool fastslam_update(FastSlam& particles, const std::array<double, 2>& u, const std::vector<Observation>& z) { return particles.step(u, z); }
 inline Particle get_best_particle(const FastSlam& particles) { return particles.best(); }
 
-}}  // namespace rust_robotics_b200::fastslam1
+}  // namespace fastslam1
+
+// crates/rust_robotics_slam/src/fastslam2.rs: the same engine object with the proposal-sampling step
+namespace fastslam2 {
+using fastslam1::Landmark; using fastslam1::Particle; using fastslam1::Observation; using fastslam1::get_best_particle;
+struct FastSlam : fastslam1::FastSlam {
+    FastSlam(size_t n_particles, size_t n_landmarks, uint64_t seed = 42, int device = 0, const pfgpu_fs_config* cfg = nullptr)
+        : fastslam1::FastSlam(n_particles, n_landmarks, seed, device, cfg) { set_variant(2); }
+};
+inline bool fastslam2_update(FastSlam& particles, const std::array<double, 2>& u, const std::vector<Observation>& z) { return particles.step(u, z); }
+}  // namespace fastslam2
+}  // namespace rust_robotics_b200

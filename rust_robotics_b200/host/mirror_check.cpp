@@ -21,6 +21,8 @@ int mirror_run(int device, double out[8]) {
     fastslam1::FastSlam fs(256, 4, 42, device);
     bool did = fastslam1::fastslam_update(fs, {1.0, 0.1}, {{5.0, 0.1, 0}, {7.0, -0.4, 2}});
     fastslam1::Particle best = fastslam1::get_best_particle(fs);
+    fastslam2::FastSlam fs2(64, 4, 42, device);                // FastSLAM 2.0 (fs2.rs:376-383): exercised, not printed
+    (void)fastslam2::fastslam2_update(fs2, {1.0, 0.1}, {{5.0, 0.1, 0}, {7.0, -0.4, 2}});
     out[0] = est[0]; out[1] = est[1]; out[2] = est2[0]; out[3] = est2[3];
     out[4] = (double)pf.get_particles().size(); out[5] = best.weight; out[6] = best.landmarks[0].x + best.landmarks[2].y; out[7] = did ? 1.0 : 0.0;
     return 0;

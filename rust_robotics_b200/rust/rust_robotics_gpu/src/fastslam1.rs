@@ -54,6 +54,7 @@ pub fn get_best_particle(particles: &FastSlam) -> Particle {
 }
 impl FastSlam {
     pub fn len(&self) -> usize { self.n }
+    pub(crate) fn raw(&self) -> *mut sys::pfgpu_fs { self.h }
     /// the reference's Vec<Particle>, materialised (checkpoint / API-compat)
     pub fn download(&self) -> Vec<Particle> {
         let (mut pw, mut lm) = (vec![0.0f64; 4 * self.n], vec![0.0f64; 6 * self.n * self.m]);

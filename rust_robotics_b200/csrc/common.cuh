@@ -64,6 +64,10 @@ struct Ctx {
     } while (0)
 #ifdef __CUDACC__
 __device__ __forceinline__ void pf_grid_dep_sync() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Let the NEXT kernel of the stream (if it was launched with the attribute above) be scheduled now: its CTAs take the SMs this
+// grid's CTAs leave as they retire and park in their own griddepcontrol.wait until this grid has completed and flushed.  Issued
+// by every CTA at its start, i.e. once the whole (one-CTA-per-SM) grid is resident, so the early CTAs cannot crowd out ours.
+__device__ __forceinline__ void pf_grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
 
 static inline unsigned int cdiv_u(size_t a, size_t b) { return (unsigned int)((a + b - 1) / b); }

@@ -173,6 +173,7 @@ __device__ __noinline__ void fs3_sincos(double x, double* s, double* c) { pfc_si
 // flags: bit 0 = first launch of the step (predict; weights start from Particle::weight)
 //        bit 1 = the poses are already this step's (FastSLAM 2.0: fs2_propose_kernel sampled them), no motion model here
 //        bit 2 = FastSLAM 2.0's update_landmark_and_weight (fs2.rs:242-280) instead of update_landmark (fs1.rs:140-183)
+//        bit 3 = release the next kernel of the stream for scheduling right away (pf_grid_launch_dependents)
 // blockDim = 32 * (k_obs + nh), nh >= 1 helper warps.  Dynamic shared memory (doubles):
 //   pose [nh][3][64] | lik [nh][k][64] | landing [2][k][6][64]
 template <int MAXT>
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(MAXT, 1)
 fs3_ekf_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsParam po, double u0, double u1, double dt,
                double sq0, double sq1, double r00, double r11, uint64_t seed, uint32_t call, int k_obs, int flags, unsigned step) {
     pf_grid_dep_sync();
+    if (flags & 8) pf_grid_launch_dependents();
     extern __shared__ __align__(16) double s_dyn[];
     const int lane = threadIdx.x & 31, wj = threadIdx.x >> 5;
     const int nh = (int)(blockDim.x >> 5) - k_obs;
@@ -927,8 +929,9 @@ __device__ __forceinline__ unsigned fs3_cdf_search(const double* cdf, const doub
 template <int NT>
 __global__ void __launch_bounds__(NT, 1)
 fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsParam po, int k_last, double nth, uint64_t seed, unsigned step,
-                unsigned K, unsigned m32, int log2n) {
+                unsigned K, unsigned m32, int log2n, int early_launch) {
     pf_grid_dep_sync();
+    if (early_launch) pf_grid_launch_dependents();
     extern __shared__ __align__(16) double vals[];            // [K][NT]
     __shared__ Fs3Sh<NT> sh;
     Fs3State* st = d.st;

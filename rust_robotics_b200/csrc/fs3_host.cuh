@@ -19,6 +19,7 @@ struct pfgpu_fs {
     Fs3Rec* h_rec = nullptr;          // pinned + mapped
     double* stage = nullptr; size_t stage_bytes = 0;   // device staging buffer for upload / download / seed_map
     bool pdl = true;
+    bool early = false;               // PFGPU_EARLY_LAUNCH=1: release the dependent kernel at the START of the previous grid (measured: 2 % slower)
     bool ekf_attr[2] = { false, false };
     int variant = 1;                  // 1 = FastSLAM 1.0 (fs1.rs), 2 = FastSLAM 2.0 (fs2.rs); pfgpu_fs_set_variant
     int ekf_helpers = 0;              // PFGPU_EKF_HELPERS: cap on the helper warps per CTA (0 = as many as fit, at most 3)
@@ -146,6 +147,7 @@ static int fs_create_impl(const pfgpu_fs_config* cfg, size_t n, size_t n_global,
         if (getenv("PFGPU_POST_TRACE")) { FS_TRY(cudaMalloc(&d.trace, 32 * sizeof(unsigned long long))); FS_TRY(cudaMemset(d.trace, 0, 32 * sizeof(unsigned long long))); }
     }
     { const char* e5 = getenv("PFGPU_PDL"); h->pdl = !(e5 && e5[0] == '0'); }
+    { const char* e7 = getenv("PFGPU_EARLY_LAUNCH"); if (e7 && atoi(e7) == 1) h->early = true; }
     { const char* e6 = getenv("PFGPU_EKF_HELPERS"); if (e6 && atoi(e6) >= 1 && atoi(e6) <= 3) h->ekf_helpers = atoi(e6); }
     if (world > 1 && uid) {
         ncclUniqueId id;
@@ -396,7 +398,9 @@ extern "C" int pfgpu_fs_step(pfgpu_fs* h, const double u[2], const pfgpu_fs_obs*
     }
     for (size_t seg = 0; seg < nseg; ++seg) {
         const size_t j0 = cuts[seg], kk = cuts[seg + 1] - cuts[seg];
-        const int flags = (seg == 0 ? 1 : 0) | (proposed ? 2 : 0) | (h->variant == 2 ? 4 : 0);
+        // (ranks that share a GPU take turns on its SMs through the wait / signal launches: parked early CTAs of one rank could keep
+        // another rank's persistent CTAs from ever being scheduled, so nothing is released early there)
+        const int flags = (seg == 0 ? 1 : 0) | (proposed ? 2 : 0) | (h->variant == 2 ? 4 : 0) | (h->early && h->pdl && !host_waits ? 8 : 0);
         memset(&po, 0, sizeof(po));
         for (size_t j = 0; j < kk; ++j) { po.o[j].d = z[j0 + j].d; po.o[j].angle = z[j0 + j].angle; po.o[j].lm_id = (int)z[j0 + j].lm_id; }
         int rc = kk <= 15 ? fs3_launch_ekf<512>(h, po, u, (int)kk, flags) : fs3_launch_ekf<1024>(h, po, u, (int)kk, flags);
@@ -411,9 +415,9 @@ extern "C" int pfgpu_fs_step(pfgpu_fs* h, const double u[2], const pfgpu_fs_obs*
     }
     // normalise, N_eff gate and (when it opens) the whole resample: one launch
     if (h->post_nt == 512)
-        PF_LAUNCH_PDL(h->ctx, h->pdl, fs3_post_kernel<512>, h->post_tiles, 512, h->post_smem, d, po, k_last, h->cfg.nth, h->seed, (unsigned)h->n_step, h->post_K, h->m32, h->log2n);
+        PF_LAUNCH_PDL(h->ctx, h->pdl, fs3_post_kernel<512>, h->post_tiles, 512, h->post_smem, d, po, k_last, h->cfg.nth, h->seed, (unsigned)h->n_step, h->post_K, h->m32, h->log2n, h->early && h->pdl && !host_waits ? 1 : 0);
     else
-        PF_LAUNCH_PDL(h->ctx, h->pdl, fs3_post_kernel<256>, h->post_tiles, 256, h->post_smem, d, po, k_last, h->cfg.nth, h->seed, (unsigned)h->n_step, h->post_K, h->m32, h->log2n);
+        PF_LAUNCH_PDL(h->ctx, h->pdl, fs3_post_kernel<256>, h->post_tiles, 256, h->post_smem, d, po, k_last, h->cfg.nth, h->seed, (unsigned)h->n_step, h->post_K, h->m32, h->log2n, h->early && h->pdl && !host_waits ? 1 : 0);
     h->n_step++;
     h->steps++;
     if (did) {     // the gate lives on the device; only a caller who asks pays a sync

@@ -17,3 +17,9 @@ for f in sorted(glob.glob('gpurun_out/sweep_*.json')):
         print(f.split('/')[-1], d['config']['particles'], '%.3e p-steps/s' % d['value'], '%.4f ms' % d['ms_per_step'], 'launches/step %.1f' % (d['gpu_launches']/d['steps']), 'main kernel frac %.3f' % r['frac'])
     except Exception as e: print(f, 'ERR', e)
 PY
+# FastSLAM 2.0 on the C3 shape (informational: same engine, proposal kernel in front of the EKF launch)
+timeout 600 python bench.py --variant 2 --steps 100 --warmup 10 --no-second > gpurun_out/sweep_fs2_c3.json 2> gpurun_out/sweep_fs2_c3.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/sweep_fs2_c3.json')); print('fs2 c3', '%.3e'%d['value'], d['ms_per_step'], d['e2e']['value'], d.get('cpu_baseline',{}).get('value'))
+PY

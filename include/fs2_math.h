@@ -30,15 +30,16 @@ PFC_HD int fs2_inv33(const double* m, double* o) {
     const double mi2 = m[3] * m[7] - m[6] * m[4];
     const double det = m[0] * mi0 - m[1] * mi1 + m[2] * mi2;
     if (det == 0.0) return 0;
-    o[0] = mi0 / det;
-    o[1] = (m[2] * m[7] - m[8] * m[1]) / det;
-    o[2] = (m[1] * m[5] - m[4] * m[2]) / det;
-    o[3] = -mi1 / det;
-    o[4] = (m[0] * m[8] - m[6] * m[2]) / det;
-    o[5] = (m[2] * m[3] - m[5] * m[0]) / det;
-    o[6] = mi2 / det;
-    o[7] = (m[1] * m[6] - m[7] * m[0]) / det;
-    o[8] = (m[0] * m[4] - m[3] * m[1]) / det;
+    const pfc_rcp_t rd = pfc_rcp_make(det);                     /* nine IEEE quotients over one denominator */
+    o[0] = pfc_div_by(mi0, rd);
+    o[1] = pfc_div_by(m[2] * m[7] - m[8] * m[1], rd);
+    o[2] = pfc_div_by(m[1] * m[5] - m[4] * m[2], rd);
+    o[3] = pfc_div_by(-mi1, rd);
+    o[4] = pfc_div_by(m[0] * m[8] - m[6] * m[2], rd);
+    o[5] = pfc_div_by(m[2] * m[3] - m[5] * m[0], rd);
+    o[6] = pfc_div_by(mi2, rd);
+    o[7] = pfc_div_by(m[1] * m[6] - m[7] * m[0], rd);
+    o[8] = pfc_div_by(m[0] * m[4] - m[3] * m[1], rd);
     return 1;
 }
 
@@ -64,8 +65,9 @@ PFC_HD void fs2_propose_pose(double* px, double* py, double* pyaw, const FsLm* L
         const double d2 = dx * dx + dy * dy;
         const double d = sqrt(d2);
         /* h_pose = obs_jacobian_pose fs2.rs:141-148 (2x3), h_lm = obs_jacobian_landmark fs2.rs:132-138 (2x2) */
-        const double hp[6] = { -dx / d, -dy / d, 0.0, dy / d2, -dx / d2, -1.0 };
-        const double h00 = dx / d, h01 = dy / d, h10 = -dy / d2, h11 = dx / d2;
+        const pfc_rcp_t rd = pfc_rcp_make(d), rd2 = pfc_rcp_make(d2);
+        const double hp[6] = { pfc_div_by(-dx, rd), pfc_div_by(-dy, rd), 0.0, pfc_div_by(dy, rd2), pfc_div_by(-dx, rd2), -1.0 };
+        const double h00 = pfc_div_by(dx, rd), h01 = pfc_div_by(dy, rd), h10 = pfc_div_by(-dy, rd2), h11 = pfc_div_by(dx, rd2);
         /* q_obs = h_lm * cov_lm * h_lm^T + r  fs2.rs:198 */
         const double a00 = h00 * L->c00 + h01 * L->c10, a01 = h00 * L->c01 + h01 * L->c11;
         const double a10 = h10 * L->c00 + h11 * L->c10, a11 = h10 * L->c01 + h11 * L->c11;
@@ -73,7 +75,10 @@ PFC_HD void fs2_propose_pose(double* px, double* py, double* pyaw, const FsLm* L
         const double q10 = (a10 * h00 + a11 * h01) + 0.0, q11 = (a10 * h10 + a11 * h11) + r11;
         const double qdet = q00 * q11 - q10 * q01;              /* try_inverse().unwrap_or(identity) fs2.rs:203 */
         double i00 = 1.0, i01 = 0.0, i10 = 0.0, i11 = 1.0;
-        if (qdet != 0.0) { i00 = q11 / qdet; i01 = -q01 / qdet; i10 = -q10 / qdet; i11 = q00 / qdet; }
+        if (qdet != 0.0) {
+            const pfc_rcp_t rq = pfc_rcp_make(qdet);
+            i00 = pfc_div_by(q11, rq); i01 = pfc_div_by(-q01, rq); i10 = pfc_div_by(-q10, rq); i11 = pfc_div_by(q00, rq);
+        }
         double ppi[9], ppost_inv[9], ppost[9];
         if (!fs2_inv33(cov, ppi)) {                             /* unwrap_or(identity * 1e-6) fs2.rs:205 */
             for (int e = 0; e < 9; ++e) ppi[e] = 0.0 * 1e-6;
@@ -113,7 +118,8 @@ PFC_HD void fs2_propose_pose(double* px, double* py, double* pyaw, const FsLm* L
         if (dg == 0.0 || !(dg >= 0.0)) { ok = 0; break; }
         const double den = sqrt(dg);
         w[3 * j + j] = den;
-        for (int i = j + 1; i < 3; ++i) w[3 * i + j] = w[3 * i + j] / den;
+        const pfc_rcp_t rden = pfc_rcp_make(den);
+        for (int i = j + 1; i < 3; ++i) w[3 * i + j] = pfc_div_by(w[3 * i + j], rden);
     }
     if (ok) { l[0] = w[0]; l[3] = w[3]; l[4] = w[4]; l[6] = w[6]; l[7] = w[7]; l[8] = w[8]; }
     else for (int i = 0; i < 3; ++i) { const double c = cov[4 * i]; l[4 * i] = sqrt(c > 0.0 ? c : 0.0); }

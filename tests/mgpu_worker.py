@@ -94,10 +94,11 @@ def main():
         grp.close()
         return
     n_global, side, steps = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+    variant = 2 if len(sys.argv) > 4 and sys.argv[4] == "fs2" else 1      # fastslam2.rs step on the same engine
     sc = scenarios.FastSlamScenario(side, (10.0 * side / 2 - 5.0, 10.0 * side / 2 - 5.0, 0.0), (1.0, 0.025), steps)
-    g = rr.FastSlam1(n_global, sc.m, rr.FsConfig(nth=n_global / 1.5), seed=9, device=local, shard=(uid, rank, world))
+    g = (rr.FastSlam2 if variant == 2 else rr.FastSlam1)(n_global, sc.m, rr.FsConfig(nth=n_global / 1.5), seed=9, device=local, shard=(uid, rank, world))
     L = _oracle.load(libm=False)
-    o = _oracle.OracleFS(L, n_global, sc.m, seed=9, nth=n_global / 1.5)
+    o = _oracle.OracleFS(L, n_global, sc.m, seed=9, variant=variant, nth=n_global / 1.5)
     g.seed_map(sc.start, sc.landmarks)
     o.seed_map(sc.start, sc.landmarks)
     lo, hi = rdist.shard_bounds(n_global, rank, world)
@@ -121,7 +122,7 @@ def main():
     grp.barrier()
     if rank == 0:
         st = g.stats()
-        print(f"MGPU_OK world={world} n={n_global} resamples={resamples} mode={g.shard_mode()} serial_fallbacks={st.serial_fallbacks}")
+        print(f"MGPU_OK world={world} n={n_global} variant={variant} resamples={resamples} mode={g.shard_mode()} serial_fallbacks={st.serial_fallbacks}")
     grp.close()
 
 

@@ -31,7 +31,9 @@ def lib(request):
     return _build(request.param)
 
 
-@pytest.mark.parametrize("kind,min_cover", [(0, 0.999), (1, 0.3), (2, 0.05)])
+# kind 2 = twelve adversarial shapes; almost all of them are outside the fast form's domain by construction (the one with cov00
+# exactly 100 left it when the fresh-landmark test became `!(cov00 < 100)`, the union of fs1.rs:144 and fs2.rs:50)
+@pytest.mark.parametrize("kind,min_cover", [(0, 0.999), (1, 0.3), (2, 0.001)])
 def test_fast_form_is_bit_identical(lib, kind, min_cover):
     o = (C.c_uint64 * 4)()
     lib.ekf_math_compare(20260924 + kind, kind, 400000, o)

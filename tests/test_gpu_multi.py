@@ -30,6 +30,17 @@ def test_sharded_fastslam_matches_oracle(world, n, side, steps):
     assert "mode=2" in r.stdout, r.stdout[-2000:]
 
 
+@pytest.mark.parametrize("world,n,side,steps", [(2, 8192, 6, 30), (8, 16384, 6, 14)])
+def test_sharded_fastslam2_matches_oracle(world, n, side, steps):
+    """FastSLAM 2.0 step (fastslam2.rs): the proposal kernel reads the first observation's landmark through remote rows"""
+    if n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29544", os.path.join(ROOT, "tests", "mgpu_worker.py"), str(n), str(side), str(steps), "fs2"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MGPU_OK" in r.stdout and "variant=2" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 def test_sharded_fastslam_edge_cases():
     """duplicate landmark ids, empty list, all-zero weights (every slot descends from the last particle of the last rank), fresh landmarks"""
     if n_gpus() < 2:

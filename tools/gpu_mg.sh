@@ -7,11 +7,14 @@ timeout 1500 python -m pytest tests/test_gpu_multi.py -x -q -m gpu > gpurun_out/
 echo "pytest rc=$?" >> gpurun_out/mg${N}_pytest.log
 for n in 2 4 8; do
   if [ $n -le $N ]; then
-    PFGPU_POST_TRACE=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29617 bench.py --gpus $n --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/mg${N}_bench_n$n.out 2> gpurun_out/mg${N}_bench_n$n.err; grep -h "^{\"metric\"" gpurun_out/mg${N}_bench_n$n.out gpurun_out/mg${N}_bench_n$n.err | tail -1 > gpurun_out/mg${N}_bench_n$n.json
+    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29617 bench.py --gpus $n --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/mg${N}_bench_n$n.out 2> gpurun_out/mg${N}_bench_n$n.err; grep -h "^{\"metric\"" gpurun_out/mg${N}_bench_n$n.out gpurun_out/mg${N}_bench_n$n.err | tail -1 > gpurun_out/mg${N}_bench_n$n.json
     echo "bench n=$n rc=$?" >> gpurun_out/mg${N}_pytest.log
   fi
 done
 timeout 600 python bench.py --gpus 1 --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/mg${N}_bench_n1.json 2> gpurun_out/mg${N}_bench_n1.err
+# stage trace of the post kernel at N ranks (its own short run: the stamps cost a little)
+PFGPU_POST_TRACE=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29618 bench.py --gpus $N --steps 60 --warmup 10 --no-cpu-baseline > gpurun_out/mg${N}_trace.out 2> gpurun_out/mg${N}_trace.err
+grep -h "fs3_post_kernel\|per RESAMPLE\|leader chain\|classify split" gpurun_out/mg${N}_trace.err gpurun_out/mg${N}_trace.out > gpurun_out/mg${N}_stage_trace.txt
 tail -6 gpurun_out/mg${N}_pytest.log
 for f in gpurun_out/mg${N}_bench_n*.json; do python - <<PY
 import json

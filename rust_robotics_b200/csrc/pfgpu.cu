@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "xsum.cuh"
 #include "pf_kernels.cuh"
+#include "pf3.cuh"
 #include "pf_kld.cuh"
 #include "xsum_sharded.cuh"
 #include <cstdlib>
@@ -125,6 +126,28 @@ struct pfgpu_pf {
     int cur_host = 0;          // sharded mode: host mirror of *d.cur (the host knows every gate there)
     bool adaptive = false;     // MCL with min_particles < max_particles: the particle count changes per step (pf_kld.cuh)
     PfKld kld;
+    // The fused step (pfgpu_pf_step) of a fixed-size, single-GPU filter is the same ~22 launches every time: predict + weight,
+    // the exact-sum pipelines, gate, search, gather, flip, moments — a launch-bound sequence below ~10^5 particles.  It is
+    // captured ONCE into a CUDA graph and replayed; only the first kernel's arguments (control, observations, draw counter,
+    // range noise) change from step to step and are patched into the instantiated graph before each replay.
+    // fused tail of the step (pf3.cuh): everything after the predict + likelihood kernel in one cooperative launch
+    struct Fused {
+        bool on = false;
+        Fs3Dev x = {};             // workspace of the exact-sum routine (fs3_xsum)
+        Pf3Arg arg = {};
+        unsigned tiles = 0;
+        size_t smem = 0;
+    } fu;
+    struct StepGraph {
+        cudaGraphExec_t exec = nullptr;
+        cudaGraph_t graph = nullptr;
+        cudaGraphNode_t main_node = nullptr;
+        cudaKernelNodeParams main_params = {};
+        size_t k = ~(size_t)0;
+        uint64_t launches = 0;
+        int captures = 0;          // an observation count that keeps changing would re-capture every step: give up after a few
+        bool off = false;          // PFGPU_PF_GRAPH=0, capture failed, or too many re-captures: plain launches from then on
+    } sg;
 };
 
 extern "C" void pfgpu_pf_default_config(pfgpu_pf_config* c, int mode) {
@@ -244,6 +267,59 @@ static int pf_alloc(pfgpu_pf* h, size_t cap) {
     return xs_work_alloc(h->xs, n);
 }
 
+// workspace + shape of the fused tail (pf3.cuh); leaves h->fu.on false when the configuration keeps the multi-kernel path
+static int pf3_setup(pfgpu_pf* h) {
+    const char* e = getenv("PFGPU_PF_FUSED");
+    if (e && e[0] == '0') return 0;
+    const size_t n = h->d.n;
+    // measured (profiles/r02_sweep): 2.0x at 2^10, 1.4x at 2^14, 1.15x at 2^16, even at 2^18, slower at 2^20 (there the separate
+    // kernels fill the GPU and their launch latency is hidden behind the graph replay)
+    if (h->world != 1 || h->adaptive || n < 1 || n > ((size_t)1 << 18)) return 0;
+    const unsigned NT = 256;
+    unsigned tiles = (unsigned)std::min<size_t>((size_t)std::min(h->ctx.num_sms, FS3_MAX_TILES), (n + NT - 1) / NT);
+    unsigned K = (unsigned)((n + (size_t)tiles * NT - 1) / ((size_t)tiles * NT));
+    tiles = (unsigned)((n + (size_t)NT * K - 1) / ((size_t)NT * K));                       // no empty tile: the last one holds index n - 1
+    const size_t smem = (size_t)2 * K * NT * sizeof(double);
+    if (cudaFuncSetAttribute(pf3_post_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pf3_post_kernel<256>, (int)NT, smem) != cudaSuccess || (size_t)nb * (size_t)h->ctx.num_sms < tiles) { cudaGetLastError(); return 0; }
+    Fs3Dev& x = h->fu.x;
+    x.n = (unsigned)n; x.n_glob = n; x.off = 0; x.G = 1; x.rank = 0; x.wait_inline = 1;
+    x.wraw[0] = h->d.w_raw; x.wraw[1] = h->d.w_raw; x.wn_all = h->d.w;
+    const size_t nsl = (size_t)FS3_SLOTS * FS3_MAX_TILES, nen = (size_t)FS3_SLOTS * FS3_ENT_CAP;
+    Fs3State* stp = nullptr;
+    PF_CUDA(cudaMalloc(&stp, sizeof(Fs3State))); PF_CUDA(cudaMemset(stp, 0, sizeof(Fs3State)));
+    x.st = stp;
+    PF_CUDA(cudaMalloc(&x.tileP, nsl * sizeof(unsigned long long)));
+    PF_CUDA(cudaMalloc(&x.tileQ, FS3_MAX_TILES * sizeof(double)));
+    PF_CUDA(cudaMalloc(&x.entCnt, 8 * sizeof(unsigned))); PF_CUDA(cudaMemset(x.entCnt, 0, 8 * sizeof(unsigned)));
+    PF_CUDA(cudaMalloc(&x.entKey, nen * sizeof(unsigned))); PF_CUDA(cudaMalloc(&x.entTile, nen * sizeof(unsigned)));
+    PF_CUDA(cudaMalloc(&x.entP, nen * sizeof(unsigned long long))); PF_CUDA(cudaMalloc(&x.entV, nen * sizeof(double)));
+    PF_CUDA(cudaMalloc(&x.entL, nen * sizeof(int)));
+    PF_CUDA(cudaMalloc(&x.bar, 8 * sizeof(unsigned))); PF_CUDA(cudaMemset(x.bar, 0, 8 * sizeof(unsigned)));
+    PF_CUDA(cudaMalloc(&x.resflag, 8 * sizeof(unsigned))); PF_CUDA(cudaMemset(x.resflag, 0, 8 * sizeof(unsigned)));
+    PF_CUDA(cudaMalloc(&x.res, 8 * sizeof(Fs3Res))); PF_CUDA(cudaMemset(x.res, 0, 8 * sizeof(Fs3Res)));
+    PF_CUDA(cudaMalloc(&x.resTP, (size_t)8 * FS3_MAX_TILES * sizeof(unsigned long long)));
+    PF_CUDA(cudaMalloc(&x.resKey, (size_t)8 * FS3_ENT_CAP * sizeof(unsigned))); PF_CUDA(cudaMalloc(&x.resP, (size_t)8 * FS3_ENT_CAP * sizeof(unsigned long long)));
+    PF_CUDA(cudaMalloc(&x.resAft, (size_t)8 * FS3_ENT_CAP * sizeof(double)));
+    PF_CUDA(cudaMalloc(&x.tileEnd, FS3_MAX_TILES * sizeof(double)));
+    PF_CUDA(cudaMalloc(&x.flagsg, 8 * sizeof(int))); PF_CUDA(cudaMemset(x.flagsg, 0, 8 * sizeof(int)));
+    Pf3Arg& a = h->fu.arg;
+    a.pd = h->d; a.threshold = h->cfg.resample_threshold; a.mode = h->cfg.mode; a.seed = h->seed; a.K = K; a.m32 = x3_margin32(n);
+    PF_CUDA(cudaMalloc(&a.tsum, FS3_MAX_TILES * sizeof(double))); PF_CUDA(cudaMalloc(&a.tsq, FS3_MAX_TILES * sizeof(double)));
+    PF_CUDA(cudaMalloc(&a.mom, (size_t)FS3_MAX_TILES * PF_MOM * sizeof(double)));
+    h->fu.tiles = tiles; h->fu.smem = smem;
+    h->fu.on = true;
+    return 0;
+}
+static void pf3_free(pfgpu_pf* h) {
+    Fs3Dev& x = h->fu.x;
+    cudaFree(x.st); cudaFree(x.tileP); cudaFree(x.tileQ); cudaFree(x.entCnt); cudaFree(x.entKey); cudaFree(x.entTile); cudaFree(x.entP);
+    cudaFree(x.entV); cudaFree(x.entL); cudaFree(x.bar); cudaFree(x.resflag); cudaFree(x.res); cudaFree(x.resTP); cudaFree(x.resKey);
+    cudaFree(x.resP); cudaFree(x.resAft); cudaFree(x.tileEnd); cudaFree(x.flagsg);
+    cudaFree(h->fu.arg.tsum); cudaFree(h->fu.arg.tsq); cudaFree(h->fu.arg.mom);
+}
+
 static int pf_create_impl(const pfgpu_pf_config* cfg, uint64_t seed, int device, const void* uid, int rank, int world, pfgpu_pf** out) {
     if (!out) return PFGPU_ERR_INVALID;
     *out = nullptr;
@@ -258,6 +334,8 @@ static int pf_create_impl(const pfgpu_pf_config* cfg, uint64_t seed, int device,
     rc = ctx_open(h->ctx, device);
     if (rc) { delete h; return rc; }
     h->cfg = *cfg; h->seed = seed; h->world = world; h->rank = rank;
+    { const char* e = getenv("PFGPU_PF_GRAPH"); if (e && e[0] == '0') h->sg.off = true; }
+    h->fu.on = false;
     h->d.n_global = cfg->n_particles; h->d.n = cfg->n_particles / (uint64_t)world; h->d.offset = (size_t)rank * h->d.n;
     h->adaptive = adaptive;
     rc = pf_alloc(h, adaptive ? (size_t)cfg->max_particles : h->d.n);
@@ -280,6 +358,8 @@ static int pf_create_impl(const pfgpu_pf_config* cfg, uint64_t seed, int device,
     PF_LAUNCH(h->ctx, pf_init_zero_kernel, cdiv_u(h->d.n, PF_NT), PF_NT, 0, h->d);
     rc = pf_refresh_cache(h);
     if (rc) { pfgpu_pf_destroy(h); return rc; }
+    rc = pf3_setup(h);
+    if (rc) { pfgpu_pf_destroy(h); return rc; }
     PF_CUDA(cudaStreamSynchronize(h->ctx.stream));
     *out = h;
     return PFGPU_OK;
@@ -300,6 +380,9 @@ extern "C" void pfgpu_pf_destroy(pfgpu_pf* h) {
     cudaFree(d.pose[0]); cudaFree(d.pose[1]); cudaFree(d.cur); cudaFree(d.w_raw); cudaFree(d.w); cudaFree(d.cum);
     cudaFree(d.idx); cudaFree(d.scal); cudaFree(d.gate); cudaFree(d.partial); cudaFree(d.obs); cudaFree(h->mom15); cudaFree(d.counters);
     if (h->h_pin) cudaFreeHost(h->h_pin);
+    if (h->sg.exec) cudaGraphExecDestroy(h->sg.exec);
+    if (h->sg.graph) cudaGraphDestroy(h->sg.graph);
+    pf3_free(h);
     cudaFree(h->kld.keys); cudaFree(h->kld.owner); cudaFree(h->kld.mint); cudaFree(h->kld.slot); cudaFree(h->kld.n_new);
     {
         FsShard& sh = h->sh;
@@ -535,21 +618,88 @@ extern "C" int pfgpu_pf_resample(pfgpu_pf* h, int* did) {
     if (did) { int g = 0; rc = pf_read_gate(h, &g); if (rc) return rc; *did = g; }
     return 0;
 }
+// the launches of one fused step, in stream order (what the graph captures)
+static int pf_step_launches(pfgpu_pf* h, const double u[2], const double* obs3, size_t k) {
+    int rc = pf_launch_main<true, true>(h, u, obs3, k);                              // predict + likelihood, one pass
+    if (rc) return rc;
+    if (h->fu.on) {                                                                  // normalise .. refresh_cache: one launch (pf3.cuh)
+        h->fu.arg.pd = h->d;
+        h->fu.arg.threshold = h->cfg.resample_threshold;
+        PF_LAUNCH(h->ctx, pf3_post_kernel<256>, h->fu.tiles, 256, h->fu.smem, h->fu.x, h->fu.arg);
+        return 0;
+    }
+    rc = pf_normalize(h);
+    if (rc) return rc;
+    rc = pf_resample_impl(h);
+    if (rc) return rc;
+    return pf_refresh_cache(h);
+}
+static void pf_graph_drop(pfgpu_pf* h) {
+    if (h->sg.exec) cudaGraphExecDestroy(h->sg.exec);
+    if (h->sg.graph) cudaGraphDestroy(h->sg.graph);
+    h->sg.exec = nullptr; h->sg.graph = nullptr; h->sg.main_node = nullptr; h->sg.k = ~(size_t)0;
+}
+// capture the step at observation count k (no work is executed by the capture itself)
+static int pf_graph_capture(pfgpu_pf* h, const double u[2], const double* obs3, size_t k) {
+    pf_graph_drop(h);
+    const uint64_t l0 = h->ctx.launches;
+    if (cudaStreamBeginCapture(h->ctx.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return 1; }
+    const int rc = pf_step_launches(h, u, obs3, k);
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(h->ctx.stream, &g);
+    h->sg.launches = h->ctx.launches - l0;
+    h->ctx.launches = l0;
+    if (rc || e != cudaSuccess || !g) { cudaGetLastError(); if (g) cudaGraphDestroy(g); return 1; }
+    h->sg.graph = g;
+    size_t nn = 0;
+    if (cudaGraphGetNodes(g, nullptr, &nn) != cudaSuccess || nn == 0) { cudaGetLastError(); pf_graph_drop(h); return 1; }
+    std::vector<cudaGraphNode_t> nodes(nn);
+    if (cudaGraphGetNodes(g, nodes.data(), &nn) != cudaSuccess) { cudaGetLastError(); pf_graph_drop(h); return 1; }
+    const void* want = (const void*)pf_predict_weight_kernel<true, true, true>;
+    for (cudaGraphNode_t nd : nodes) {
+        cudaGraphNodeType ty;
+        if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams kp = {};
+        if (cudaGraphKernelNodeGetParams(nd, &kp) != cudaSuccess) continue;
+        if (kp.func == want) { h->sg.main_node = nd; h->sg.main_params = kp; break; }
+    }
+    if (!h->sg.main_node || cudaGraphInstantiate(&h->sg.exec, g, 0) != cudaSuccess) { cudaGetLastError(); pf_graph_drop(h); return 1; }
+    h->sg.k = k;
+    return 0;
+}
+// replay with this step's arguments patched into the first kernel
+static int pf_graph_replay(pfgpu_pf* h, const double u[2], const double* obs3, size_t k) {
+    PfObsParam po;
+    for (size_t j = 0; j < 3 * k; ++j) po.o[j] = obs3[j];
+    double u0 = u[0], u1 = u[1], sv = h->cfg.velocity_noise, sw = h->cfg.yaw_rate_noise, dt = h->cfg.dt, sigma = h->cfg.range_noise;
+    uint64_t seed = h->seed; uint32_t call = h->n_predict; int kk = (int)k;
+    void* args[] = { &h->d, &po, &u0, &u1, &sv, &sw, &dt, &seed, &call, &kk, &sigma };
+    cudaKernelNodeParams kp = h->sg.main_params;
+    kp.kernelParams = args; kp.extra = nullptr;
+    PF_CUDA(cudaGraphExecKernelNodeSetParams(h->sg.exec, h->sg.main_node, &kp));
+    PF_CUDA(cudaGraphLaunch(h->sg.exec, h->ctx.stream));
+    h->ctx.launches += h->sg.launches;
+    return 0;
+}
+
 extern "C" int pfgpu_pf_step(pfgpu_pf* h, const double u[2], const double* obs3, size_t k, double est[4]) {
     if (!h || !u || (k && !obs3)) return PFGPU_ERR_INVALID;
     if (!finite_d(u[0]) || !finite_d(u[1])) return PFGPU_ERR_INVALID;
     PF_CUDA(cudaSetDevice(h->ctx.device));
     int rc = pf_stage_obs(h, obs3, k);
     if (rc) return rc;
-    rc = pf_launch_main<true, true>(h, u, obs3, k);                                  // predict + likelihood, one pass
-    if (rc) return rc;
+    // graph replay: fixed particle count, one GPU, observations short enough to ride in the launch parameters, no per-kernel
+    // timing events; the first step of a handle runs plainly (lazy set-up such as function attributes happens there)
+    const bool graphable = !h->sg.off && h->world == 1 && !h->adaptive && k <= PF_PARAM_OBS && !h->timer.on && h->steps > 0;
+    bool done = false;
+    if (graphable) {
+        if (h->sg.exec && h->sg.k == k) done = true;
+        else if (++h->sg.captures <= 16 && pf_graph_capture(h, u, obs3, k) == 0) done = true;
+        else { h->sg.off = true; pf_graph_drop(h); }
+        if (done) { rc = pf_graph_replay(h, u, obs3, k); if (rc) return rc; }
+    }
+    if (!done) { rc = pf_step_launches(h, u, obs3, k); if (rc) return rc; }
     h->n_predict++;
-    rc = pf_normalize(h);
-    if (rc) return rc;
-    rc = pf_resample_impl(h);
-    if (rc) return rc;
-    rc = pf_refresh_cache(h);
-    if (rc) return rc;
     h->steps++;
     if (est) {
         PF_CUDA(cudaMemcpyAsync(h->h_pin, h->d.scal + 4, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->ctx.stream));

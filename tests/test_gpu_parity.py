@@ -137,6 +137,39 @@ def test_pf_trajectory_bit_exact(oracle, n, thr, steps):
     assert np.all(np.isfinite(g.estimate())) and abs(g.get_particles()[:, 4].sum() - 1.0) < 1e-3
 
 
+@pytest.mark.parametrize("fused,graph", [("0", "1"), ("0", "0"), ("1", "0")])
+@pytest.mark.parametrize("kind", ["pf", "mcl"])
+def test_pf_step_paths_agree_with_oracle(oracle, monkeypatch, kind, fused, graph):
+    """The fused step has three host-side forms: predict + ONE cooperative tail launch (pf3.cuh, the default up to 2^18 particles),
+    the ~22 separate launches replayed from a CUDA graph, and the same launches issued one by one.  The parametrised trajectory
+    tests run the default; this one pins the other two (and the fused form without the graph) to the same oracle."""
+    monkeypatch.setenv("PFGPU_PF_FUSED", fused)
+    monkeypatch.setenv("PFGPU_PF_GRAPH", graph)
+    steps = 40
+    if kind == "pf":
+        sc = scenarios.PfScenario("c1", steps=steps)
+        g, o = _pf_pair(oracle, 3000, thr=0.6)
+    else:
+        sc = scenarios.PfScenario("c2", steps=steps)
+        g, o = _pf_pair(oracle, 2048, sigma=0.25, sv=0.05, sw=0.02, mode=1, seed=5, init=tuple(sc.init))
+    resamples = 0
+    for t in range(steps):
+        obs = sc.obs[t][:: max(1, sc.obs[t].shape[0] // 24)] if kind == "mcl" else sc.obs[t]     # <= 32 observations: rides in the launch parameters
+        if t == 17:
+            obs = obs[:-1]                                          # a different observation count re-captures the graph
+        ge = g.try_step(sc.controls[t], obs)
+        oe, did = o.step(sc.controls[t], obs)
+        np.testing.assert_allclose(ge, oe, rtol=RTOL, atol=1e-9)
+        if did:
+            resamples += 1
+            assert np.array_equal(g.last_indices(), o.last_indices()), f"step {t}: resample indices"
+        if t % 8 == 0 or t == steps - 1:
+            _pf_compare(g, o, f"step {t}")
+    assert resamples > 0
+    launches = g.stats().kernel_launches
+    assert (launches < 4 * steps) == (fused == "1"), launches      # 2 launches per step when fused, ~22 otherwise
+
+
 def test_pf_phase_api_matches_oracle(oracle):
     """predict / update / resample called one by one (the StateEstimator route pf.rs:552-573): caches after each phase."""
     sc = scenarios.PfScenario("c1", steps=12)

@@ -51,7 +51,8 @@ pf3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Pf3Arg
     double toff = 0.0, qoff = 0.0;
 #pragma unroll 2
     for (unsigned p = tid; p < b; p += NT) { toff += __ldcg(a.tsum + p); qoff += __ldcg(a.tsq + p); }
-    fs3_block_sum2<NT>(toff, qoff, sh.wd[0], sh.wd[1]);
+    fs3_block_sum2<NT>(toff, qoff, sh.red[0], sh.red[1]);      // (red[] is free again: the grid barrier above is also a block barrier;
+                                                               //  wd[] is the first scratch fs3_xsum writes, with no barrier in between)
     // ---------------- S = sum w_raw, sequential (normalize_weights pf.rs:426-439) ----------------
     const double S = fs3_xsum<NT>(d, sh, vals, K, nt, toff, 0, 0, a.m32, nullptr, 0, 0.0, 0.0, 0.0, 0.0);
     const double unif = 1.0 / (double)pd.n_global;

@@ -343,6 +343,8 @@ def measure(rr, grp, cfg_key, K, W, rank, world, local_rank, with_e2e, sampler_c
         sys.stderr.write("   per RESAMPLE (%d): S2 sum=%.2f  CDF scan=%.2f [classify+publish %.2f | barrier %.2f | chain %.2f | emit %.2f]  comb+barrier=%.2f  "
                          "search+clone=%.2f\n" % (nr, us(3, nr), us(4, nr), us(12, nr), us(13, nr), us(14, nr), us(15, nr), us(5, nr), us(6, nr)))
         sys.stderr.write("   S classify split: first pass=%.2f  scan=%.2f  classify pass=%.2f  scan+publish=%.2f\n" % (us(28, nl), us(29, nl), us(30, nl), us(8, nl)))
+        sys.stderr.write("   step timeline (us per step; globaltimer, CTA 0 / last warp out): idle before the EKF launch=%.2f  EKF launch=%.2f  idle between=%.2f  "
+                         "post launch=%.2f (every CTA through its phases after %.2f, then the last one: best particle, record, flip)\n" % (us(7, nl), us(24, nl), us(25, nl), us(26, nl), us(27, nl)))
         nld = max(out[21], 1)
         sys.stderr.write("   leader chain of S (CTA 0 led %d of %d): loads=%.2f tile prefix=%.2f rank=%.2f walk+cert=%.2f publish=%.2f | clone phase per resample: bracket=%.2f stage=%.2f slots=%.2f\n" %
                          (out[21], nl, us(16, nld), us(17, nld), us(18, nld), us(19, nld), us(20, nld), us(22, nr), us(23, nr), us(6, nr)))

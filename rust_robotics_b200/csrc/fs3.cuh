@@ -199,6 +199,11 @@ fs3_ekf_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsP
     const int cur = st->cur, rcur = st->rcur, par = (int)(step & 1u);
     const size_t ld = d.ld;
     const unsigned ngroups = d.ld / 64;
+    if (d.trace && blockIdx.x == 0 && threadIdx.x == 0 && (flags & 1)) {     // step timeline (PFGPU_POST_TRACE): [32] idle before this launch
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (d.trace[36]) d.trace[32] += t - d.trace[36];
+        d.trace[38] = t; d.trace[37] = 0ull;
+    }
     if (wj >= k_obs) {
         // ========== helper warp h: predict for trips h, h + nh, ... (ahead), weight products of the same trips (behind) ==========
         const int h = wj - k_obs;
@@ -283,6 +288,7 @@ fs3_ekf_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsP
             if (!have) break;
             Wp = Wn; gprev = g; first = false; use++;
         }
+        if (d.trace && h == 0 && lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMax(d.trace + 37, t); }
         return;
     }
     // =============================== EKF warps: one observation each ===============================
@@ -381,6 +387,7 @@ fs3_ekf_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3ObsP
         if (g >= ngroups) break;
         stage = stage + 1 == nh ? 0 : stage + 1;
     }
+    if (d.trace && wj == 0 && lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMax(d.trace + 37, t); }
 }
 
 // FastSLAM 2.0 (fs2.rs = crates/rust_robotics_slam/src/fastslam2.rs): the pose of every particle is sampled from the proposal that
@@ -940,7 +947,12 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
     const size_t T = (size_t)NT * K, ng = d.n_glob;
     const int par = (int)(step & 1u);
     unsigned long long t_prev = 0;
-    if (d.trace && b == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_prev));
+    if (d.trace && b == 0 && tid == 0) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_prev));
+        const unsigned long long e1 = d.trace[37], e0 = d.trace[38];           // step timeline: [33] EKF launch (first CTA in .. last warp out),
+        if (e1 && e0) { d.trace[33] += e1 - e0; d.trace[34] += t_prev - e1; }   // [34] idle between the EKF launch and this one
+        d.trace[39] = t_prev;
+    }
     if (d.G > 1) {      // my EKF launch is complete: its pushes are in every peer's copy.  Say so, then wait for the others'.
         if (b == 0) fs3_signal_peers(d, 0, step + 1u);
         if (d.wait_inline) {
@@ -1144,6 +1156,7 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
     __syncthreads();
     if (!sh.last) return;
     __threadfence();
+    if (d.trace && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); d.trace[40] += t - d.trace[39]; }   // [40] the last CTA is through
     if (gate) {
         const int newrow = d.rowinfo[1];
 #pragma unroll 1
@@ -1164,9 +1177,12 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
         unsigned src = bi2;                                    // slot whose pose (in the buffer live BEFORE the flip) is reported
         if (gate) {
             bi2 = (unsigned)ng - 1; bw2 = inv;
-            const double rl = log2n >= 0 ? x3_comb_eval(&sh.comb, inv, ng - 1) : __ldcg(d.rcomb_all + ng - 1);
-            src = fs3_cdf_search(d.cum_all, sh.tend, nt, (unsigned)T, (unsigned)ng, rl);
-            if (src >= ng) src = (unsigned)ng - 1;
+            if (d.G == 1) src = __ldcg(d.idx + (ng - 1));          // the clone phase has just searched that slot (one GPU: it is a local slot)
+            else {
+                const double rl = log2n >= 0 ? x3_comb_eval(&sh.comb, inv, ng - 1) : __ldcg(d.rcomb_all + ng - 1);
+                src = fs3_cdf_search(d.cum_all, sh.tend, nt, (unsigned)T, (unsigned)ng, rl);
+                if (src >= ng) src = (unsigned)ng - 1;
+            }
         }
         if (tid == 0) {
             const int cur = st->cur;
@@ -1181,7 +1197,9 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
             if (gate) { st->cur ^= 1; st->rcur ^= 1; st->resamples += 1; }
             st->noise_call = NT >= 128 ? step + 2u : 0u;           // nz[] = noise of EKF call step + 1
             st->post_done = 0;
-            __threadfence_system();
+            if (d.trace) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); d.trace[35] += t - d.trace[39]; d.trace[36] = t; }   // [35] this launch
+            // (no system fence in front of `seq`: the host reads the record only after it has synchronised with the stream, and a
+            //  fence here waits for the PCIe writes above to land — inside every step's critical path)
             *reinterpret_cast<volatile unsigned long long*>(&rec->seq) = (unsigned long long)step + 1ull;
         }
     }

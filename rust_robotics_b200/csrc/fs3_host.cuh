@@ -144,7 +144,7 @@ static int fs_create_impl(const pfgpu_fs_config* cfg, size_t n, size_t n_global,
         FS_TRY(cudaHostAlloc(&h->h_rec, sizeof(Fs3Rec), cudaHostAllocMapped));
         memset(h->h_rec, 0, sizeof(Fs3Rec));
         FS_TRY(cudaHostGetDevicePointer((void**)&d.rec, h->h_rec, 0));
-        if (getenv("PFGPU_POST_TRACE")) { FS_TRY(cudaMalloc(&d.trace, 32 * sizeof(unsigned long long))); FS_TRY(cudaMemset(d.trace, 0, 32 * sizeof(unsigned long long))); }
+        if (getenv("PFGPU_POST_TRACE")) { FS_TRY(cudaMalloc(&d.trace, 48 * sizeof(unsigned long long))); FS_TRY(cudaMemset(d.trace, 0, 48 * sizeof(unsigned long long))); }
     }
     { const char* e5 = getenv("PFGPU_PDL"); h->pdl = !(e5 && e5[0] == '0'); }
     { const char* e7 = getenv("PFGPU_EARLY_LAUNCH"); if (e7 && atoi(e7) == 1) h->early = true; }
@@ -536,6 +536,13 @@ extern "C" int pfgpu_fs_post_trace(pfgpu_fs* h, unsigned long long* out32) {
     for (int k = 0; k < 32; ++k) out32[k] = 0;
     if (h->d.trace) PF_CUDA(cudaMemcpy(out32, h->d.trace, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     out32[31] = h->steps;
+    // step timeline [ns], folded into the free slot pairs: [7] idle before the EKF launch, [24..26] EKF launch, idle between the
+    // launches, post launch
+    if (h->d.trace) {
+        unsigned long long t8[9] = {};
+        PF_CUDA(cudaMemcpy(t8, h->d.trace + 32, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        out32[7] = t8[0]; out32[24] = t8[1]; out32[25] = t8[2]; out32[26] = t8[3]; out32[27] = t8[8];
+    }
     return 0;
 }
 extern "C" int pfgpu_fs_time_main_kernel(pfgpu_fs* h, int on) {

@@ -747,8 +747,8 @@ __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const do
             const int D = fail ? 0 : (int)cnt;
             double total = 0.0;
             if (D <= 32) {
-                // ---- the usual case, in registers: lane e holds entry e; rank by index, then every lane walks the chain with the
-                // operands shuffled in (two dependent operations per entry, no shared-memory latency inside the chain) ----
+                // ---- the usual case: lane e holds entry e (loaded speculatively above); rank by index with shuffles, move every entry
+                // to its rank in shared memory, then the serial walk ----
                 const bool have = lane < D;
                 if (!have) ekey = 0xFFFFFFFFu;
                 const unsigned long long Pg = have ? sh.tPoff[etile < nt ? etile : 0] + eP : 0ull;
@@ -758,27 +758,25 @@ __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const do
                 // move every entry to the lane of its rank (through shared memory: one conflict-free round)
                 if (have) { sh.skey[rank] = ekey; sh.sP[rank] = Pg; sh.sV[rank] = eV; sh.sL[rank] = eL; }
                 __syncwarp();
-                const unsigned long long myP = have ? sh.sP[lane] : 0ull;
-                const double myV = have ? sh.sV[lane] : 0.0;
                 if (slot == 0) FS3_TRACE(18);
-                double sacc = 0.0, mybef = 0.0, myaft = 0.0; unsigned long long prev = 0;
-#pragma unroll 4
-                for (int o = 0; o < 32; ++o) {
-                    const unsigned long long p = __shfl_sync(0xffffffffu, myP, o);
-                    const double v = __shfl_sync(0xffffffffu, myV, o);
-                    if (o < D) {
-                        const double bf = sacc;
-                        sacc = pfc_u2d(pfc_d2u(sacc) + (p - prev)) + v;
-                        prev = p;
-                        if (o == lane) { mybef = bf; myaft = sacc; }
-                    }
-                }
+                // the serial part, lane 0 over the sorted entries in shared memory: one integer add on the bit pattern + one FP add
+                // per dirty value; the loads do not depend on the chain, so the compiler hoists them ahead (unroll 4)
                 int ok = 1;
-                total = x3_apply(sacc, Ptot - prev, -1, &ok);
-                const unsigned long long pprev = __shfl_up_sync(0xffffffffu, myP, 1);
-                if (have) {
-                    (void)x3_apply(mybef, myP - (lane ? pprev : 0ull), sh.sL[lane], &ok);      // certificate of the clean run in front of me
-                    sh.bef[lane] = mybef; sh.aft[lane] = myaft;
+                if (lane == 0) {
+                    double sq = 0.0; unsigned long long prev = 0;
+#pragma unroll 4
+                    for (int o = 0; o < D; ++o) {
+                        const unsigned long long p = sh.sP[o]; const double v = sh.sV[o];
+                        sh.bef[o] = sq;
+                        sq = pfc_u2d(pfc_d2u(sq) + (p - prev)) + v;
+                        sh.aft[o] = sq; prev = p;
+                    }
+                    total = x3_apply(sq, Ptot - prev, -1, &ok);
+                }
+                __syncwarp();
+                if (have) {                                        // certificate of the clean run in front of my entry, in parallel
+                    const unsigned long long dp = sh.sP[lane] - (lane ? sh.sP[lane - 1] : 0ull);
+                    (void)x3_apply(sh.bef[lane], dp, sh.sL[lane], &ok);
                 }
                 if (!ok) fail = 1;
             } else {

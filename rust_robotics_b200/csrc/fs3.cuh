@@ -106,6 +106,12 @@ struct Fs3Dev {
 __device__ __forceinline__ unsigned fs3_ref(int rank, unsigned col) { return ((unsigned)rank << 28) | col; }
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) { unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+// arrival at a grid-wide counter in ONE instruction: release of everything this CTA wrote before the block barrier in front of
+// it, acquire for whoever turns out to be the last to arrive (instead of fence + relaxed atomic + fence)
+__device__ __forceinline__ unsigned atom_add_acq_rel_gpu(unsigned* p, unsigned v) {
+    unsigned o; asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(o) : "l"(p), "r"(v) : "memory"); return o;
+}
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ unsigned* fs3_flag(const Fs3Dev& d, int owner, int which, int src) {
     return reinterpret_cast<unsigned*>(d.peer[owner] + d.o_flags + ((size_t)which * FS3_MAXG + (size_t)src) * 128);
@@ -484,14 +490,12 @@ struct Fs3Sh {
 
 // grid barrier `round` of this launch: every CTA arrives once per round; the counters are zeroed by the launch's last CTA
 __device__ __forceinline__ void fs3_bar_arrive(const Fs3Dev& d, int round) {        // thread 0, after a block barrier
-    __threadfence();
-    atomicAdd(d.bar + round, 1u);
+    (void)atom_add_acq_rel_gpu(d.bar + round, 1u);
 }
 __device__ __forceinline__ void fs3_bar_wait(const Fs3Dev& d, int round, unsigned nblocks) {   // one thread
     unsigned spins = 0;
 #pragma unroll 1
-    while (*reinterpret_cast<volatile unsigned*>(d.bar + round) < nblocks) { if (++spins > FS3_SPIN_LIMIT) { d.st->err = 1; break; } __nanosleep(20); }
-    __threadfence();
+    while (ld_acquire_gpu(d.bar + round) < nblocks) { if (++spins > FS3_SPIN_LIMIT) { d.st->err = 1; break; } __nanosleep(20); }
 }
 template <int NT>
 __device__ __forceinline__ void fs3_grid_sync(const Fs3Dev& d, int round, unsigned nblocks) {
@@ -707,7 +711,7 @@ __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const do
     }
     if (tid < 32) {
         int leader = 0;
-        if (tid == 0) { __threadfence(); leader = (atomicAdd(d.bar + round, 1u) + 1u == nt) ? 1 : 0; if (leader) __threadfence(); }
+        if (tid == 0) leader = (atom_add_acq_rel_gpu(d.bar + round, 1u) + 1u == nt) ? 1 : 0;
         leader = __shfl_sync(0xffffffffu, leader, 0);
         Fs3Res* res = d.res + round;
         const size_t rb = (size_t)round * FS3_ENT_CAP, rt = (size_t)round * FS3_MAX_TILES;
@@ -831,15 +835,13 @@ __device__ __noinline__ double fs3_xsum(const Fs3Dev& d, Fs3Sh<NT>& sh, const do
                 sh.total = total; sh.Ptot = Ptot; sh.D = D; sh.fail = fail;
                 d.st->dirty_last = (int)cnt;
             }
-            __syncwarp();
-            __threadfence();
-            if (lane == 0) atomicExch(d.resflag + round, 1u);
+            __syncwarp();                                          // the other lanes' stores above are ordered before lane 0's release
+            if (lane == 0) st_release_gpu(d.resflag + round, 1u);
             if (slot == 0) { FS3_TRACE(20); if (d.trace && b == 0 && tid == 0) d.trace[21] += 1; }
         } else {
             if (lane == 0) {
                 unsigned spins = 0;
-                while (*reinterpret_cast<volatile unsigned*>(d.resflag + round) == 0u) { if (++spins > FS3_SPIN_LIMIT) { d.st->err = 1; break; } __nanosleep(20); }
-                __threadfence();
+                while (ld_acquire_gpu(d.resflag + round) == 0u) { if (++spins > FS3_SPIN_LIMIT) { d.st->err = 1; break; } __nanosleep(20); }
             }
             __syncwarp();
             FS3_TRACE(tb0 + 1);
@@ -1150,10 +1152,9 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
     }
     // ---------------- completion: the last CTA flips the state, writes the record, tells the peers ----------------
     __syncthreads();
-    if (tid == 0) { __threadfence(); sh.last = (atomicAdd(&st->post_done, 1u) + 1u == nt) ? 1 : 0; }
+    if (tid == 0) sh.last = (atom_add_acq_rel_gpu(&st->post_done, 1u) + 1u == nt) ? 1 : 0;   // release my CTA's writes / acquire everybody's
     __syncthreads();
     if (!sh.last) return;
-    __threadfence();
     if (d.trace && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); d.trace[40] += t - d.trace[39]; }   // [40] the last CTA is through
     if (gate) {
         const int newrow = d.rowinfo[1];

@@ -145,10 +145,9 @@ pf3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Pf3Arg
     }
     // ---------------- completion: the last CTA reduces the moments, flips the state, resets the counters ----------------
     __syncthreads();
-    if (tid == 0) { __threadfence(); sh.last = (atomicAdd(&st->post_done, 1u) + 1u == nt) ? 1 : 0; }
+    if (tid == 0) sh.last = (atom_add_acq_rel_gpu(&st->post_done, 1u) + 1u == nt) ? 1 : 0;   // release my CTA's writes / acquire everybody's
     __syncthreads();
     if (!sh.last) return;
-    __threadfence();
     if (tid < FS3_SLOTS) { d.flagsg[tid] = 0; d.entCnt[tid] = 0u; }
     if (tid < 8) { d.bar[tid] = 0u; d.resflag[tid] = 0u; }
     if (tid < PF_MOM) {

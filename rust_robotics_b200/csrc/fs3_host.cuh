@@ -67,11 +67,13 @@ static int fs_create_impl(const pfgpu_fs_config* cfg, size_t n, size_t n_global,
 #define FS_TRY(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { snprintf(g_pfgpu_err, sizeof(g_pfgpu_err), "%s -> %s", #x, cudaGetErrorString(e__)); return fail(PFGPU_ERR_CUDA); } } while (0)
     // post kernel shape: <= 128 tiles (one CTA each, co-resident), NT threads x K values
     {
-        // up to 65 536 weights: 128 tiles of 256 threads x 2 (latency matters, not throughput); beyond that the per-value phases
-        // (classify, normalise, emit: ~100 instructions per value and sum) dominate, so every SM gets a tile of 512 threads
+        // below 65 536 weights: up to 128 tiles of 256 threads (latency matters, not throughput); at 65 536: 128 tiles of 512 threads,
+        // one value per thread (measured 1.3 % faster than 256 x 2; fewer, fatter tiles are slower: 64 x 512 x 2 -2 %, 32 x 512 x 4
+        // -13 %); beyond that the per-value phases (classify, normalise, emit: ~100 instructions per value and sum) dominate, so
+        // every SM gets a tile of 512 threads
         const char* env = getenv("PFGPU_POST_NT");
         const bool big = n_global > (size_t)128 * 256 * 2;
-        h->post_nt = env ? (atoi(env) == 512 ? 512 : 256) : (big ? 512 : 256);
+        h->post_nt = env ? (atoi(env) == 512 ? 512 : 256) : (n_global >= (size_t)128 * 512 ? 512 : 256);
         unsigned want = (unsigned)std::min<int>(big ? 148 : 128, h->ctx.num_sms);
         { const char* ew = getenv("PFGPU_POST_TILES"); if (ew && atoi(ew) >= 1 && atoi(ew) <= (int)want) want = (unsigned)atoi(ew); }   // tests: several values per thread at small n
         unsigned K = (unsigned)((n_global + (size_t)want * h->post_nt - 1) / ((size_t)want * h->post_nt));

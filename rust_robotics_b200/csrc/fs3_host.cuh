@@ -19,7 +19,8 @@ struct pfgpu_fs {
     Fs3Rec* h_rec = nullptr;          // pinned + mapped
     double* stage = nullptr; size_t stage_bytes = 0;   // device staging buffer for upload / download / seed_map
     bool pdl = true;
-    bool early = false;               // PFGPU_EARLY_LAUNCH=1: release the dependent kernel at the START of the previous grid (measured: 2 % slower)
+    bool early = false;               // PFGPU_EARLY_LAUNCH=1: release the dependent kernel at the START of the previous grid (measured: 2 % slower;
+                                      // releasing the next EKF launch when the post kernel's CTAs are through their phases: also 1.7 % slower)
     bool ekf_attr[2] = { false, false };
     int variant = 1;                  // 1 = FastSLAM 1.0 (fs1.rs), 2 = FastSLAM 2.0 (fs2.rs); pfgpu_fs_set_variant
     int ekf_helpers = 0;              // PFGPU_EKF_HELPERS: cap on the helper warps per CTA (0 = as many as fit, at most 3)

@@ -139,9 +139,10 @@ __device__ __forceinline__ void fs3_signal_peers(const Fs3Dev& d, int which, uns
 // One CTA per SM walks groups of 64 particles (two per lane).  Warps 0..k-1 each own one observation: per group they take the
 // group's landmark columns out of a cp.async landing buffer (issued one group ahead, so the HBM latency of the next group
 // hides behind the ~600 FP64 instructions of this one), run update_landmark for their two pairs, store the columns and
-// publish the two likelihood factors.  Warp k is the helper: it runs predict_particle one group AHEAD (Philox, Box-Muller,
-// sincos: a ~2 us dependent chain that would otherwise sit in front of every group) and the weight products of the group
-// BEHIND.  Hand-offs go through four double-buffered named barriers (pose full/empty, likelihoods full/empty).
+// publish the two likelihood factors.  Warps k.. (up to three) are helpers: helper h runs predict_particle for trips h, h + nh, ...
+// one trip AHEAD (sincos + the motion model on the N(0,1) pairs the previous post kernel's idle warps drew: a dependent chain
+// that would otherwise sit in front of every group) and the weight products of the same trips one trip BEHIND.  Hand-offs go
+// through shared-memory mbarriers, four per stage (pose full / empty, likelihoods full / empty), see below.
 __device__ __noinline__ double fs3_update_slow(FsLm* L, double px, double py, double pyaw, double z0, double z1, double r00, double r11, int variant) {
     int wrote;
     return fs_update_landmark_v(L, px, py, pyaw, z0, z1, r00, r11, &wrote, variant);   // 1.0 whenever the weight is left alone

@@ -67,11 +67,23 @@ pf3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Pf3Arg
     int gate = 1;
     double Q = 0.0, neff = 0.0;
     if (a.mode == 0) {
-        const double toffq = S > 0.0 ? fs3_div(fs3_div(qoff, S), S) : (double)((size_t)b * T) * unif * unif;
+        // Only the DECISION feeds back into the state.  Q is first taken from the tree-order tile sums of w_raw^2 (already in a.tsq):
+        // sum w_raw_i^2 / S^2 differs from the reference's sequential sum of fl(w_raw_i / S)^2 by at most (n + 64) 2^-51 relatively;
+        // only when N_eff lands that close to the threshold is the exact sequential sum evaluated (fs3_xsum over the squares).
+        double qa = (unsigned)tid < nt ? __ldcg(a.tsq + tid) : 0.0, dummy = 0.0;
         __syncthreads();
-        Q = fs3_xsum<NT>(d, sh, vals2, K, nt, toffq, 1, 1, a.m32, nullptr, 0, 0.0, 0.0, 0.0, 0.0);
+        fs3_block_sum2<NT>(qa, dummy, sh.red[0], sh.red[1]);
+        Q = S > 0.0 ? fs3_div(fs3_div(qa, S), S) : unif;           // uniform fallback: n * (1/n)^2
         neff = Q > 0.0 ? fs3_div(1.0, Q) : 0.0;
-        gate = neff < (double)pd.n_global * a.threshold ? 1 : 0;
+        const double thr = (double)pd.n_global * a.threshold;
+        const double slack = 16.0 * (double)(n + 64) * 2.220446049250313e-16;
+        if (!(fabs(neff - thr) > slack * fmax(fabs(thr), fabs(neff)))) {     // rare; the same decision in every CTA
+            const double toffq = S > 0.0 ? fs3_div(fs3_div(qoff, S), S) : (double)((size_t)b * T) * unif * unif;
+            __syncthreads();
+            Q = fs3_xsum<NT>(d, sh, vals2, K, nt, toffq, 1, 1, a.m32, nullptr, 0, 0.0, 0.0, 0.0, 0.0);
+            neff = Q > 0.0 ? fs3_div(1.0, Q) : 0.0;
+        }
+        gate = neff < thr ? 1 : 0;
     }
     double ctot = 0.0;
     if (gate) {

@@ -241,6 +241,22 @@ class _PfBase:
 
     step = try_step
 
+    # -- impl StateEstimator (traits.rs:31-52; pf.rs:552-573, mcl.rs:450-471) --
+    def predict(self, control, dt=None):
+        """`predict(&mut self, control, _dt)`: the dt argument is ignored, the filter steps with its configured dt (pf.rs:558-560)"""
+        self.try_predict_with_control(control)
+
+    def update(self, measurement):
+        """`update(&mut self, measurement)` = update_with_observations + resample (pf.rs:562-565)"""
+        self.try_update_with_observations(measurement)
+        self.resample()
+
+    def get_state(self):
+        return self.estimate()
+
+    def get_covariance(self):
+        return self.calc_covariance()
+
     def estimate(self):
         est = np.empty(4)
         _check(self.L, self.L.pfgpu_pf_estimate(self.h, _dp(est), None))

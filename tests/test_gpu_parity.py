@@ -659,8 +659,9 @@ def test_cpp_mirror_runs(tmp_path):
     pf = rr.ParticleFilterLocalizer.try_with_initial_state([5.0, 5.0, 0.0, 0.0], rr.ParticleFilterConfig(1000, 0.5, 0.25), seed=42)
     z = [(3.1, 2.0, 2.0), (5.0, 10.0, 2.0)]
     e1 = pf.try_step([1.1, 0.0], z)
-    pf.try_predict_with_control([0.5, 0.63]); pf.try_update_with_observations(z); pf.resample()
-    e2 = pf.estimate()
+    pf.predict([0.5, 0.63], 0.1); pf.update(z)                 # the StateEstimator route (pf.rs:552-573): update = update + resample
+    e2 = pf.get_state()
+    assert np.array_equal(pf.get_covariance(), pf.calc_covariance())
     fs = rr.FastSlam1(256, 4, seed=42)
     did = fs.fastslam_update([1.0, 0.1], [(5.0, 0.1, 0), (7.0, -0.4, 2)])
     bi, bp = fs.get_best_particle()

@@ -1017,7 +1017,11 @@ fs3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Fs3Obs
     if (S > 0.0) Q = fs3_div(fs3_div(Q, S), S);
     double neff = Q > 0.0 ? fs3_div(1.0, Q) : 0.0;
     const double slack = 16.0 * (double)(ng + 64) * 2.220446049250313e-16;
-    if (!(fabs(neff - nth) > slack * fmax(fabs(nth), fabs(neff)))) {     // rare; the same decision in every CTA
+    // The error bound of the shortcut assumes that no w_raw^2 that matters under- or overflows: with S inside [1e-120, 1e120] the
+    // squares of all weights within 1e-34 of the largest are normal numbers.  Outside (e.g. an outlier observation that drives
+    // EVERY likelihood to 1e-170: the normalised weights are perfectly ordinary, their raw squares are all zero) the exact sum decides.
+    const bool scale_ok = !(S > 0.0) || (S >= 1e-120 && S <= 1e120);
+    if (!scale_ok || !(fabs(neff - nth) > slack * fmax(fabs(nth), fabs(neff)))) {     // rare; the same decision in every CTA
         fs3_grid_sync<NT>(d, 6, nt);                           // wn_all is complete
         if (tid == 0) {
             double s = 0.0;

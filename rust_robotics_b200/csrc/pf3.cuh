@@ -77,7 +77,10 @@ pf3_post_kernel(const __grid_constant__ Fs3Dev d, const __grid_constant__ Pf3Arg
         neff = Q > 0.0 ? fs3_div(1.0, Q) : 0.0;
         const double thr = (double)pd.n_global * a.threshold;
         const double slack = 16.0 * (double)(n + 64) * 2.220446049250313e-16;
-        if (!(fabs(neff - thr) > slack * fmax(fabs(thr), fabs(neff)))) {     // rare; the same decision in every CTA
+        // (the bound assumes that no w_raw^2 that matters under- or overflows: S inside [1e-120, 1e120]; K likelihood factors of
+        //  1 / sqrt(2 pi sigma^2) each can leave that window in either direction)
+        const bool scale_ok = !(S > 0.0) || (S >= 1e-120 && S <= 1e120);
+        if (!scale_ok || !(fabs(neff - thr) > slack * fmax(fabs(thr), fabs(neff)))) {     // rare; the same decision in every CTA
             const double toffq = S > 0.0 ? fs3_div(fs3_div(qoff, S), S) : (double)((size_t)b * T) * unif * unif;
             __syncthreads();
             Q = fs3_xsum<NT>(d, sh, vals2, K, nt, toffq, 1, 1, a.m32, nullptr, 0, 0.0, 0.0, 0.0, 0.0);

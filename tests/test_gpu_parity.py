@@ -202,6 +202,18 @@ def test_pf_edge_cases(oracle):
     for t in range(8):
         g2.try_step(sc.controls[t], sc.obs[t]); o2.step(sc.controls[t], sc.obs[t])
     _pf_compare(g2, o2, "zero noise")
+    # every likelihood tiny but not zero (co-located particles ~7 m off the measured range: exp(-392) ~ 1e-170 each): the
+    # normalised weights are exactly uniform, so N_eff = n and nothing resamples — while the SQUARES of the raw weights all
+    # underflow, which is what the tree-order N_eff shortcut would have looked at (it must hand over to the exact sum here)
+    g3, o3 = _pf_pair(oracle, 400, thr=0.5, sigma=0.25, sv=0.0, sw=0.0)
+    same = np.tile([5.0, 5.0, 0.0, 0.0, 1.0 / 400], (400, 1))
+    g3.set_particles(same); o3.set_particles(same)
+    tiny = [[10.0 + 6.99, 15.0, 5.0]]                             # landmark 10 m away, range reading 16.99
+    ge = g3.try_step([0.0, 0.0], tiny); oe, did3 = o3.step([0.0, 0.0], tiny)
+    assert not did3 and g3.stats().resamples == 0
+    assert np.array_equal(g3.get_particles(), o3.particles()), "tiny uniform weights"     # (the covariance of 400 identical particles is
+    np.testing.assert_allclose(ge, oe, rtol=RTOL, atol=1e-9)                                # rounding noise on both sides: not compared)
+    assert np.allclose(g3.get_particles()[:, 4], 1.0 / 400, rtol=1e-12)      # (w_raw / S with a sequentially rounded S: uniform up to an ulp or two)
     # validation (pf.rs:515-549, 81-117)
     with pytest.raises(rr.InvalidParameter):
         g.try_step([np.nan, 0.0], far)
@@ -392,6 +404,14 @@ def test_fastslam_edge_cases(oracle):
     assert o.step([1.0, 0.1], z[:2]) == 1
     assert np.all(g.last_indices() == n - 1)
     _fs_compare(g, o, "zero weights")
+    # tiny uniform weights (1e-170 each, e.g. after an outlier observation): normalised they are 1/n, N_eff = n, no resample —
+    # but every raw square underflows, so the tree-order N_eff shortcut must hand over to the exact sum
+    p, l = g.state()
+    p[:, 0] = 1e-170
+    g.set_state(p, l); o.set_state(p, l)
+    assert g.fastslam_update([1.0, 0.1], []) is False and o.step([1.0, 0.1], []) == 0
+    _fs_compare(g, o, "tiny uniform weights")
+    assert g.last_neff() == pytest.approx(float(n), rel=1e-12)
     # mixed fresh (cov 1000) and initialised landmarks through upload
     p, l = g.state()
     l[:, 2, :] = [0.0, 0.0, 1000.0, 0.0, 0.0, 1000.0]
